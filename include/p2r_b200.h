@@ -1,0 +1,105 @@
+/*
+ * p2r_b200.h -- C ABI of libp2r_b200.so: the B200 (sm_100a) kernels behind the P2RNet hot path.
+ *
+ * Boundary rules
+ *   - plain C: raw DEVICE pointers, int sizes, an opaque `void* stream` (a cudaStream_t / CUstream;
+ *     NULL = legacy default stream).  No torch / ATen types.
+ *   - every tensor is contiguous, row-major, in the layout the reference operator uses; dtypes are
+ *     float32 / int32 / int64 / float64 / uint8 exactly as named below.
+ *   - every call is asynchronous on `stream` and performs no allocation and no host sync.
+ *   - return value: 0 on success, a positive cudaError_t value for a launch failure, -1 for a bad
+ *     argument.  p2r_last_error() returns a thread-local description.  (The reference calls
+ *     exit(-1) on a launch failure, _ext-src/include/cuda_utils.h:30-39.)
+ *   - outputs marked [zeroed by caller] are accumulated into with atomics, mirroring the
+ *     reference's torch::zeros allocation + atomicAdd kernels.
+ *
+ * Citations "ref:" are into /root/reference.
+ */
+#ifndef P2R_B200_H
+#define P2R_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------- */
+int p2r_abi_version(void);
+int p2r_compiled_arch(void); /* 100 */
+const char* p2r_last_error(void);
+int p2r_device_sm_count(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- the nine pointnet2_ops._ext operators --------------------------------------------------
+ * ref: external/pointnet2_ops_lib/pointnet2_ops/_ext-src/src/bindings.cpp:6-19 (pybind names),
+ *      sampling.cpp:15-87, ball_query.cpp:8-32, group_points.cpp:12-62, interpolate.cpp:14-99.     */
+
+/* furthest_point_sampling(points f32[B,N,3], nsamples) -> i32[B,nsamples]   (sampling.cpp:66-87)
+ * scratch: b*n floats, only read when n > 32768 (may be NULL otherwise).                          */
+int p2r_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idxs, float* scratch, void* stream);
+
+/* gather_points(points f32[B,C,N], idx i32[B,M]) -> f32[B,C,M]              (sampling.cpp:15-38)  */
+int p2r_gather_points(const float* points, const int* idx, int b, int c, int n, int m, float* out, void* stream);
+
+/* gather_points_grad(grad_out f32[B,C,M], idx, N) -> f32[B,C,N] [zeroed by caller] (sampling.cpp:40-64) */
+int p2r_gather_points_grad(const float* grad_out, const int* idx, int b, int c, int n, int m, float* grad_points,
+                           void* stream);
+
+/* ball_query(new_xyz f32[B,M,3], xyz f32[B,N,3], radius, nsample) -> i32[B,M,nsample]
+ * (ball_query.cpp:8-32; every slot is written, no pre-zeroing needed)                             */
+int p2r_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius, int nsample, int* idx,
+                   void* stream);
+
+/* group_points(points f32[B,C,N], idx i32[B,P,S]) -> f32[B,C,P,S]           (group_points.cpp:12-36) */
+int p2r_group_points(const float* points, const int* idx, int b, int c, int n, int npoints, int nsample, float* out,
+                     void* stream);
+
+/* group_points_grad(grad_out f32[B,C,P,S], idx, N) -> f32[B,C,N] [zeroed by caller] (group_points.cpp:38-62) */
+int p2r_group_points_grad(const float* grad_out, const int* idx, int b, int c, int n, int npoints, int nsample,
+                          float* grad_points, void* stream);
+
+/* three_nn(unknown f32[B,n,3], known f32[B,m,3]) -> (dist2 f32[B,n,3], idx i32[B,n,3])  (interpolate.cpp:14-40)
+ * dist2 is the SQUARED distance, like the reference's native op (Python takes the sqrt).         */
+int p2r_three_nn(const float* unknown, const float* known, int b, int n, int m, float* dist2, int* idx, void* stream);
+
+/* three_interpolate(points f32[B,C,m], idx i32[B,n,3], weight f32[B,n,3]) -> f32[B,C,n] (interpolate.cpp:42-70) */
+int p2r_three_interpolate(const float* points, const int* idx, const float* weight, int b, int c, int m, int n,
+                          float* out, void* stream);
+
+/* three_interpolate_grad(grad_out f32[B,C,n], idx, weight, m) -> f32[B,C,m] [zeroed by caller] (interpolate.cpp:71-99) */
+int p2r_three_interpolate_grad(const float* grad_out, const int* idx, const float* weight, int b, int c, int n, int m,
+                               float* grad_points, void* stream);
+
+/* ---- graph stage (ref: net_utils/vn_dgcnn_util.py) ----------------------------------------- */
+/* knn(x f32[B,C,N], k) -> i64[B,N,k]                                         (vn_dgcnn_util.py:4-10) */
+int p2r_knn_graph(const float* x, int b, int c, int n, int k, long long* idx, void* stream);
+/* get_graph_offset(x f32[B,3d,N], idx i64[B,N,k]) -> f32[B,N,k,d,3] = x[idx]-x  (vn_dgcnn_util.py:70-95) */
+int p2r_graph_offset(const float* x, const long long* idx, int b, int d3, int n, int k, float* out, void* stream);
+
+/* ---- losses (ref: net_utils/nn_distance.py:34-61) ------------------------------------------ */
+/* mode 0 = squared L2, 1 = L1 (l1=True), 2 = smooth-L1 (l1smooth=True, delta).                    */
+int p2r_nn_distance(const float* pc1, const float* pc2, int b, int n, int m, int c, int mode, float delta,
+                    float* dist1, long long* idx1, float* dist2, long long* idx2, void* stream);
+/* backward of the above; g1 f32[B,N] / g2 f32[B,M] may be NULL; grads [zeroed by caller].        */
+int p2r_nn_distance_grad(const float* pc1, const float* pc2, const long long* idx1, const long long* idx2,
+                         const float* g1, const float* g2, int b, int n, int m, int c, int mode, float delta,
+                         float* grad_pc1, float* grad_pc2, void* stream);
+
+/* ---- eval post-processing (ref: net_utils/ap_helper.py:133-255, nms.py, box_util.py) -------- */
+/* decode: center f32[B,K,3], log_size f32[B,K,3], heading (sin,cos) f64[B,K,2], hip f32 with
+ * `hip_stride` floats between frames and T*hip_stride between scenes ->
+ * corners f64[B,K,8,3] (utils/tools.py:33-51 order), aabb f64[B,K,6] (min xyz, max xyz),
+ * nonempty u8[B,K] (size in [0.01,10] and some hip point inside the box enlarged by `contact`).  */
+int p2r_decode_boxes(const float* center, const float* log_size, const double* heading_sincos, const float* hip,
+                     int hip_stride, int b, int k, int t, double contact, double* corners, double* aabb,
+                     unsigned char* nonempty, void* stream);
+/* nms_3d_faster / nms_3d_faster_samecls (nms.py:41-119): boxes f64[B,K,6], score f64[B,K],
+ * valid u8[B,K] or NULL, cls i32[B,K] or NULL -> keep u8[B,K], order i32[B,K] (-1 padded).        */
+int p2r_nms3d(const double* boxes, const double* score, const unsigned char* valid, const int* cls, int b, int k,
+              double thr, int old_type, unsigned char* keep, int* order, void* stream);
+/* box3d_iou (box_util.py:90-118) for every pair: c1 f64[P,8,3], c2 f64[G,8,3] -> f64[P,G] x2.    */
+int p2r_box3d_iou(const double* corners1, const double* corners2, int np_, int ng, double* iou3d, double* iou2d,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2R_B200_H */

@@ -1,0 +1,67 @@
+"""ctypes binding of libp2r_b200.so (the C ABI in include/p2r_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+PyTorch is used by the callers for device memory and streams only.
+"""
+import ctypes
+import os.path as osp
+
+_HERE = osp.dirname(osp.abspath(__file__))
+LIB_PATH = osp.join(_HERE, "lib", "libp2r_b200.so")
+
+_c_int, _c_float, _c_double, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "p2r_abi_version": [],
+    "p2r_compiled_arch": [],
+    "p2r_last_error": [],
+    "p2r_device_sm_count": [_c_int, _vp, _vp, _vp],
+    "p2r_furthest_point_sampling": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp],
+    "p2r_gather_points": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_gather_points_grad": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_ball_query": [_vp, _vp, _c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp],
+    "p2r_group_points": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_group_points_grad": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_three_nn": [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp],
+    "p2r_three_interpolate": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_three_interpolate_grad": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_knn_graph": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_graph_offset": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_nn_distance": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp, _vp, _vp, _vp, _vp],
+    "p2r_nn_distance_grad": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
+                             _vp, _vp, _vp],
+    "p2r_decode_boxes": [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_double, _vp, _vp, _vp, _vp],
+    "p2r_nms3d": [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_double, _c_int, _vp, _vp, _vp],
+    "p2r_box3d_iou": [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp],
+}
+_RESTYPES = {"p2r_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load the library once; raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not osp.exists(LIB_PATH):
+        raise RuntimeError(
+            "pose2room_b200: %s is missing -- build it with `python -m pose2room_b200.build` "
+            "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, _c_int)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an entry point and turn a non-zero status into a RuntimeError."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("pose2room_b200.%s failed (%d): %s" % (name, rc, lib.p2r_last_error().decode()))
+    return rc

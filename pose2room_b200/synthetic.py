@@ -1,0 +1,97 @@
+"""Seeded synthetic pose sequences + ground truth in the reference's `data` dict schema.
+
+Host-side data plumbing (numpy, no kernels).  Schema = what `P2RNet_VirtualHome.__getitem__`
+collates (/root/reference/models/p2rnet/dataloader.py:137-146): input_joints f32 (B,T,J,3),
+box_label_mask f32 (B,10), sem_cls_label i64 (B,10), center_label f32 (B,10,3), size f32 (B,10,3)
+= log size, heading f32 (B,10,2) = (sin, cos), vote_label f32 (B,T,J,9), vote_label_mask i64 (B,T,J).
+
+Generator follows SURVEY.md section 8(d): hip = cumulative N(0, 0.05^2) steps with y clamped to
+[0.8, 1.0]; other joints = hip + N(0, 0.3^2), joint 0 = hip; 1..10 GT boxes per scene with centres
+= hip at random frames + N(0, 0.3^2), size ~ U(0.2, 1.7), heading ~ U(-pi, pi), class ~ U{0..21};
+votes = (centre - joint) of the first <=3 boxes whose OBB enlarged by 1.0 m contains the joint, the
+first vote replicated into unused slots (schema of utils/virtualhome/3_generate_samples.py:56-79).
+"""
+import numpy as np
+
+MAX_GT = 10
+NUM_CLASS = 22
+CONTACT = 1.0
+
+
+def _rot(theta):
+    c, s = np.cos(theta), np.sin(theta)
+    return np.array([[c, 0.0, -s], [0.0, 1.0, 0.0], [s, 0.0, c]])
+
+
+def make_scene(rng, T, J):
+    steps = rng.normal(0.0, 0.05, size=(T, 3))
+    hip = np.cumsum(steps, axis=0)
+    hip[:, 1] = np.clip(0.9 + hip[:, 1], 0.8, 1.0)
+    joints = hip[:, None, :] + rng.normal(0.0, 0.3, size=(T, J, 3))
+    joints[:, 0] = hip
+
+    n_gt = int(rng.integers(1, MAX_GT + 1))
+    frames = rng.integers(0, T, size=n_gt)
+    centers = hip[frames] + rng.normal(0.0, 0.3, size=(n_gt, 3))
+    sizes = rng.uniform(0.2, 1.7, size=(n_gt, 3))
+    theta = rng.uniform(-np.pi, np.pi, size=n_gt)
+    classes = rng.integers(0, NUM_CLASS, size=n_gt)
+
+    votes = np.zeros((T, J, 9))
+    mask = np.zeros((T, J), np.int64)
+    slot = np.zeros((T, J), np.int64)
+    flat = joints.reshape(-1, 3)
+    for g in range(n_gt):
+        local = (flat - centers[g]) @ _rot(theta[g]).T
+        inside = np.all(np.abs(local) <= sizes[g] / 2.0 + CONTACT, axis=1).reshape(T, J)
+        v = centers[g][None, None, :] - joints
+        tt, jj = np.nonzero(inside)
+        for t, j in zip(tt, jj):
+            s = slot[t, j]
+            votes[t, j, 3 * s:3 * s + 3] = v[t, j]
+            if s == 0:
+                votes[t, j, 3:6] = v[t, j]
+                votes[t, j, 6:9] = v[t, j]
+        mask[inside] = 1
+        slot[inside] = np.minimum(2, slot[inside] + 1)
+
+    out = dict(
+        input_joints=joints.astype(np.float32),
+        box_label_mask=np.zeros(MAX_GT, np.float32),
+        sem_cls_label=np.zeros(MAX_GT, np.int64),
+        center_label=np.zeros((MAX_GT, 3), np.float32),
+        size=np.zeros((MAX_GT, 3), np.float32),
+        heading=np.zeros((MAX_GT, 2), np.float32),
+        vote_label=votes.astype(np.float32),
+        vote_label_mask=mask,
+    )
+    out["box_label_mask"][:n_gt] = 1
+    out["sem_cls_label"][:n_gt] = classes
+    out["center_label"][:n_gt] = centers
+    out["size"][:n_gt] = np.log(sizes)
+    out["heading"][:n_gt, 0] = np.sin(theta)
+    out["heading"][:n_gt, 1] = np.cos(theta)
+    return out
+
+
+def make_batch(B, T, J, seed=1234, as_torch=True, pin=False):
+    """A collated batch of B scenes.  seed = 1234 + rank by convention."""
+    rng = np.random.default_rng(seed)
+    scenes = [make_scene(rng, T, J) for _ in range(B)]
+    batch = {k: np.stack([s[k] for s in scenes]) for k in scenes[0]}
+    batch["sample_idx"] = ["synthetic_%d_%d" % (seed, i) for i in range(B)]
+    if as_torch:
+        import torch
+        for k, v in list(batch.items()):
+            if isinstance(v, np.ndarray):
+                t = torch.from_numpy(v)
+                batch[k] = t.pin_memory() if pin else t
+    return batch
+
+
+def make_cloud(B, N, seed=0, extent=2.0):
+    """Microbench point clouds (B,N,3) f32: a random walk blurred by N(0,0.3^2), like T*J joints."""
+    rng = np.random.default_rng(seed)
+    walk = np.cumsum(rng.normal(0.0, 0.05, size=(B, N, 3)), axis=1)
+    pts = walk + rng.normal(0.0, 0.3, size=(B, N, 3))
+    return np.clip(pts, -extent * 4, extent * 4).astype(np.float32)
