@@ -186,8 +186,11 @@ def test_python_operator_api_vs_reference_goldens(cuda, golden_pointnet2):
     assert np.array_equal(new_xyz.cpu().numpy(), g["new_xyz"])
     grouper = pu.QueryAndGroup(0.4, S, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
     nf, gx = grouper(xyz, new_xyz, feats)
-    assert np.array_equal(nf.detach().cpu().numpy(), g["qg_features"])
-    assert np.array_equal(gx.detach().cpu().numpy(), g["qg_xyz"])
+    # grouped features: pure gather -> exact.  grouped xyz: torch's CUDA `x /= radius` multiplies by the
+    # reciprocal (torch glue, identical in the reference on GPU) -> 1 ulp from the CPU-generated golden.
+    assert np.array_equal(nf.detach().cpu().numpy()[:, 3:], g["qg_features"][:, 3:])
+    assert np.allclose(nf.detach().cpu().numpy()[:, :3], g["qg_features"][:, :3], rtol=0, atol=2e-7)
+    assert np.allclose(gx.detach().cpu().numpy(), g["qg_xyz"], rtol=0, atol=2e-7)
     (nf * torch.from_numpy(g["qg_w"]).to(cuda)).sum().backward()
     assert np.allclose(feats.grad.cpu().numpy(), g["qg_feats_grad"], rtol=1e-5, atol=1e-6)
     dist, idx = pu.three_nn(xyz, new_xyz)
