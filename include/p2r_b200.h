@@ -74,6 +74,10 @@ int p2r_knn_graph(const float* x, int b, int c, int n, int k, long long* idx, vo
 /* get_graph_offset(x f32[B,3d,N], idx i64[B,N,k]) -> f32[B,N,k,d,3] = x[idx]-x  (vn_dgcnn_util.py:70-95) */
 int p2r_graph_offset(const float* x, const long long* idx, int b, int d3, int n, int k, float* out, void* stream);
 
+/* 'uniform' seed sampling of STGCN.forward (ref: models/p2rnet/modules/stgcn.py:96-101): hip f32 with `stride`
+ * floats between frames (T*stride between sequences) -> seed_inds i64[B,S]                              */
+int p2r_uniform_seed_inds(const float* hip, int stride, int b, int t, int s, long long* seed_inds, void* stream);
+
 /* ---- losses (ref: net_utils/nn_distance.py:34-61) ------------------------------------------ */
 /* mode 0 = squared L2, 1 = L1 (l1=True), 2 = smooth-L1 (l1smooth=True, delta).                    */
 int p2r_nn_distance(const float* pc1, const float* pc2, int b, int n, int m, int c, int mode, float delta,
@@ -98,6 +102,48 @@ int p2r_nms3d(const double* boxes, const double* score, const unsigned char* val
 /* box3d_iou (box_util.py:90-118) for every pair: c1 f64[P,8,3], c2 f64[G,8,3] -> f64[P,G] x2.    */
 int p2r_box3d_iou(const double* corners1, const double* corners2, int np_, int ng, double* iou3d, double* iou2d,
                   void* stream);
+
+/* ---- dense per-point layers, channel-last (rows = points, columns = channels) -----------------
+ * dtype codes: 0 = float32, 1 = bfloat16 (storage; arithmetic is fp32, BN column sums are fp64).
+ * Replace the cuDNN/cuBLAS calls behind the reference's 1x1 Conv / BatchNorm / ReLU stacks:
+ * ref: models/p2rnet/modules/sub_modules.py:88-113 (SingleConv 'cbr'), stgcn.py:45-67,
+ *      stgcn_layers.py:50-67,402-414, vote_center.py:28-32, proposal_net.py:63-94,
+ *      pointnet2_modules.py:9-19,243-247.                                                          */
+
+/* C[M,N] (+)= op(A).op(B) (+bias[N]) (ReLU).  trans_a: A stored [K,M]; trans_b: B stored [N,K]
+ * (the nn.Linear / 1x1-conv weight layout).  splits > 1: split-K, fp32 atomics into zeroed C.      */
+int p2r_sgemm(int M, int N, int K, const void* A, int lda, int trans_a, int a_dtype, const void* B, int ldb,
+              int trans_b, int b_dtype, void* C, int ldc, int c_dtype, const float* bias, int relu, int accumulate,
+              int splits, void* stream);
+/* column sums of x[M,C]: s1 = sum x, s2 = sum x^2 (f64[C], zeroed by caller)                       */
+int p2r_col_stats(const void* x, int dtype, long long M, int C, double* s1, double* s2, void* stream);
+/* backward column sums: dz = relu ? dy*(y>0) : dy; s1 = sum dz, s2 = sum dz*(x-mean)*rstd (s2/x may be NULL) */
+int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
+                      const float* rstd, int relu, double* s1, double* s2, void* stream);
+/* training-mode BatchNorm statistics -> mean, rstd, fused scale/shift; updates running stats like torch */
+int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                    float* scale, float* shift, void* stream);
+/* y = x*scale[c] + shift[c] (+residual) (ReLU)                                                     */
+int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift,
+                   const void* residual, int relu, void* y, void* stream);
+/* BN(+ReLU)(+residual) backward, elementwise part (s1 == NULL: eval-mode BN)                       */
+int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
+                     const float* rstd, const float* scale, const double* s1, const double* s2, int relu, void* dx,
+                     void* dres, void* stream);
+/* dz = dy * (y > 0)                                                                                */
+int p2r_relu_bwd(const void* dy, const void* y, int dtype, long long total, void* dz, void* stream);
+/* (KT x 1) temporal conv as GEMM: x[B,T,V,C] -> col[B*T*V, KT*C] (zero padded), and its adjoint    */
+int p2r_temporal_unfold(const void* x, int dtype, int B, int Tn, int V, int C, int KT, void* col, void* stream);
+int p2r_temporal_fold(const void* dcol, int dtype, int B, int Tn, int V, int C, int KT, void* dx, void* stream);
+/* channel-last grouping + max-pool of the SA layer (ref: pointnet2_utils.py:319-346, pointnet2_modules.py:243-247) */
+int p2r_group_rows(const void* feats, int dtype, const int* idx, int B, int N, int C, int P, int S, void* out,
+                   void* stream);
+int p2r_group_rows_grad(const void* grad, int dtype, const int* idx, int B, int N, int C, int P, int S, float* dfeats,
+                        void* stream);
+int p2r_maxpool_rows(const void* x, int dtype, long long R, int S, int C, void* out, unsigned char* arg, void* stream);
+int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg, long long R, int S, int C, void* dx,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ _HERE = osp.dirname(osp.abspath(__file__))
 LIB_PATH = osp.join(_HERE, "lib", "libp2r_b200.so")
 
 _c_int, _c_float, _c_double, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+_c_ll = ctypes.c_longlong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -28,12 +29,27 @@ SIGNATURES = {
     "p2r_three_interpolate_grad": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_knn_graph": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_graph_offset": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_uniform_seed_inds": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_nn_distance": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp, _vp, _vp, _vp, _vp],
     "p2r_nn_distance_grad": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                              _vp, _vp, _vp],
     "p2r_decode_boxes": [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_double, _vp, _vp, _vp, _vp],
     "p2r_nms3d": [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_double, _c_int, _vp, _vp, _vp],
     "p2r_box3d_iou": [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp],
+    "p2r_sgemm": [_c_int, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int,
+                  _c_int, _vp, _c_int, _c_int, _c_int, _vp],
+    "p2r_col_stats": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp],
+    "p2r_col_bwd_stats": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp],
+    "p2r_bn_finalize": [_c_int, _c_ll, _vp, _vp, _vp, _vp, _c_float, _c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "p2r_affine_act": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp],
+    "p2r_bn_bwd_apply": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp],
+    "p2r_relu_bwd": [_vp, _vp, _c_int, _c_ll, _vp, _vp],
+    "p2r_temporal_unfold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_temporal_fold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_group_rows": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_group_rows_grad": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_maxpool_rows": [_vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp, _vp],
+    "p2r_maxpool_rows_grad": [_vp, _c_int, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
 }
 _RESTYPES = {"p2r_last_error": ctypes.c_char_p}
 

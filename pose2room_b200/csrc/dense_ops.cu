@@ -1,0 +1,544 @@
+// dense_ops.cu -- per-point dense layers of the P2RNet hot path in CHANNEL-LAST layout
+// (rows = points / frames, columns = channels), so that every 1x1 conv of the reference
+// (models/p2rnet/modules/stgcn.py:45-67, stgcn_layers.py:50-56,402-414, vote_center.py:28-32,
+//  proposal_net.py:78-94, pointnet2_modules.py:9-19) is a row-major GEMM and every BatchNorm is a
+// column statistic.  This file holds the fp32-exact SIMT GEMM (parity mode, and the small-K layers of
+// the bf16 mode), the training-mode BatchNorm forward/backward, the temporal unfold/fold, the
+// channel-last grouping + max-pool of the set-abstraction layer, and small fused elementwise pieces.
+// The bf16 tensor-core GEMM (tcgen05 + TMA) lives in gemm_sm100.cu.
+//
+// Storage type T is float or __nv_bfloat16; arithmetic is always fp32 (double for BN column sums).
+#include "p2r_common.cuh"
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// ================================================================================================
+// SIMT GEMM:  C[M,N] (+)= op(A)[M,K] . op(B)[K,N]  (+ bias[N]) (ReLU)
+//   TRANS_A = false: A is [M,K] row-major (lda);  true: A is [K,M] row-major (lda)
+//   TRANS_B = true : B is [N,K] row-major (ldb) -- the nn.Linear / 1x1-conv weight layout;
+//             false: B is [K,N] row-major (ldb)
+//   gridDim.z > 1 = split-K with fp32 atomicAdd into a zero-filled C (TC must be float, no epilogue).
+// 64x64 tile, 16-deep k slab, 256 threads, 4x4 micro-tile; fixed summation order along K inside a
+// split => deterministic when gridDim.z == 1.
+// ================================================================================================
+#define SG_BM 64
+#define SG_BN 64
+#define SG_BK 16
+template <typename TA, typename TB, typename TC, bool TRANS_A, bool TRANS_B>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const TA* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
+             TC* __restrict__ C, int ldc, const float* __restrict__ bias, int relu, int accumulate, int k_per_split) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Bs[SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4 (m) x 4 (n)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += SG_BK) {
+    // ---- stage A tile: As[k][m]
+#pragma unroll
+    for (int e = tid; e < SG_BM * SG_BK; e += 256) {
+      int m, k;
+      if (!TRANS_A) { m = e / SG_BK; k = e % SG_BK; }   // k fastest: coalesced along a row of A
+      else          { k = e / SG_BM; m = e % SG_BM; }   // m fastest: coalesced along a row of A^T storage
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = TRANS_A ? ldf<TA>(A + (size_t)gk * lda + gm) : ldf<TA>(A + (size_t)gm * lda + gk);
+      As[k][m] = v;
+    }
+    // ---- stage B tile: Bs[k][n]
+#pragma unroll
+    for (int e = tid; e < SG_BN * SG_BK; e += 256) {
+      int n, k;
+      if (TRANS_B) { n = e / SG_BK; k = e % SG_BK; }
+      else         { k = e / SG_BN; n = e % SG_BN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = TRANS_B ? ldf<TB>(B + (size_t)gn * ldb + gk) : ldf<TB>(B + (size_t)gk * ldb + gn);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (gridDim.z > 1) {
+        atomicAdd(reinterpret_cast<float*>(C) + (size_t)gm * ldc + gn, v);
+      } else {
+        if (bias) v += __ldg(bias + gn);
+        if (accumulate) v += ldf<TC>(C + (size_t)gm * ldc + gn);
+        if (relu) v = fmaxf(v, 0.f);
+        stf<TC>(C + (size_t)gm * ldc + gn, v);
+      }
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TC>
+static int launch_sgemm(int M, int N, int K, const void* A, int lda, int trans_a, const void* B, int ldb, int trans_b,
+                        void* C, int ldc, const float* bias, int relu, int accumulate, int splits, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  int kps = K;
+  if (splits > 1) {
+    kps = ((K + splits - 1) / splits + SG_BK - 1) / SG_BK * SG_BK;
+    splits = (K + kps - 1) / kps;
+  } else splits = 1;
+  dim3 grid(p2r_ceil_div(N, SG_BN), p2r_ceil_div(M, SG_BM), splits);
+#define SG_LAUNCH(TA_, TB_)                                                                                   \
+  sgemm_kernel<TA, TB, TC, TA_, TB_><<<grid, 256, 0, st>>>(M, N, K, (const TA*)A, lda, (const TB*)B, ldb,    \
+                                                            (TC*)C, ldc, bias, relu, accumulate, kps)
+  if (!trans_a && trans_b) SG_LAUNCH(false, true);
+  else if (!trans_a && !trans_b) SG_LAUNCH(false, false);
+  else if (trans_a && !trans_b) SG_LAUNCH(true, false);
+  else SG_LAUNCH(true, true);
+#undef SG_LAUNCH
+  P2R_RETURN_LAUNCH("p2r_sgemm");
+}
+
+// dtype codes: 0 = float32, 1 = bfloat16
+extern "C" int p2r_sgemm(int M, int N, int K, const void* A, int lda, int trans_a, int a_dtype, const void* B, int ldb,
+                         int trans_b, int b_dtype, void* C, int ldc, int c_dtype, const float* bias, int relu,
+                         int accumulate, int splits, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "p2r_sgemm");
+  P2R_CHECK_ARG(!(splits > 1 && (c_dtype != 0 || bias || relu)), "p2r_sgemm (split-K needs fp32 C and no epilogue)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int code = a_dtype * 4 + b_dtype * 2 + c_dtype;
+  switch (code) {
+    case 0: return launch_sgemm<float, float, float>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    case 1: return launch_sgemm<float, float, __nv_bfloat16>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    case 2: return launch_sgemm<float, __nv_bfloat16, float>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    case 3: return launch_sgemm<float, __nv_bfloat16, __nv_bfloat16>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    case 4: return launch_sgemm<__nv_bfloat16, float, float>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    case 5: return launch_sgemm<__nv_bfloat16, float, __nv_bfloat16>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    case 6: return launch_sgemm<__nv_bfloat16, __nv_bfloat16, float>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+    default: return launch_sgemm<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate, splits, st);
+  }
+}
+
+// ================================================================================================
+// column reductions over rows of a [M,C] matrix (BatchNorm statistics, bias gradients)
+//   mode 0: s1 = sum x,            s2 = sum x*x
+//   mode 1: s1 = sum dz,           s2 = sum dz * (x - mean) * rstd      dz = dy * (y > 0) if relu else dy
+// Thread layout: 256 threads = RL row lanes x CP channels (CP = min(C,256), C | 256 or 256 | C).
+// Per-thread fp32 partials over <= 64 rows, then double atomics into s1/s2 (zero-filled by caller).
+// ================================================================================================
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_kernel(long long M, int C, const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int rows_per_cta,
+                 double* __restrict__ s1, double* __restrict__ s2) {
+  __shared__ float sh1[256], sh2[256];
+  const int cp = C < 256 ? C : 256;
+  const int rl = 256 / cp;
+  const int cl = threadIdx.x % cp, r_lane = threadIdx.x / cp;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(M, r0 + rows_per_cta);
+  for (int cbase = 0; cbase < C; cbase += cp) {
+    const int c = cbase + cl;
+    float a1 = 0.f, a2 = 0.f;
+    float mu = 0.f, rs = 1.f;
+    if (MODE == 1) { mu = __ldg(mean + c); rs = __ldg(rstd + c); }
+    for (long long r = r0 + r_lane; r < r1; r += rl) {
+      const size_t o = (size_t)r * C + c;
+      if (MODE == 0) {
+        const float v = ldf<T>(x + o);
+        a1 += v;
+        a2 = fmaf(v, v, a2);
+      } else {
+        float dz = ldf<T>(dy + o);
+        if (relu && !(ldf<T>(y + o) > 0.f)) dz = 0.f;
+        a1 += dz;
+        if (x) a2 = fmaf(dz, (ldf<T>(x + o) - mu) * rs, a2);
+      }
+    }
+    sh1[threadIdx.x] = a1;
+    sh2[threadIdx.x] = a2;
+    __syncthreads();
+    if (r_lane == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int l = 0; l < rl; ++l) { t1 += (double)sh1[l * cp + cl]; t2 += (double)sh2[l * cp + cl]; }
+      atomicAdd(s1 + c, t1);
+      if (s2) atomicAdd(s2 + c, t2);
+    }
+    __syncthreads();
+  }
+}
+
+static int colreduce_grid(long long M, int* rows_per_cta) {
+  // ~4 CTAs per SM, at least 64 rows each
+  long long target = (M + (long long)P2R_SM_COUNT * 4 - 1) / ((long long)P2R_SM_COUNT * 4);
+  if (target < 64) target = 64;
+  *rows_per_cta = (int)target;
+  return (int)((M + target - 1) / target);
+}
+
+// sum / sum-of-squares per column. s1, s2: double[C], zero-filled by the caller.
+extern "C" int p2r_col_stats(const void* x, int dtype, long long M, int C, double* s1, double* s2, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && C > 0 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "p2r_col_stats");
+  if (M == 0) return 0;
+  int rpc;
+  const int grid = colreduce_grid(M, &rpc);
+  if (dtype == 0)
+    colreduce_kernel<float, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+  else
+    colreduce_kernel<__nv_bfloat16, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+  P2R_RETURN_LAUNCH("p2r_col_stats");
+}
+
+// backward column sums: s1 = sum dz, s2 = sum dz*xhat (s2/x/mean/rstd may be NULL -> only s1, e.g. a bias grad)
+extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
+                                 const float* mean, const float* rstd, int relu, double* s1, double* s2, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && C > 0 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "p2r_col_bwd_stats");
+  P2R_CHECK_ARG(!(relu && y == nullptr), "p2r_col_bwd_stats (relu needs y)");
+  if (M == 0) return 0;
+  int rpc;
+  const int grid = colreduce_grid(M, &rpc);
+  if (dtype == 0)
+    colreduce_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2);
+  else
+    colreduce_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2);
+  P2R_RETURN_LAUNCH("p2r_col_bwd_stats");
+}
+
+// BatchNorm finalize (training): mean/var from the column sums, running-stat update exactly like
+// torch.nn.BatchNorm (momentum, unbiased variance for the running estimate), fused affine scale/shift.
+__global__ void bn_finalize_kernel(int C, double inv_m, double unbias, const double* __restrict__ s1,
+                                   const double* __restrict__ s2, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = s1[c] * inv_m;
+  double var = s2[c] * inv_m - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float rs = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  rstd[c] = rs;
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  scale[c] = g * rs;
+  shift[c] = bt - (float)mu * g * rs;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
+  }
+}
+
+extern "C" int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  P2R_CHECK_ARG(C > 0 && M > 0, "p2r_bn_finalize");
+  const double unbias = M > 1 ? (double)M / (double)(M - 1) : 1.0;
+  bn_finalize_kernel<<<p2r_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, 1.0 / (double)M, unbias, s1, s2, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
+  P2R_RETURN_LAUNCH("p2r_bn_finalize");
+}
+
+// y = x*scale[c] + shift[c] (+ residual) (ReLU).  Vectorised over 4 channels when C % 4 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_act_kernel(long long total, int C, const T* __restrict__ x, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const T* __restrict__ residual, int relu, T* __restrict__ y) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    float v = fmaf(ldf<T>(x + e), __ldg(scale + c), __ldg(shift + c));
+    if (residual) v += ldf<T>(residual + e);
+    if (relu) v = fmaxf(v, 0.f);
+    stf<T>(y + e, v);
+  }
+}
+
+extern "C" int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift,
+                              const void* residual, int relu, void* y, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_affine_act");
+  const long long total = M * C;
+  if (total == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
+  if (dtype == 0)
+    affine_act_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
+  else
+    affine_act_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, (const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y);
+  P2R_RETURN_LAUNCH("p2r_affine_act");
+}
+
+// BatchNorm(+ReLU)(+residual) backward, elementwise part:
+//   dz = relu ? dy * (y > 0) : dy
+//   training: dx = scale[c] * (dz - s1[c]/M - xhat * s2[c]/M)      eval (s1 == NULL): dx = scale[c] * dz
+//   dres (optional) = dz
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(long long total, int C, double inv_m, const T* __restrict__ dy, const T* __restrict__ x,
+                    const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
+                    int relu, T* __restrict__ dx, T* __restrict__ dres) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    float dz = ldf<T>(dy + e);
+    if (relu && !(ldf<T>(y + e) > 0.f)) dz = 0.f;
+    if (dres) stf<T>(dres + e, dz);
+    float g = dz;
+    if (s1) {
+      const float xh = (ldf<T>(x + e) - __ldg(mean + c)) * __ldg(rstd + c);
+      g = dz - (float)(s1[c] * inv_m) - xh * (float)(s2[c] * inv_m);
+    }
+    stf<T>(dx + e, g * __ldg(scale + c));
+  }
+}
+
+extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
+                                const float* mean, const float* rstd, const float* scale, const double* s1,
+                                const double* s2, int relu, void* dx, void* dres, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_bn_bwd_apply");
+  const long long total = M * C;
+  if (total == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
+  if (dtype == 0)
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres);
+  else
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
+  P2R_RETURN_LAUNCH("p2r_bn_bwd_apply");
+}
+
+// dz = dy * (y > 0)   (backward of a ReLU fused into a GEMM epilogue)
+template <typename T>
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(long long total, const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    stf<T>(dz + e, ldf<T>(y + e) > 0.f ? ldf<T>(dy + e) : 0.f);
+}
+
+extern "C" int p2r_relu_bwd(const void* dy, const void* y, int dtype, long long total, void* dz, void* stream) {
+  if (total <= 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
+  if (dtype == 0)
+    relu_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, (const float*)dy, (const float*)y, (float*)dz);
+  else
+    relu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dz);
+  P2R_RETURN_LAUNCH("p2r_relu_bwd");
+}
+
+// ================================================================================================
+// temporal unfold / fold for the (3x1) temporal convolution (stgcn_layers.py:405-411, padding 1):
+//   x [B,T,V,C] -> col [B*T*V, KT*C], col[(b,t,v), dt*C + c] = x[b, t+dt-pad, v, c] or 0 outside [0,T)
+//   fold is the adjoint (gather form, no atomics): dx[b,t,v,c] = sum_dt dcol[(b,t-dt+pad,v), dt*C+c]
+// ================================================================================================
+template <typename T, bool FOLD>
+__global__ void __launch_bounds__(256)
+temporal_unfold_kernel(int Tn, int V, int C, int KT, long long total, const T* __restrict__ src, T* __restrict__ dst) {
+  const int pad = (KT - 1) / 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    if (!FOLD) {
+      // e indexes col: ((b*T + t)*V + v) * (KT*C) + dt*C + c
+      const int c = (int)(e % C);
+      long long r = e / C;
+      const int dt = (int)(r % KT);
+      r /= KT;  // (b*T + t)*V + v
+      const int v = (int)(r % V);
+      const long long bt = r / V;
+      const int t = (int)(bt % Tn);
+      const int ts = t + dt - pad;
+      float val = 0.f;
+      if (ts >= 0 && ts < Tn) val = ldf<T>(src + ((bt - t + ts) * V + v) * C + c);
+      stf<T>(dst + e, val);
+    } else {
+      // e indexes dx: ((b*T + t)*V + v)*C + c
+      const int c = (int)(e % C);
+      long long r = e / C;
+      const int v = (int)(r % V);
+      const long long bt = r / V;
+      const int t = (int)(bt % Tn);
+      float acc = 0.f;
+      for (int dt = 0; dt < KT; ++dt) {
+        const int tr = t - dt + pad;  // row whose tap dt read x[t]
+        if (tr >= 0 && tr < Tn) acc += ldf<T>(src + (((bt - t + tr) * V + v) * KT + dt) * C + c);
+      }
+      stf<T>(dst + e, acc);
+    }
+  }
+}
+
+extern "C" int p2r_temporal_unfold(const void* x, int dtype, int B, int Tn, int V, int C, int KT, void* col,
+                                   void* stream) {
+  P2R_CHECK_ARG(B >= 0 && Tn > 0 && V > 0 && C > 0 && KT > 0 && (KT & 1), "p2r_temporal_unfold");
+  const long long total = (long long)B * Tn * V * C * KT;
+  if (total == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
+  if (dtype == 0)
+    temporal_unfold_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>(Tn, V, C, KT, total, (const float*)x, (float*)col);
+  else
+    temporal_unfold_kernel<__nv_bfloat16, false><<<grid, 256, 0, (cudaStream_t)stream>>>(Tn, V, C, KT, total, (const __nv_bfloat16*)x, (__nv_bfloat16*)col);
+  P2R_RETURN_LAUNCH("p2r_temporal_unfold");
+}
+
+extern "C" int p2r_temporal_fold(const void* dcol, int dtype, int B, int Tn, int V, int C, int KT, void* dx,
+                                 void* stream) {
+  P2R_CHECK_ARG(B >= 0 && Tn > 0 && V > 0 && C > 0 && KT > 0 && (KT & 1), "p2r_temporal_fold");
+  const long long total = (long long)B * Tn * V * C;
+  if (total == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
+  if (dtype == 0)
+    temporal_unfold_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(Tn, V, C, KT, total, (const float*)dcol, (float*)dx);
+  else
+    temporal_unfold_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(Tn, V, C, KT, total, (const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx);
+  P2R_RETURN_LAUNCH("p2r_temporal_fold");
+}
+
+// ================================================================================================
+// channel-last grouping for the set-abstraction layer (the layout the fused path uses instead of the
+// reference's (B,C,N) -> (B,C,P,S) group_points):
+//   group_rows:      feats [B,N,C], idx [B,P,S] i32 -> out [B,P,S,C]      (row gather, 128-bit copies)
+//   group_rows_grad: grad  [B,P,S,C] -> dfeats [B,N,C] (fp32 atomics, zero-filled by caller)
+//   maxpool_rows:    x [R,S,C] -> out [R,C], arg [R,C] u8  (first maximum wins, like F.max_pool2d)
+//   maxpool_rows_grad: dout [R,C], arg -> dx [R,S,C]
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+group_rows_kernel(int N, int C, long long rows, int rows_per_batch, const T* __restrict__ feats,
+                  const int* __restrict__ idx, T* __restrict__ out) {
+  // one warp per output row
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  const long long b = w / rows_per_batch;
+  const int src_row = __ldg(idx + w);
+  const T* s = feats + ((size_t)b * N + src_row) * C;
+  T* d = out + (size_t)w * C;
+  constexpr int VEC = 16 / sizeof(T);
+  if (C % VEC == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    for (int i = lane; i < C / VEC; i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = lane; i < C; i += 32) d[i] = s[i];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+group_rows_grad_kernel(int N, int C, long long rows, int rows_per_batch, const T* __restrict__ grad,
+                       const int* __restrict__ idx, float* __restrict__ dfeats) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  const long long b = w / rows_per_batch;
+  const int dst_row = __ldg(idx + w);
+  float* d = dfeats + ((size_t)b * N + dst_row) * C;
+  const T* g = grad + (size_t)w * C;
+  for (int i = lane; i < C; i += 32) atomicAdd(d + i, ldf<T>(g + i));
+}
+
+extern "C" int p2r_group_rows(const void* feats, int dtype, const int* idx, int B, int N, int C, int P, int S, void* out,
+                              void* stream) {
+  P2R_CHECK_ARG(B >= 0 && N > 0 && C > 0 && P >= 0 && S >= 0, "p2r_group_rows");
+  const long long rows = (long long)B * P * S;
+  if (rows == 0) return 0;
+  const int grid = p2r_ceil_div(rows * 32, 256);
+  if (dtype == 0)
+    group_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, rows, P * S, (const float*)feats, idx, (float*)out);
+  else
+    group_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, rows, P * S, (const __nv_bfloat16*)feats, idx, (__nv_bfloat16*)out);
+  P2R_RETURN_LAUNCH("p2r_group_rows");
+}
+
+// dfeats is ALWAYS float32 [B,N,C], zero-filled by the caller.
+extern "C" int p2r_group_rows_grad(const void* grad, int dtype, const int* idx, int B, int N, int C, int P, int S,
+                                   float* dfeats, void* stream) {
+  P2R_CHECK_ARG(B >= 0 && N > 0 && C > 0 && P >= 0 && S >= 0, "p2r_group_rows_grad");
+  const long long rows = (long long)B * P * S;
+  if (rows == 0) return 0;
+  const int grid = p2r_ceil_div(rows * 32, 256);
+  if (dtype == 0)
+    group_rows_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, rows, P * S, (const float*)grad, idx, dfeats);
+  else
+    group_rows_grad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, rows, P * S, (const __nv_bfloat16*)grad, idx, dfeats);
+  P2R_RETURN_LAUNCH("p2r_group_rows_grad");
+}
+
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256)
+maxpool_rows_kernel(long long R, int S, int C, const T* __restrict__ src, unsigned char* __restrict__ arg,
+                    T* __restrict__ dst) {
+  const long long total = R * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long r = e / C;
+    const int c = (int)(e % C);
+    if (!GRAD) {
+      const T* p = src + (size_t)r * S * C + c;
+      float best = ldf<T>(p);
+      int bi = 0;
+      for (int s = 1; s < S; ++s) {
+        const float v = ldf<T>(p + (size_t)s * C);
+        if (v > best) { best = v; bi = s; }
+      }
+      stf<T>(dst + e, best);
+      arg[e] = (unsigned char)bi;
+    } else {
+      const float g = ldf<T>(src + e);
+      const int a = arg[e];
+      T* p = dst + (size_t)r * S * C + c;
+      for (int s = 0; s < S; ++s) stf<T>(p + (size_t)s * C, s == a ? g : 0.f);
+    }
+  }
+}
+
+extern "C" int p2r_maxpool_rows(const void* x, int dtype, long long R, int S, int C, void* out, unsigned char* arg,
+                                void* stream) {
+  P2R_CHECK_ARG(R >= 0 && S > 0 && S <= 255 && C > 0, "p2r_maxpool_rows");
+  if (R == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (R * C + 255) / 256);
+  if (dtype == 0)
+    maxpool_rows_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>(R, S, C, (const float*)x, arg, (float*)out);
+  else
+    maxpool_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, (cudaStream_t)stream>>>(R, S, C, (const __nv_bfloat16*)x, arg, (__nv_bfloat16*)out);
+  P2R_RETURN_LAUNCH("p2r_maxpool_rows");
+}
+
+extern "C" int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg, long long R, int S, int C,
+                                     void* dx, void* stream) {
+  P2R_CHECK_ARG(R >= 0 && S > 0 && S <= 255 && C > 0, "p2r_maxpool_rows_grad");
+  if (R == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (R * C + 255) / 256);
+  if (dtype == 0)
+    maxpool_rows_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(R, S, C, (const float*)dout, const_cast<unsigned char*>(arg), (float*)dx);
+  else
+    maxpool_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(R, S, C, (const __nv_bfloat16*)dout, const_cast<unsigned char*>(arg), (__nv_bfloat16*)dx);
+  P2R_RETURN_LAUNCH("p2r_maxpool_rows_grad");
+}

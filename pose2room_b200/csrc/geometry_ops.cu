@@ -114,6 +114,64 @@ extern "C" int p2r_graph_offset(const float* x, const long long* idx, int b, int
   P2R_RETURN_LAUNCH("p2r_graph_offset");
 }
 
+
+// ================================================================================================
+// uniform_seed_inds: arc-length-uniform frame sampling (models/p2rnet/modules/stgcn.py:96-101).
+// hip (B,T,3) with `stride` floats between frames -> seed_inds (B,S) i64 =
+//   argmin_t | cum[t] - s * cum[T-1]/(S-1) |, cum = cumulative hip path length.
+// Arithmetic mirrors the reference as executed by torch on CPU (what the golden vectors pin):
+// step = sqrtf(fma(dz,dz,fma(dy,dy,dx*dx))), cumulative sum accumulated in double and rounded to float
+// per element, fp32 division / multiply / subtract, first minimal index wins.
+// One CTA per sequence; T <= 16384.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+uniform_seed_kernel(int T, int S, int stride, const float* __restrict__ hip, long long* __restrict__ seed) {
+  extern __shared__ float s_cum[];  // [T]
+  const int b = blockIdx.x;
+  const float* h = hip + (size_t)b * T * stride;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float d = 0.f;
+    if (t > 0) {
+      const float dx = __fsub_rn(__ldg(h + (size_t)t * stride), __ldg(h + (size_t)(t - 1) * stride));
+      const float dy = __fsub_rn(__ldg(h + (size_t)t * stride + 1), __ldg(h + (size_t)(t - 1) * stride + 1));
+      const float dz = __fsub_rn(__ldg(h + (size_t)t * stride + 2), __ldg(h + (size_t)(t - 1) * stride + 2));
+      d = __fsqrt_rn(p2r_sqnorm3(dx, dy, dz));
+    }
+    s_cum[t] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int t = 0; t < T; ++t) {
+      acc += (double)s_cum[t];
+      s_cum[t] = (float)acc;
+    }
+  }
+  __syncthreads();
+  const float step = __fdiv_rn(s_cum[T - 1], (float)(S - 1));
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float target = __fmul_rn(step, (float)s);
+    float best = fabsf(__fsub_rn(s_cum[0], target));
+    int bi = 0;
+    for (int t = 1; t < T; ++t) {
+      const float v = fabsf(__fsub_rn(s_cum[t], target));
+      if (v < best) { best = v; bi = t; }
+    }
+    seed[(size_t)b * S + s] = bi;
+  }
+}
+
+extern "C" int p2r_uniform_seed_inds(const float* hip, int stride, int b, int t, int s, long long* seed_inds,
+                                     void* stream) {
+  P2R_CHECK_ARG(b >= 0 && t > 0 && t <= 16384 && s > 1 && stride >= 3, "p2r_uniform_seed_inds");
+  if (b == 0) return 0;
+  const size_t smem = (size_t)t * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(uniform_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  uniform_seed_kernel<<<b, 256, smem, (cudaStream_t)stream>>>(t, s, stride, hip, seed_inds);
+  P2R_RETURN_LAUNCH("p2r_uniform_seed_inds");
+}
+
 // ================================================================================================
 // nn_distance: pc1 (B,N,C), pc2 (B,M,C) -> dist1,idx1 (B,N), dist2,idx2 (B,M).
 // mode 0: squared L2, 1: L1, 2: smooth-L1 (huber, delta).  Per-pair cost = sequential fp32 sum over

@@ -1,0 +1,277 @@
+"""Autograd operators of the dense (channel-last) part of the P2RNet hot path, on libp2r_b200.so.
+
+Every forward AND backward here is a hand-written kernel call through the C ABI; PyTorch only owns
+the memory, the stream and the autograd graph.  Layout convention: activations are [rows, channels]
+(rows = points / frames), i.e. the reference's (B, C, N) Conv1d / (B, C, T, V) Conv2d tensors transposed
+to channel-last, which turns every 1x1 conv into a row-major GEMM and every BatchNorm into a column
+statistic ("data layout").
+
+Precision: activations may be float32 (parity mode: fp32-exact SIMT GEMM, fixed summation order) or
+bfloat16 (throughput mode: tensor-core GEMM from gemm_sm100.cu, fp32 accumulate).  Parameters stay fp32.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _splits_for(out_rows, out_cols, reduce_dim):
+    tiles = ((out_rows + 63) // 64) * ((out_cols + 63) // 64)
+    want = max(1, (148 * 4) // max(tiles, 1))
+    return int(max(1, min(want, (reduce_dim + 255) // 256)))
+
+
+# gemm backend hook: gemm_sm100 installs a tensor-core implementation for bf16 operands here
+_TC_GEMM = {"fn": None}
+
+
+def sgemm(a, b, trans_a=False, trans_b=True, bias=None, relu=False, out_dtype=None, splits=1, out=None):
+    """C = op(a) @ op(b) (+bias)(ReLU) with the SIMT fp32-accumulate kernel (see include/p2r_b200.h)."""
+    assert a.is_cuda and b.is_cuda and a.dim() == 2 and b.dim() == 2
+    a = a if a.is_contiguous() else a.contiguous()
+    b = b if b.is_contiguous() else b.contiguous()
+    m, k = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    n = b.shape[0] if trans_b else b.shape[1]
+    kb = b.shape[1] if trans_b else b.shape[0]
+    assert k == kb, (a.shape, b.shape, trans_a, trans_b)
+    out_dtype = out_dtype or a.dtype
+    if splits > 1:
+        assert out_dtype == torch.float32 and bias is None and not relu
+        c = torch.zeros(m, n, dtype=torch.float32, device=a.device) if out is None else out
+    else:
+        c = torch.empty(m, n, dtype=out_dtype, device=a.device) if out is None else out
+    if bias is not None:
+        bias = bias.float().contiguous()
+    with torch.cuda.device(a.device):
+        _lib.call("p2r_sgemm", m, n, k, a.data_ptr(), a.stride(0), int(trans_a), _DT[a.dtype], b.data_ptr(),
+                  b.stride(0), int(trans_b), _DT[b.dtype], c.data_ptr(), c.stride(0), _DT[c.dtype], _ptr(bias),
+                  int(relu), 0, int(splits), _stream())
+    return c
+
+
+def _col_sum(dy, y=None, relu=False):
+    """sum over rows of dz = relu ? dy*(y>0) : dy -> float32 [C] (bias gradients)."""
+    m, c = dy.shape
+    if c > 256 and c % 256 or c <= 256 and 256 % c:
+        return (dy.float() if not relu else dy.float() * (y > 0)).sum(0)  # odd channel counts (259, 100, 24): tiny tensors
+    s1 = torch.zeros(c, dtype=torch.float64, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.call("p2r_col_bwd_stats", dy.data_ptr(), None, _ptr(y), _DT[dy.dtype], m, c, None, None, int(relu),
+                  s1.data_ptr(), None, _stream())
+    return s1.float()
+
+
+class _Linear(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x = x if x.is_contiguous() else x.contiguous()
+        tc = _TC_GEMM["fn"]
+        if tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
+            y = tc.linear_fwd(x, weight, bias, relu)
+        else:
+            y = sgemm(x, weight, False, True, bias, relu, out_dtype=x.dtype)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        if ctx.relu:
+            dz = torch.empty_like(dy)
+            with torch.cuda.device(dy.device):
+                _lib.call("p2r_relu_bwd", dy.data_ptr(), y.data_ptr(), _DT[dy.dtype], dy.numel(), dz.data_ptr(), _stream())
+        else:
+            dz = dy
+        m, n = dz.shape
+        k = x.shape[1]
+        dx = dw = db = None
+        tc = _TC_GEMM["fn"]
+        use_tc = tc is not None and x.dtype == torch.bfloat16 and tc.supports(m, n, k)
+        if ctx.needs_input_grad[0]:
+            dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
+        if ctx.needs_input_grad[1]:
+            if use_tc:
+                dw = tc.linear_dw(dz, x)
+            else:
+                dw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _col_sum(dz)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, relu=False):
+    """y[M,N] = x[M,K] @ weight[N,K]^T (+bias)(ReLU): a 1x1 Conv1d/Conv2d in channel-last form."""
+    return _Linear.apply(x, weight, bias, relu)
+
+
+class _BatchNormAct(Function):
+    """Training- or eval-mode BatchNorm over the rows of x[M,C] (+residual)(+ReLU).
+    ref: nn.BatchNorm1d/2d inside SingleConv 'cbr' (sub_modules.py:64-70) and st_gcn_block.tcn
+    (stgcn_layers.py:402-414) followed by `+ res` and ReLU (:436-438)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu):
+        x = x if x.is_contiguous() else x.contiguous()
+        m, c = x.shape
+        dev = x.device
+        dt = _DT[x.dtype]
+        stats = torch.empty(4, c, dtype=torch.float32, device=dev)  # mean, rstd, scale, shift
+        with torch.cuda.device(dev):
+            if training:
+                sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
+                _lib.call("p2r_col_stats", x.data_ptr(), dt, m, c, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+                _lib.call("p2r_bn_finalize", c, m, sums[0].data_ptr(), sums[1].data_ptr(), _ptr(gamma), _ptr(beta),
+                          float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), stats[0].data_ptr(),
+                          stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), _stream())
+            else:
+                rstd = torch.rsqrt(running_var + eps)
+                stats[0] = running_mean
+                stats[1] = rstd
+                stats[2] = gamma * rstd
+                stats[3] = beta - running_mean * gamma * rstd
+            y = torch.empty_like(x)
+            if residual is not None:
+                residual = residual if residual.is_contiguous() else residual.contiguous()
+            _lib.call("p2r_affine_act", x.data_ptr(), dt, m, c, stats[2].data_ptr(), stats[3].data_ptr(),
+                      _ptr(residual), int(relu), y.data_ptr(), _stream())
+        ctx.save_for_backward(x, y if relu else None, stats)
+        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, stats = ctx.saved_tensors
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        m, c = x.shape
+        dev = x.device
+        dt = _DT[x.dtype]
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
+                      stats[1].data_ptr(), int(ctx.relu), sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+            _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
+                      stats[1].data_ptr(), stats[2].data_ptr(), sums[0].data_ptr() if ctx.training else None,
+                      sums[1].data_ptr() if ctx.training else None, int(ctx.relu), dx.data_ptr(), _ptr(dres), _stream())
+        dgamma = sums[1].float() if ctx.needs_input_grad[1] else None
+        dbeta = sums[0].float() if ctx.needs_input_grad[2] else None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+def batchnorm_act(x, bn, relu=False, residual=None):
+    """Apply nn.BatchNorm{1,2}d module `bn` (its parameters / running stats / momentum / eps / mode) to the
+    channel-last matrix x[M,C], optionally adding `residual` and a ReLU -- one fused elementwise pass."""
+    training = bn.training or not bn.track_running_stats
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training,
+                               momentum, bn.eps, relu)
+
+
+class _TemporalUnfold(Function):
+    @staticmethod
+    def forward(ctx, x, kt):
+        b, t, v, c = x.shape
+        x = x if x.is_contiguous() else x.contiguous()
+        col = torch.empty(b * t * v, kt * c, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("p2r_temporal_unfold", x.data_ptr(), _DT[x.dtype], b, t, v, c, kt, col.data_ptr(), _stream())
+        ctx.shape = (b, t, v, c, kt)
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        b, t, v, c, kt = ctx.shape
+        dcol = dcol if dcol.is_contiguous() else dcol.contiguous()
+        dx = torch.empty(b, t, v, c, dtype=dcol.dtype, device=dcol.device)
+        with torch.cuda.device(dcol.device):
+            _lib.call("p2r_temporal_fold", dcol.data_ptr(), _DT[dcol.dtype], b, t, v, c, kt, dx.data_ptr(), _stream())
+        return dx, None
+
+
+def temporal_conv(x, weight, bias):
+    """(KT x 1) temporal convolution, zero padding (KT-1)/2, stride 1 (stgcn_layers.py:405-411).
+    x [B,T,V,Ci] channel-last, weight (Co,Ci,KT,1) as stored by nn.Conv2d -> [B*T*V, Co]."""
+    co, ci, kt, _ = weight.shape
+    tc = _TC_GEMM["fn"]
+    if tc is not None and x.dtype == torch.bfloat16 and tc.supports_tconv(x.shape, co):
+        return tc.temporal_conv(x, weight, bias)
+    col = _TemporalUnfold.apply(x, kt)
+    w2 = weight[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci)  # column = dt*Ci + ci
+    return linear(col, w2, bias)
+
+
+class _GroupRows(Function):
+    @staticmethod
+    def forward(ctx, feats, idx):
+        b, n, c = feats.shape
+        _, p, s = idx.shape
+        feats = feats if feats.is_contiguous() else feats.contiguous()
+        out = torch.empty(b, p, s, c, dtype=feats.dtype, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _lib.call("p2r_group_rows", feats.data_ptr(), _DT[feats.dtype], idx.data_ptr(), b, n, c, p, s,
+                      out.data_ptr(), _stream())
+        ctx.save_for_backward(idx)
+        ctx.shape = (b, n, c, p, s)
+        ctx.dtype = feats.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        b, n, c, p, s = ctx.shape
+        g = g if g.is_contiguous() else g.contiguous()
+        d = torch.zeros(b, n, c, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.call("p2r_group_rows_grad", g.data_ptr(), _DT[g.dtype], idx.data_ptr(), b, n, c, p, s, d.data_ptr(),
+                      _stream())
+        return d.to(ctx.dtype), None
+
+
+def group_rows(feats, idx):
+    """feats [B,N,C], idx [B,P,S] int32 -> [B,P,S,C]: channel-last twin of grouping_operation."""
+    return _GroupRows.apply(feats, idx.contiguous())
+
+
+class _MaxPoolRows(Function):
+    @staticmethod
+    def forward(ctx, x):
+        r, s, c = x.shape
+        x = x if x.is_contiguous() else x.contiguous()
+        out = torch.empty(r, c, dtype=x.dtype, device=x.device)
+        arg = torch.empty(r, c, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("p2r_maxpool_rows", x.data_ptr(), _DT[x.dtype], r, s, c, out.data_ptr(), arg.data_ptr(), _stream())
+        ctx.save_for_backward(arg)
+        ctx.shape = (r, s, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        r, s, c = ctx.shape
+        g = g if g.is_contiguous() else g.contiguous()
+        dx = torch.empty(r, s, c, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.call("p2r_maxpool_rows_grad", g.data_ptr(), _DT[g.dtype], arg.data_ptr(), r, s, c, dx.data_ptr(), _stream())
+        return dx
+
+
+def maxpool_rows(x):
+    """x [R,S,C] -> max over S -> [R,C] (F.max_pool2d over nsample, pointnet2_modules.py:243-247)."""
+    return _MaxPoolRows.apply(x)

@@ -1,0 +1,109 @@
+"""Detection losses of P2RNet on the B200 nn_distance kernel.
+
+Same registered names, constructor `(weight, device, cfg)`, call signature and returned dict (ten 0-d tensors,
+'total' differentiable) as /root/reference/models/loss.py:22-189.  The three nn_distance call sites
+(loss.py:64,105,128) go through pose2room_b200.geometry.nn_distance (one kernel each, indices bit-identical
+to the reference); the per-sample Python loop of compute_correspondence (loss.py:126-133, boolean-mask
+indexing = a host sync per sample) is replaced by ONE batched call in which padded GT slots are moved far
+away, which yields the same distances and indices because valid boxes always form a prefix
+(models/p2rnet/dataloader.py:119-123).
+"""
+import torch
+from torch import nn
+
+from ..geometry import huber_loss, nn_distance
+from .registers import LOSSES
+
+FAR_THRESHOLD = 0.6
+NEAR_THRESHOLD = 0.3
+GT_VOTE_FACTOR = 3
+OBJECTNESS_CLS_WEIGHTS = [0.1, 0.9]
+_FAR_AWAY = 1.0e4  # padded GT centres: (1e4)^2 * 3 = 3e8, finite in fp32, never the nearest
+
+
+class BaseLoss(object):
+    def __init__(self, weight=1, device=0, cfg=None):
+        self.weight = weight
+        self.device = device
+        self.origin_joint_id = cfg.dataset_config.origin_joint_id
+
+
+@LOSSES.register_module
+class Null(BaseLoss):
+    def __call__(self, loss):
+        return self.weight * torch.mean(loss)
+
+
+@LOSSES.register_module
+class BoxNetDetectionLoss(BaseLoss):
+    def __init__(self, weight, device, cfg=None):
+        super().__init__(weight, device, cfg)
+        self._obj_w = torch.tensor(OBJECTNESS_CLS_WEIGHTS)
+        self._sem_ce = nn.CrossEntropyLoss(reduction="none")
+
+    def compute_vote_loss(self, est, gt):
+        """loss.py:90-115: supervise each vote with the GT vote closest to any body joint of its seed."""
+        b, s, j = est["seed_skeleton"].shape[:3]
+        vote_xyz = est["vote_xyz"]
+        seed_inds = est["seed_inds"].long()
+        o = self.origin_joint_id
+        mask = torch.gather(gt["vote_label_mask"][..., o], 1, seed_inds)
+        votes = torch.gather(gt["vote_label"][:, :, o], 1, seed_inds.view(b, s, 1).expand(b, s, 3 * GT_VOTE_FACTOR))
+        votes = est["seed_skeleton"][:, :, [o]] + votes.view(b, s, GT_VOTE_FACTOR, 3)
+        skeleton = est["seed_skeleton"].reshape(b * s, j, 3)
+        _, _, dist2, ind2 = nn_distance(votes.view(b * s, GT_VOTE_FACTOR, 3), skeleton)
+        pick = torch.gather(ind2, 1, dist2.argmin(-1, keepdim=True)).view(b, s, 1)
+        target = torch.gather(votes, 2, pick.unsqueeze(-1).expand(b, s, 1, 3)).squeeze(2)
+        vote_loss = torch.mean(huber_loss(vote_xyz - target, delta=1.0), -1)
+        m = mask.float()
+        return torch.sum(vote_loss * m) / (torch.sum(m) + 1e-6)
+
+    def compute_correspondence(self, est, gt):
+        """loss.py:117-150, batched."""
+        agg = est["aggregated_vote_xyz"]
+        gt_center = gt["center_label"][:, :, 0:3]
+        box_mask = gt["box_label_mask"]
+        padded = torch.where(box_mask.unsqueeze(-1) > 0, gt_center, torch.full_like(gt_center, _FAR_AWAY))
+        dist1, assignment, _, _ = nn_distance(agg, padded)
+        dist = torch.sqrt(dist1 + 1e-6)
+        near = dist < NEAR_THRESHOLD
+        objectness_label = near.long()
+        objectness_mask = (near | (dist > FAR_THRESHOLD)).float()
+        scores = est["objectness_scores"]
+        ce = nn.functional.cross_entropy(scores.transpose(2, 1), objectness_label,
+                                         weight=self._obj_w.to(scores.device), reduction="none")
+        objectness_loss = torch.sum(ce * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
+        return assignment, objectness_loss, objectness_label, objectness_mask
+
+    def compute_box_and_sem_cls_loss(self, est, gt, meta, config):
+        """loss.py:42-88."""
+        assignment = meta["object_assignment"]
+        obj = meta["objectness_label"].float()
+        denom = torch.sum(obj) + 1e-6
+        box_mask = gt["box_label_mask"]
+        dist1, _, dist2, _ = nn_distance(est["center"], gt["center_label"])
+        center_loss = (torch.sum(dist1 * obj) / denom + torch.sum(dist2 * box_mask) / (torch.sum(box_mask) + 1e-6)) / 2.
+        gt_size = torch.gather(gt["size"], 1, assignment.unsqueeze(-1).expand(-1, -1, 3))
+        size_loss = torch.sum(torch.mean(huber_loss(est["size"] - gt_size, delta=1.0), -1) * obj) / denom
+        gt_heading = torch.gather(gt["heading"], 1, assignment.unsqueeze(-1).expand(-1, -1, 2))
+        heading_loss = torch.sum(torch.mean(huber_loss(est["heading"] - gt_heading, delta=1.0), -1) * obj) / denom
+        gt_cls = torch.gather(gt["sem_cls_label"], 1, assignment)
+        sem = self._sem_ce(est["sem_cls_scores"].transpose(2, 1), gt_cls)
+        sem_cls_loss = torch.sum(sem * obj) / denom
+        return center_loss, size_loss, heading_loss, sem_cls_loss
+
+    def __call__(self, est, gt, dataset_config):
+        vote_loss = self.compute_vote_loss(est, gt)
+        assignment, objectness_loss, objectness_label, objectness_mask = self.compute_correspondence(est, gt)
+        meta = {"object_assignment": assignment, "objectness_label": objectness_label}
+        center_loss, size_loss, heading_loss, sem_cls_loss = self.compute_box_and_sem_cls_loss(est, gt, meta,
+                                                                                               dataset_config)
+        total = 10 * vote_loss + 5 * objectness_loss + 10 * center_loss + 10 * size_loss + 10 * heading_loss + sem_cls_loss
+        n_prop = float(objectness_label.shape[0] * objectness_label.shape[1])
+        pos_ratio = torch.sum(objectness_label.float()) / n_prop
+        neg_ratio = torch.sum(objectness_mask) / n_prop - pos_ratio
+        obj_pred = torch.argmax(est["objectness_scores"], 2)
+        obj_acc = torch.sum((obj_pred == objectness_label).float() * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
+        return {"total": total, "vote_loss": vote_loss, "objectness_loss": objectness_loss, "center_loss": center_loss,
+                "size_loss": size_loss, "heading_loss": heading_loss, "sem_cls_loss": sem_cls_loss,
+                "pos_ratio": pos_ratio, "neg_ratio": neg_ratio, "obj_acc": obj_acc}

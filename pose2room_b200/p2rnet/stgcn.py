@@ -1,0 +1,163 @@
+"""STGCN backbone: pose sequence (B,T,J,3) -> seed skeletons + 256-d seed features.
+
+Same module surface and state-dict as the reference's STGCN / st_gcn_block / ConvTemporalGraphical
+(/root/reference/models/p2rnet/modules/stgcn.py:12-152, stgcn_layers.py:10-67,362-439), re-laid out
+for B200:
+
+* activations are channel-last [B, T, V, C]; a frame is one row of V*C contiguous values;
+* the graph convolution (1x1 conv 64 -> 11*64 followed by einsum 'nkctv,kvw->nctw', stgcn_layers.py:58-67)
+  is ONE dense GEMM per block:  out[(n,t), (w,co)] = sum_{(v,ci)} x[(n,t), (v,ci)] * W_eff[(w,co), (v,ci)],
+  W_eff = sum_k W_k (x) A_k  rebuilt each step from the conv weight and A*edge_importance (56 MFLOP), so the
+  (B, 704, T, V) intermediate (2.3 GB at the BASELINE shape) never exists and autograd still reaches the
+  conv weight, its bias and the edge importance;
+* BatchNorm (+ReLU) (+residual) is a fused column-statistics + elementwise pass on rows;
+* the (3x1) temporal conv is a GEMM over three row-shifted views of the same tensor;
+* conv_joint is applied AFTER gathering the 512 seed frames (a 1x1 conv commutes with the gather: half the
+  work, same values);
+* the arc-length-uniform seed sampling is one small kernel instead of a (B,T,S) argmin tensor.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from .graph import layout_for_joints, spatial_adjacency
+from .registers import MODULES
+from .sub_modules import SingleConv, run_rows
+
+
+class ConvTemporalGraphical(nn.Module):
+    """Parameter holder with the reference's names (gcn.conv.{weight,bias}); see st_gcn_block.forward_rows."""
+
+    def __init__(self, in_channels, out_channels, kernel_size):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.conv = nn.Conv2d(in_channels, out_channels * kernel_size, kernel_size=(1, 1), bias=True)
+
+    def effective_weight(self, A):
+        """W_eff [(w,co), (v,ci)] and b_eff [(w,co)] for adjacency stack A (K,V,V)."""
+        k, co, ci = self.kernel_size, self.out_channels, self.in_channels
+        v = A.shape[1]
+        wk = self.conv.weight.reshape(k, co, ci)
+        w_eff = torch.einsum("koi,kvw->wovi", wk, A).reshape(v * co, v * ci)
+        b_eff = torch.einsum("ko,kw->wo", self.conv.bias.reshape(k, co), A.sum(1)).reshape(v * co)
+        return w_eff, b_eff
+
+
+class st_gcn_block(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, dropout=0, residual=True):
+        super().__init__()
+        assert stride == 1 and kernel_size[0] % 2 == 1 and dropout == 0
+        assert (not residual) or in_channels == out_channels, "the hot path only uses identity / no residual"
+        self.gcn = ConvTemporalGraphical(in_channels, out_channels, kernel_size[1])
+        self.tcn = nn.Sequential(
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, (kernel_size[0], 1), (1, 1), ((kernel_size[0] - 1) // 2, 0)),
+            nn.BatchNorm2d(out_channels),
+            nn.Dropout(dropout, inplace=True),
+        )
+        self.has_residual = residual
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward_rows(self, x, A):
+        """x [B,T,V,C] channel-last -> [B,T,V,C]."""
+        b, t, v, c = x.shape
+        co = self.gcn.out_channels
+        w_eff, b_eff = self.gcn.effective_weight(A)
+        g = ops.linear(x.reshape(b * t, v * c), w_eff, b_eff)                    # graph conv: one GEMM
+        h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True)  # BN + ReLU
+        y = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias)
+        res = x.reshape(b * t * v, c) if self.has_residual else None
+        out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res)         # BN + residual + ReLU
+        return out.reshape(b, t, v, co)
+
+
+@MODULES.register_module
+class STGCN(nn.Module):
+    def __init__(self, cfg, optim_spec=None):
+        super().__init__()
+        self.optim_spec = optim_spec
+        joint_num = cfg.dataset_config.joint_num
+        A = torch.tensor(spatial_adjacency(layout_for_joints(joint_num), max_hop=5), dtype=torch.float32)
+        self.register_buffer("A", A)
+        self.n_seeds = cfg.config["data"]["num_seeds"]
+        self.origin_joint_id = cfg.dataset_config.origin_joint_id
+        self.precision = cfg.config.get("precision", "fp32") if isinstance(cfg.config, dict) else "fp32"
+        self.knn = 20
+        k_spatial = A.size(0)
+
+        def mlp3():
+            return nn.Sequential(SingleConv(3, 64, order="cbr"), SingleConv(64, 64, order="cbr"),
+                                 SingleConv(64, 64, order="c"))
+        self.pos_embed = mlp3()
+        self.sk_feat = mlp3()
+        self.st_gcn_networks = nn.ModuleList(
+            [st_gcn_block(64, 64, (3, k_spatial), 1, residual=False)] +
+            [st_gcn_block(64, 64, (3, k_spatial), 1) for _ in range(5)])
+        self.conv_joint = nn.Conv1d(joint_num * 64, 256, kernel_size=1)
+        self.edge_importance = nn.ParameterList([nn.Parameter(torch.ones(self.A.size())) for _ in self.st_gcn_networks])
+        if self.n_seeds >= cfg.config["data"]["num_frames"]:
+            self.seed_inds = torch.round(torch.linspace(0, cfg.config["data"]["num_frames"] - 1, self.n_seeds)).long()
+        else:
+            self.seed_sampling = cfg.config["data"]["seed_sampling"]
+        self._idx_cache = {}
+
+    # ------------------------------------------------------------------ pieces
+    def _seed_inds(self, input_joints):
+        b, t, j, _ = input_joints.shape
+        dev = input_joints.device
+        if self.n_seeds >= t:
+            return self.seed_inds.repeat(b, 1).to(dev)
+        if self.seed_sampling == "random":
+            inds = torch.argsort(torch.rand(size=(b, t)), dim=1)[:, :self.n_seeds]
+            return torch.sort(inds, dim=1)[0].to(dev)
+        if self.seed_sampling != "uniform":
+            raise NotImplementedError
+        hip = input_joints[:, :, self.origin_joint_id]  # strided view, read in place by the kernel
+        out = torch.empty(b, self.n_seeds, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("p2r_uniform_seed_inds", hip.data_ptr(), int(hip.stride(1)), b, t, self.n_seeds, out.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream)
+        return out
+
+    def _window_idx(self, t, dev):
+        key = (t, str(dev))
+        if key not in self._idx_cache:
+            base = torch.arange(t, device=dev)[:, None] + torch.arange(-self.knn // 2, self.knn // 2, device=dev)[None]
+            self._idx_cache[key] = base.clamp_(0, t - 1)
+        return self._idx_cache[key]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_joints, end_points=None):
+        end_points = {} if end_points is None else end_points
+        if not input_joints.is_cuda:
+            raise RuntimeError("pose2room_b200.STGCN: CUDA tensor required (there is no CPU path)")
+        input_joints = input_joints.contiguous()
+        b, t, j, d = input_joints.shape
+        act = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        seed_inds = self._seed_inds(input_joints)
+
+        hip = input_joints[:, :, self.origin_joint_id]                       # (B,T,3)
+        x0 = input_joints - hip[:, :, None]                                  # joints relative to the hip
+        rel = hip[:, self._window_idx(t, hip.device)] - hip[:, :, None]      # (B,T,20,3): stgcn.py:109-117
+        pos = run_rows(self.pos_embed, rel.reshape(b * t * self.knn, 3).to(act))
+        pos = pos.reshape(b, t, self.knn, 64).float().mean(dim=2)            # (B,T,64)
+        sk = run_rows(self.sk_feat, x0.reshape(b * t * j, 3).to(act)).reshape(b, t, j, 64)
+        x = (sk.float() + pos[:, :, None]).to(act)                           # (B,T,J,64) channel-last
+
+        for blk, importance in zip(self.st_gcn_networks, self.edge_importance):
+            x = blk.forward_rows(x, self.A * importance)
+
+        # conv_joint on the seed frames only; reference channel order is c*J + v (stgcn.py:136-139)
+        frames = x.reshape(b, t, j * 64)
+        sel = torch.gather(frames, 1, seed_inds[:, :, None].expand(b, self.n_seeds, j * 64))
+        wj = self.conv_joint.weight.reshape(256, 64, j).permute(0, 2, 1).reshape(256, j * 64)
+        seed_features = ops.linear(sel.reshape(b * self.n_seeds, j * 64), wj, self.conv_joint.bias)
+        seed_features = seed_features.float().reshape(b, self.n_seeds, 256)
+        seed_skeleton = torch.gather(input_joints, 1,
+                                     seed_inds[:, :, None, None].expand(b, self.n_seeds, j, d))
+        end_points["seed_inds"] = seed_inds
+        end_points["seed_skeleton"] = seed_skeleton[..., :3]
+        end_points["seed_features"] = seed_features
+        return end_points

@@ -1,0 +1,36 @@
+"""SingleConv: conv(1x1) [+ BatchNorm] [+ ReLU] with the reference's parameter names
+(/root/reference/models/p2rnet/modules/sub_modules.py:88-113; submodules 'conv', 'batchnorm', 'ReLU' in the
+order given by `order`, conv bias only when no norm layer is present), executed on channel-last rows by the
+B200 kernels.  Only the orders the hot path uses are built: 'cbr' and 'c' with kernel_size 1."""
+import torch.nn as nn
+
+from .. import ops
+
+
+class SingleConv(nn.Sequential):
+    def __init__(self, in_channels, out_channels, kernel_size=1, order="cbr", num_groups=8, padding=0, ndim=1):
+        super().__init__()
+        assert kernel_size == 1 and padding == 0 and order in ("cbr", "c"), \
+            "the P2RNet hot path only uses 1x1 'cbr' / 'c' blocks"
+        conv_cls = {1: nn.Conv1d, 2: nn.Conv2d}[ndim]
+        bn_cls = {1: nn.BatchNorm1d, 2: nn.BatchNorm2d}[ndim]
+        self.order = order
+        self.add_module("conv", conv_cls(in_channels, out_channels, 1, padding=0, bias="b" not in order))
+        if "b" in order:
+            self.add_module("batchnorm", bn_cls(out_channels))
+        if "r" in order:
+            self.add_module("ReLU", nn.ReLU(inplace=True))
+
+    def forward_rows(self, x):
+        """x [M, Cin] channel-last rows -> [M, Cout]."""
+        w = self.conv.weight.reshape(self.conv.out_channels, self.conv.in_channels)
+        y = ops.linear(x, w, self.conv.bias)
+        if "b" in self.order:
+            y = ops.batchnorm_act(y, self.batchnorm, relu="r" in self.order)
+        return y
+
+
+def run_rows(seq, x):
+    for m in seq:
+        x = m.forward_rows(x)
+    return x

@@ -95,3 +95,44 @@ def make_cloud(B, N, seed=0, extent=2.0):
     walk = np.cumsum(rng.normal(0.0, 0.05, size=(B, N, 3)), axis=1)
     pts = walk + rng.normal(0.0, 0.3, size=(B, N, 3))
     return np.clip(pts, -extent * 4, extent * 4).astype(np.float32)
+
+
+def deterministic_state_dict(reference_state_dict, seed=0):
+    """Platform-independent synthetic weights for a P2RNet state-dict (there are no checkpoints offline).
+
+    Every tensor is re-drawn from a torch CPU generator seeded by (seed, position of the key in sorted
+    order), with fan-in scaling for conv weights, so any process that knows the key -> shape/dtype map (the
+    reference model in the build container, the B200 model on the GPU box, the CPU checker) builds the SAME
+    weights without shipping megabytes of fixtures.  The GMM mixing logits get bias -4.6 and 0.1x weights so
+    that sum(pi) ~ 1 and decoded boxes are plausible ("Eval with untrained weights aborts").
+    mu tensors are kept (they come from the reference's grid initialisation and are stored with the goldens).
+    """
+    import torch
+    out = {}
+    for i, k in enumerate(sorted(reference_state_dict)):
+        v = reference_state_dict[k]
+        g = torch.Generator().manual_seed(1_000_003 * (seed + 1) + i)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros_like(v)
+        elif k == "backbone.A" or k.endswith(".mdn.mu"):
+            out[k] = v.clone()
+        elif k.endswith(".mdn.log_sigma"):
+            out[k] = torch.full_like(v, -1.0)
+        elif k.endswith("running_mean"):
+            out[k] = 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("running_var"):
+            out[k] = 1.0 + 0.2 * torch.rand(v.shape, generator=g)
+        elif "edge_importance" in k:
+            out[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif "batchnorm" in k or ".tcn.0." in k or ".tcn.3." in k:
+            out[k] = (1.0 if k.endswith("weight") else 0.0) + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith(".mdn.pi.conv.weight"):
+            out[k] = 0.1 * torch.randn(v.shape, generator=g) / float(v[0].numel()) ** 0.5
+        elif k.endswith(".mdn.pi.conv.bias"):
+            out[k] = -4.6 + 0.05 * torch.randn(v.shape, generator=g)
+        elif k.endswith("bias"):
+            out[k] = 0.1 * torch.randn(v.shape, generator=g)
+        else:  # conv / linear weights
+            out[k] = torch.randn(v.shape, generator=g) / float(v[0].numel()) ** 0.5
+        out[k] = out[k].to(v.dtype)
+    return out

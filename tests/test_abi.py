@@ -64,4 +64,7 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(osp.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("oracle/pointnet2_ref.c header", ""), osp.join(dirpath, f)
+                for line in src.splitlines():
+                    if "oracle" in line:  # only a comment pointing at the oracle's header is tolerated
+                        assert "import" not in line and "CDLL" not in line and line.lstrip().startswith(("//", "#", "*")), \
+                            (osp.join(dirpath, f), line)

@@ -1,0 +1,141 @@
+"""GPU: the dense channel-last operators (GEMM, BatchNorm fwd/bwd, temporal conv, grouping, max-pool) against
+plain PyTorch fp32 references of the same ops, forward and backward."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rtol=1e-4, atol=1e-5):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a.float() - b.float()).abs().max().item()
+    assert torch.allclose(a.float(), b.float(), rtol=rtol, atol=atol), err
+
+
+@pytest.mark.parametrize("M,K,N,bias,relu", [(1000, 64, 64, True, False), (777, 3, 64, False, False),
+                                             (300, 256, 259, True, False), (513, 1600, 1600, True, False),
+                                             (4096, 256, 256, True, True), (65, 128, 100, True, False)])
+def test_linear_fwd_bwd_fp32(cuda, M, K, N, bias, relu):
+    from pose2room_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(M, K, generator=g).to(cuda).requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(cuda).requires_grad_(True) if bias else None
+    y = ops.linear(x, w, b, relu=relu)
+    ref = F.linear(x.double(), w.double(), b.double() if bias else None)
+    ref = F.relu(ref) if relu else ref
+    _close(y, ref, rtol=1e-5, atol=1e-5)
+    go = torch.randn(M, N, generator=g).to(cuda)
+    grads = torch.autograd.grad(y, [x, w] + ([b] if bias else []), go)
+    rgrads = torch.autograd.grad(ref, [x, w] + ([b] if bias else []), go.double())
+    for a, r in zip(grads, rgrads):
+        _close(a, r, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("relu,res", [(True, False), (False, False), (True, True)])
+@pytest.mark.parametrize("M,C", [(5000, 64), (333, 256), (4096, 128)])
+def test_batchnorm_act_train_fwd_bwd(cuda, M, C, relu, res):
+    from pose2room_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(cuda).requires_grad_(True)
+    r = torch.randn(M, C, generator=g).to(cuda).requires_grad_(True) if res else None
+    bn = nn.BatchNorm1d(C).to(cuda)
+    with torch.no_grad():
+        bn.weight.normal_(1, 0.2)
+        bn.bias.normal_(0, 0.2)
+    bn_ref = nn.BatchNorm1d(C).to(cuda).double()
+    bn_ref.load_state_dict(bn.state_dict())
+    y = ops.batchnorm_act(x, bn, relu=relu, residual=r)
+    xr = x.detach().double().requires_grad_(True)
+    rr = r.detach().double().requires_grad_(True) if res else None
+    ref = bn_ref(xr)
+    if res:
+        ref = ref + rr
+    if relu:
+        ref = F.relu(ref)
+    _close(y, ref, rtol=1e-4, atol=1e-5)
+    _close(bn.running_mean, bn_ref.running_mean, rtol=1e-5, atol=1e-6)
+    _close(bn.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 1
+    go = torch.randn(M, C, generator=g).to(cuda)
+    y.backward(go)
+    ref.backward(go.double())
+    _close(x.grad, xr.grad, rtol=1e-3, atol=1e-5)
+    _close(bn.weight.grad, bn_ref.weight.grad, rtol=1e-3, atol=1e-4)
+    _close(bn.bias.grad, bn_ref.bias.grad, rtol=1e-3, atol=1e-4)
+    if res:
+        _close(r.grad, rr.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_batchnorm_eval_mode(cuda):
+    from pose2room_b200 import ops
+    bn = nn.BatchNorm1d(64).to(cuda)
+    with torch.no_grad():
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2)
+        bn.weight.normal_(1, 0.2)
+        bn.bias.normal_()
+    bn.eval()
+    x = torch.randn(1000, 64, device=cuda, requires_grad=True)
+    y = ops.batchnorm_act(x, bn, relu=True)
+    xr = x.detach().clone().requires_grad_(True)
+    ref = F.relu(bn(xr))
+    _close(y, ref, rtol=1e-5, atol=1e-6)
+    go = torch.randn_like(y)
+    y.backward(go)
+    ref.backward(go)
+    _close(x.grad, xr.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_temporal_conv_fwd_bwd(cuda):
+    from pose2room_b200 import ops
+    B, T, V, C = 2, 37, 25, 64
+    conv = nn.Conv2d(C, C, (3, 1), (1, 1), (1, 0)).to(cuda)
+    x = torch.randn(B, T, V, C, device=cuda, requires_grad=True)
+    y = ops.temporal_conv(x, conv.weight, conv.bias).reshape(B, T, V, C)
+    xr = x.detach().clone().requires_grad_(True)
+    ref = conv(xr.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    _close(y, ref, rtol=1e-4, atol=1e-5)
+    go = torch.randn_like(y)
+    gw, gb, gx = torch.autograd.grad(y, [conv.weight, conv.bias, x], go)
+    rw, rb, rx = torch.autograd.grad(ref, [conv.weight, conv.bias, xr], go)
+    _close(gx, rx, rtol=1e-4, atol=1e-5)
+    _close(gw, rw, rtol=1e-3, atol=1e-4)
+    _close(gb, rb, rtol=1e-3, atol=1e-4)
+
+
+def test_group_rows_and_maxpool(cuda):
+    from pose2room_b200 import ops
+    B, N, C, P, S = 3, 100, 256, 16, 16
+    feats = torch.randn(B, N, C, device=cuda, requires_grad=True)
+    idx = torch.randint(0, N, (B, P, S), device=cuda, dtype=torch.int32)
+    out = ops.group_rows(feats, idx)
+    fr = feats.detach().clone().requires_grad_(True)
+    ref = torch.gather(fr[:, None].expand(B, P, N, C), 2, idx.long()[..., None].expand(B, P, S, C))
+    assert torch.equal(out, ref)
+    pooled = ops.maxpool_rows(out.reshape(B * P, S, C))
+    rp = ref.reshape(B * P, S, C).max(dim=1).values
+    assert torch.equal(pooled, rp)
+    go = torch.randn_like(pooled)
+    pooled.backward(go)
+    rp.backward(go)
+    _close(feats.grad, fr.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_bf16_storage_variants(cuda):
+    """Same kernels with bf16 activations (fp32 arithmetic): agree with fp32 up to bf16 rounding."""
+    from pose2room_b200 import ops
+    x = torch.randn(2048, 64, device=cuda)
+    w = torch.randn(64, 64, device=cuda) / 8
+    y32 = ops.linear(x, w)
+    y16 = ops.linear(x.bfloat16(), w)
+    assert y16.dtype == torch.bfloat16
+    _close(y16, y32, rtol=2e-2, atol=2e-2)
+    bn = nn.BatchNorm1d(64).to(cuda)
+    z16 = ops.batchnorm_act(y16, bn, relu=True)
+    bn2 = nn.BatchNorm1d(64).to(cuda)
+    z32 = ops.batchnorm_act(y32, bn2, relu=True)
+    _close(z16, z32, rtol=3e-2, atol=3e-2)

@@ -1,0 +1,114 @@
+"""GPU parity of the whole hot path: pose2room_b200.p2rnet.P2RNet (fp32 parity mode) against goldens produced
+by the UNMODIFIED reference model on the same seeded inputs and weights.
+
+Tolerances (north_star): indices (seed_inds, FPS picks, NMS mask) bit-exact; centre / size / heading and the
+other float outputs within 1e-4 absolute; losses within 1e-4 relative; gradients within 2e-3 of the tensor's
+largest entry (fp32 accumulation order differs: one fused GEMM vs conv + einsum)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import model_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return H.load_golden()
+
+
+def _check_endpoints(ep, golden, prefix):
+    for k in H.EP_KEYS:
+        want = golden[prefix + k]
+        got = ep[k].detach().cpu().numpy()
+        if want.dtype.kind in "iu":
+            assert np.array_equal(got, want), k
+        else:
+            assert got.dtype == want.dtype, (k, got.dtype, want.dtype)
+            assert np.abs(got - want).max() < 1e-4, (k, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("name", ["small", "ref53", "bl"])
+def test_train_forward_loss_backward(cuda, golden, name):
+    net = H.make_product(name, "train", golden).to(cuda)
+    net.train()
+    data = H.make_data(name, cuda)
+    ep = net(data)
+    _check_endpoints(ep, golden, name + "_train_")
+    for k in ["seed_features", "vote_features"]:
+        head = ep[k].detach()[:, :4, :32].cpu().numpy()
+        assert np.abs(head - golden["%s_train_%s_head" % (name, k)]).max() < 1e-4, k
+        t = ep[k].detach().double()
+        stats = np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+        assert np.allclose(stats, golden["%s_train_%s_stats" % (name, k)], rtol=1e-4, atol=1e-2), k
+    loss = net.loss(ep, data)
+    assert set(loss) == {"total", "vote_loss", "objectness_loss", "center_loss", "size_loss", "heading_loss",
+                         "sem_cls_loss", "pos_ratio", "neg_ratio", "obj_acc"}
+    for k, v in loss.items():
+        want = float(golden["%s_loss_%s" % (name, k)])
+        assert abs(v.item() - want) < 1e-4 * max(1.0, abs(want)), (k, v.item(), want)
+    loss["total"].backward()
+    params = dict(net.named_parameters())
+    for key in [k for k in golden.files if k.startswith(name + "_grad_")]:
+        pk = key[len(name) + 6:]
+        want = golden[key]
+        got = params[pk].grad.cpu().numpy()
+        assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max() + 1e-7, (pk, np.abs(got - want).max(), np.abs(want).max())
+    keys = list(golden["%s_gradnorm_keys" % name])
+    vals = golden["%s_gradnorm_vals" % name]
+    for k, want in zip(keys, vals):
+        k = str(k)
+        g = params[k].grad
+        got = g.double().norm().item() if g is not None else -1.0
+        assert abs(got - want) <= 5e-3 * abs(want) + 1e-6, (k, got, want)
+    sd = net.state_dict()
+    for key in [k for k in golden.files if k.startswith(name + "_after_")]:
+        pk = key[len(name) + 7:]
+        assert np.allclose(sd[pk].cpu().numpy(), golden[key], rtol=1e-4, atol=1e-5), pk
+
+
+@pytest.mark.parametrize("name", ["small", "ref53", "bl"])
+def test_generate_eval_path(cuda, golden, name):
+    net = H.make_product(name, "test", golden).to(cuda)
+    net.eval()
+    data = H.make_data(name, cuda)
+    with torch.no_grad():
+        ep, eval_dict, parsed = net.generate(data)
+    _check_endpoints(ep, golden, name + "_gen_")
+    assert np.array_equal(eval_dict["pred_mask"], golden["%s_gen_pred_mask" % name])
+    assert np.abs(parsed["pred_corners_3d"] - golden["%s_gen_corners" % name]).max() < 1e-4
+    assert np.abs(parsed["obj_prob"] - golden["%s_gen_obj_prob" % name]).max() < 1e-5
+    assert [len(x) for x in eval_dict["batch_pred_map_cls"]] == golden["%s_gen_npred" % name].tolist()
+    assert len(eval_dict["batch_gt_map_cls"]) == data["input_joints"].shape[0]
+    assert set(ep["pi"]) == {"center", "size", "heading"}
+
+
+def test_product_vs_oracle_fresh_inputs(cuda, golden):
+    """Beyond the committed goldens: a new seed, product (GPU) vs the CPU oracle port, train step."""
+    from oracle.model_ref import RefP2RNet
+    from pose2room_b200 import synthetic
+    name = "small"
+    B, T, J, S, P = H.CONFIGS[name]
+    net = H.make_product(name, "train", golden).to(cuda)
+    net.train()
+    ref = RefP2RNet({k: v.cpu() for k, v in net.state_dict().items()}, joint_num=J, num_seeds=S, num_target=P)
+    data = synthetic.make_batch(3, 200, J, seed=77)
+    ep_r = ref.forward(data)
+    loss_r = ref.loss(ep_r, data)
+    data_g = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in data.items()}
+    ep = net(data_g)
+    loss = net.loss(ep, data_g)
+    for k in H.EP_KEYS:
+        a, b = ep[k].detach().cpu(), ep_r[k].detach()
+        if a.dtype in (torch.int64, torch.int32):
+            assert torch.equal(a, b), k
+        else:
+            assert (a - b).abs().max() < 1e-4, (k, (a - b).abs().max())
+    assert abs(loss["total"].item() - loss_r["total"].item()) < 1e-4 * abs(loss_r["total"].item())
+
+
+def test_cpu_input_fails_loudly(golden):
+    net = H.make_product("small", "train", golden)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net(H.make_data("small"))
