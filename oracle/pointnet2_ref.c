@@ -12,9 +12,12 @@
  *
  * Floating point: the reference is compiled by nvcc with default -fmad=true; the SASS of the
  * reference built for sm_100a (oracle/build_ref_ext.py; cuobjdump -sass) evaluates
- *     (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f)
- * as  FMUL t=dx*dx ; FFMA t=dy*dy+t ; FFMA t=dz*dz+t.  sqdist3() reproduces exactly that with
- * fmaf(), so index decisions (strict < and > compares) agree bit for bit.
+ *     (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f)          [x, y, z terms in source order]
+ * as  FMUL t=dy*dy ; FFMA t=dx*dx+t ; FFMA t=dz*dz+t   (the compiler fuses the FIRST product of each
+ * addition into the FMA, so the SECOND product of the first addition is the plain multiply; checked on
+ * the loads' address offsets in ball_query, three_nn and FPS; three_interpolate likewise evaluates
+ * p1*w1 + p2*w2 + p3*w3 as t=p2*w2 ; t=fma(p1,w1,t) ; t=fma(p3,w3,t)).  sqdist3() reproduces exactly that
+ * with fmaf(), so index decisions (strict < and > compares) AND the returned distances agree bit for bit.
  *
  * Pinning: the reference's own tests hold no golden vectors for these ops;
  * the pin is the reference kernels themselves, run on the GPU box from oracle/_ref/ and compared
@@ -30,8 +33,8 @@
 
 static inline float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
   float dx = ax - bx, dy = ay - by, dz = az - bz;
-  float t = dx * dx;
-  t = fmaf(dy, dy, t);
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
   t = fmaf(dz, dz, t);
   return t;
 }
@@ -73,8 +76,8 @@ void p2r_ref_furthest_point_sampling(int b, int n, int m, const float *dataset, 
       for (int k = 0; k < n; ++k) {
         int t = k % bs;
         float x2 = pts[k * 3 + 0], y2 = pts[k * 3 + 1], z2 = pts[k * 3 + 2];
-        float mag = x2 * x2;
-        mag = fmaf(y2, y2, mag);
+        float mag = y2 * y2;
+        mag = fmaf(x2, x2, mag);
         mag = fmaf(z2, z2, mag);
         if ((double)mag <= 1e-3) continue;
         float d = sqdist3(x2, y2, z2, x1, y1, z1);
@@ -202,7 +205,7 @@ void p2r_ref_three_nn(int b, int n, int m, const float *unknown, const float *kn
 }
 
 /* interpolate_gpu.cu:72-101: out[b,c,j] = p[i1]*w1 + p[i2]*w2 + p[i3]*w3
- * (nvcc: FMUL, FFMA, FFMA left to right). */
+ * (nvcc: t = p2*w2; t = fma(p1,w1,t); t = fma(p3,w3,t)). */
 void p2r_ref_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx,
                                const float *weight, float *out) {
   for (int bi = 0; bi < b; ++bi)
@@ -210,8 +213,8 @@ void p2r_ref_three_interpolate(int b, int c, int m, int n, const float *points, 
       for (int j = 0; j < n; ++j) {
         size_t o = ((size_t)bi * n + j) * 3;
         const float *p = points + ((size_t)bi * c + l) * m;
-        float t = p[idx[o + 0]] * weight[o + 0];
-        t = fmaf(p[idx[o + 1]], weight[o + 1], t);
+        float t = p[idx[o + 1]] * weight[o + 1];
+        t = fmaf(p[idx[o + 0]], weight[o + 0], t);
         t = fmaf(p[idx[o + 2]], weight[o + 2], t);
         out[((size_t)bi * c + l) * n + j] = t;
       }

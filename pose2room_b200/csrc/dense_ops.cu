@@ -170,7 +170,7 @@ colreduce_kernel(long long M, int C, const T* __restrict__ x, const T* __restric
     const int c = cbase + cl;
     float a1 = 0.f, a2 = 0.f;
     float mu = 0.f, rs = 1.f;
-    if (MODE == 1) { mu = __ldg(mean + c); rs = __ldg(rstd + c); }
+    if (MODE == 1 && mean != nullptr) { mu = __ldg(mean + c); rs = __ldg(rstd + c); }
     for (long long r = r0 + r_lane; r < r1; r += rl) {
       const size_t o = (size_t)r * C + c;
       if (MODE == 0) {

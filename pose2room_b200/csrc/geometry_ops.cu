@@ -135,7 +135,7 @@ uniform_seed_kernel(int T, int S, int stride, const float* __restrict__ hip, lon
       const float dx = __fsub_rn(__ldg(h + (size_t)t * stride), __ldg(h + (size_t)(t - 1) * stride));
       const float dy = __fsub_rn(__ldg(h + (size_t)t * stride + 1), __ldg(h + (size_t)(t - 1) * stride + 1));
       const float dz = __fsub_rn(__ldg(h + (size_t)t * stride + 2), __ldg(h + (size_t)(t - 1) * stride + 2));
-      d = __fsqrt_rn(p2r_sqnorm3(dx, dy, dz));
+      d = __fsqrt_rn(p2r_sqnorm3_xyz(dx, dy, dz));
     }
     s_cum[t] = d;
   }

@@ -25,16 +25,20 @@ static inline int p2r_ceil_div(long long a, long long b) { return (int)((a + b -
 
 // ---- exact-order fp32 arithmetic -----------------------------------------------------------
 // The reference's kernels are compiled with nvcc's default -fmad=true; its SASS for sm_100a
-// evaluates (a-b)^2+(c-d)^2+(e-f)^2 as FMUL, FFMA, FFMA (see oracle/pointnet2_ref.c header).
-// The intrinsics pin that order regardless of how this translation unit is optimised.
-__device__ __forceinline__ float p2r_sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
-  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
-  float t = __fmul_rn(dx, dx);
-  t = __fmaf_rn(dy, dy, t);
-  t = __fmaf_rn(dz, dz, t);
+// evaluates dx*dx + dy*dy + dz*dz as  t = dy*dy (FMUL); t = fma(dx,dx,t); t = fma(dz,dz,t)
+// (see oracle/pointnet2_ref.c header).  The intrinsics pin that order regardless of how this
+// translation unit is optimised, so distances are bit-identical with the reference kernels.
+__device__ __forceinline__ float p2r_sqnorm3(float x, float y, float z) {
+  float t = __fmul_rn(y, y);
+  t = __fmaf_rn(x, x, t);
+  t = __fmaf_rn(z, z, t);
   return t;
 }
-__device__ __forceinline__ float p2r_sqnorm3(float x, float y, float z) {
+__device__ __forceinline__ float p2r_sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  return p2r_sqnorm3(__fsub_rn(ax, bx), __fsub_rn(ay, by), __fsub_rn(az, bz));
+}
+// torch's CPU vector norm over 3 components: sqrt(fma(z,z, fma(y,y, x*x))) (measured)
+__device__ __forceinline__ float p2r_sqnorm3_xyz(float x, float y, float z) {
   float t = __fmul_rn(x, x);
   t = __fmaf_rn(y, y, t);
   t = __fmaf_rn(z, z, t);

@@ -443,8 +443,8 @@ three_interpolate_kernel(int c, int m, int n, int c_per_cta, const float* __rest
   for (int l = c0; l < c1; ++l) {
     if (!GRAD) {
       const float* p = src + ((size_t)b * c + l) * m;
-      float t = __fmul_rn(__ldg(p + i1), w1);
-      t = __fmaf_rn(__ldg(p + i2), w2, t);
+      float t = __fmul_rn(__ldg(p + i2), w2);  // reference SASS order: p2*w2, fma(p1,w1,.), fma(p3,w3,.)
+      t = __fmaf_rn(__ldg(p + i1), w1, t);
       t = __fmaf_rn(__ldg(p + i3), w3, t);
       dst[((size_t)b * c + l) * n + j] = t;
     } else {

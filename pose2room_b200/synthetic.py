@@ -130,6 +130,9 @@ def deterministic_state_dict(reference_state_dict, seed=0):
             out[k] = 0.1 * torch.randn(v.shape, generator=g) / float(v[0].numel()) ** 0.5
         elif k.endswith(".mdn.pi.conv.bias"):
             out[k] = -4.6 + 0.05 * torch.randn(v.shape, generator=g)
+        elif k.endswith("conv_sem_obj.2.conv.weight"):
+            # wide objectness / class logits: NMS order must not hinge on 1-ulp score differences
+            out[k] = 8.0 * torch.randn(v.shape, generator=g) / float(v[0].numel()) ** 0.5
         elif k.endswith("bias"):
             out[k] = 0.1 * torch.randn(v.shape, generator=g)
         else:  # conv / linear weights

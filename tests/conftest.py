@@ -41,4 +41,6 @@ def cuda():
         pytest.skip("no CUDA device")
     from pose2room_b200 import _lib
     _lib.load()  # fail loudly if the extension is missing on a GPU box
+    torch.backends.cuda.matmul.allow_tf32 = False   # torch references in the tests must be true fp32
+    torch.backends.cudnn.allow_tf32 = False
     return torch.device("cuda:0")

@@ -194,7 +194,9 @@ def test_python_operator_api_vs_reference_goldens(cuda, golden_pointnet2):
     (nf * torch.from_numpy(g["qg_w"]).to(cuda)).sum().backward()
     assert np.allclose(feats.grad.cpu().numpy(), g["qg_feats_grad"], rtol=1e-5, atol=1e-6)
     dist, idx = pu.three_nn(xyz, new_xyz)
-    assert np.array_equal(idx.cpu().numpy(), g["tnn_idx"]) and np.array_equal(dist.cpu().numpy(), g["tnn_dist"])
+    assert np.array_equal(idx.cpu().numpy(), g["tnn_idx"])
+    # dist = torch.sqrt(dist2): torch's CUDA sqrt is not the correctly rounded CPU sqrt (glue, same in the reference)
+    assert np.allclose(dist.cpu().numpy(), g["tnn_dist"], rtol=3e-7, atol=0)
     kf = torch.from_numpy(g["ti_kfeat"]).to(cuda).requires_grad_(True)
     out = pu.three_interpolate(kf, idx, torch.from_numpy(g["ti_weight"]).to(cuda))
     assert np.array_equal(out.detach().cpu().numpy(), g["ti_out"])
