@@ -34,6 +34,28 @@ def _splits_for(out_rows, out_cols, reduce_dim):
 # gemm backend hook: gemm_sm100 installs a tensor-core implementation for bf16 operands here
 _TC_GEMM = {"fn": None}
 
+# optional per-GEMM device timing (bench.py's roofline leg): when PROFILE["on"], every GEMM launched through
+# linear() is bracketed by CUDA events on the launching stream and logged as (tag, M, N, K, ev0, ev1).
+PROFILE = {"on": False, "log": []}
+
+
+class _Timed:
+    def __init__(self, tag, m, n, k):
+        self.rec = (tag, m, n, k)
+
+    def __enter__(self):
+        if PROFILE["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE["on"]:
+            self.e1.record()
+            PROFILE["log"].append(self.rec + (self.e0, self.e1))
+        return False
+
 
 def sgemm(a, b, trans_a=False, trans_b=True, bias=None, relu=False, out_dtype=None, splits=1, out=None):
     """C = op(a) @ op(b) (+bias)(ReLU) with the SIMT fp32-accumulate kernel (see include/p2r_b200.h)."""
@@ -76,10 +98,11 @@ class _Linear(Function):
     def forward(ctx, x, weight, bias, relu):
         x = x if x.is_contiguous() else x.contiguous()
         tc = _TC_GEMM["fn"]
-        if tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
-            y = tc.linear_fwd(x, weight, bias, relu)
-        else:
-            y = sgemm(x, weight, False, True, bias, relu, out_dtype=x.dtype)
+        with _Timed("fwd", x.shape[0], weight.shape[0], x.shape[1]):
+            if tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
+                y = tc.linear_fwd(x, weight, bias, relu)
+            else:
+                y = sgemm(x, weight, False, True, bias, relu, out_dtype=x.dtype)
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.relu = relu
         ctx.has_bias = bias is not None
@@ -101,12 +124,14 @@ class _Linear(Function):
         tc = _TC_GEMM["fn"]
         use_tc = tc is not None and x.dtype == torch.bfloat16 and tc.supports(m, n, k)
         if ctx.needs_input_grad[0]:
-            dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
+            with _Timed("dx", m, n, k):
+                dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
         if ctx.needs_input_grad[1]:
-            if use_tc:
-                dw = tc.linear_dw(dz, x)
-            else:
-                dw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
+            with _Timed("dw", m, n, k):
+                if use_tc:
+                    dw = tc.linear_dw(dz, x)
+                else:
+                    dw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _col_sum(dz)
         return dx, dw, db, None
