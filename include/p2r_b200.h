@@ -145,6 +145,14 @@ int p2r_maxpool_rows(const void* x, int dtype, long long R, int S, int C, void* 
 int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg, long long R, int S, int C, void* dx,
                           void* stream);
 
+/* bf16 tensor-core GEMM (tcgen05 + TMA + TMEM), the throughput-mode backend of every dense layer, above all the
+ * fused graph-convolution GEMM that replaces conv 64->704 + einsum (ref: stgcn_layers.py:58-67).
+ * C[M,N] (+)= op(A).op(B)^T, fp32 accumulate.  a_mn = 0: A is [M,K] row-major, 1: [K,M]; b_mn = 0: B is [N,K]
+ * row-major (nn.Linear weight layout), 1: [K,N].  c_dtype 0 = fp32, 1 = bf16.  splits > 1: split-K with fp32
+ * atomics into zeroed C.  block_n in {0 = auto, 64, 128, 160, 256}.  Pointers 16-byte aligned, pitches % 8 == 0. */
+int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                  int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

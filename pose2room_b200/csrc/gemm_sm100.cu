@@ -1,0 +1,366 @@
+// gemm_sm100.cu -- bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared
+// memory -> tcgen05.mma (accumulator in TMEM) -> tcgen05.ld epilogue.  This is the kernel behind every dense
+// per-point layer of the P2RNet hot path in throughput mode, above all the fused graph-convolution GEMM
+// (M = B*T frames, N = K = V*64) that replaces the reference's 1x1 conv 64->704 + einsum 'nkctv,kvw->nctw'
+// (/root/reference/models/p2rnet/modules/stgcn_layers.py:58-67).
+//
+//   C[M,N] (+)= A . B^T,   fp32 accumulate, C in bf16 or fp32, optional bias[N], optional ReLU.
+//   A is given either K-major ([M,K] row-major) or MN-major ([K,M] row-major),
+//   B is given either K-major ([N,K] row-major, the nn.Linear weight layout) or MN-major ([K,N] row-major);
+//   with these four combinations forward (x.W^T), input gradient (dy.W) and weight gradient (dy^T.x) all run
+//   on the same kernel without materialising a transpose.
+//
+// Structure (one 128 x BLOCK_N output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- one elected lane issues the bulk-tensor loads of the next k-block into a
+//              STAGES-deep ring, completion signalled on full[] mbarriers (expect_tx)
+//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues 4 x tcgen05.mma (K=16 each) per
+//              64-wide k-block, tcgen05.commit releases the smem stage (empty[]) and finally signals tmem_full
+//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns at a time, bias/ReLU/convert, 16-byte global stores
+//              (or fp32 atomics for split-K)
+// Two CTAs are co-resident per SM (smem <= 110 KB, TMEM <= 256 columns each) so one CTA's epilogue overlaps
+// the other's main loop.
+#include "p2r_common.cuh"
+#include <cuda.h>
+
+#define GEMM_BLOCK_M 128
+#define GEMM_BLOCK_K 64
+#define GEMM_THREADS 192
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          p2r_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(p2r_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p2r_smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(p2r_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address [0,14) (>>4),
+// leading byte offset [16,30) (>>4), stride byte offset [32,46) (>>4), version = 1 at [46,48),
+// layout type [61,64) = 2 (SWIZZLE_128B).
+//  K-major tile  [rows][64 bf16]: 128-byte rows, 8-row groups 1024 B apart -> SBO = 1024, LBO field = 1.
+//  MN-major tile [MN/64][BLOCK_K][64 bf16]: 128-byte k-rows, 8-k groups 1024 B apart (SBO), 64-wide MN blocks
+//  BLOCK_K*128 B apart (LBO).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b format BF16 = 1 @7/@10,
+// a_major @15, b_major @16 (1 = MN-major), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 OutT* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ bias, int relu,
+                 int kblocks_per_split) {
+  using S = GemmSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tmem_full = empty + S::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * GEMM_BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int kb0 = blockIdx.z * kblocks_per_split;
+  const int kb1 = min(total_kb, kb0 + kblocks_per_split);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      p2r_mbar_init(full + s, 1);
+      p2r_mbar_init(empty + s, 1);
+    }
+    p2r_mbar_init(tmem_full, 1);
+    p2r_fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S::STAGES;
+        const uint32_t ph = (uint32_t)(i / S::STAGES) & 1u;
+        p2r_mbar_wait(empty + s, ph ^ 1u);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + S::A_BYTES;
+        p2r_mbar_expect_tx(full + s, S::STAGE_BYTES);
+        const int k0 = (kb0 + i) * GEMM_BLOCK_K;
+        if (!A_MN) {
+          tma_load_2d(a_dst, &tma_a, full + s, k0, m0);                 // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int h = 0; h < GEMM_BLOCK_M / 64; ++h)                   // boxes {64 m, 64 k}
+            tma_load_2d(a_dst + h * (GEMM_BLOCK_K * 128), &tma_a, full + s, m0 + h * 64, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(b_dst, &tma_b, full + s, k0, n0);                 // box {64 k, BLOCK_N n}
+        } else {
+#pragma unroll
+          for (int h = 0; h < BLOCK_N / 64; ++h)                        // boxes {64 n, 64 k}
+            tma_load_2d(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, n0 + h * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(GEMM_BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S::STAGES;
+        const uint32_t ph = (uint32_t)(i / S::STAGES) & 1u;
+        p2r_mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = p2r_smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+          const uint64_t adesc = A_MN ? make_desc(a_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
+                                      : make_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_desc(b_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
+                                      : make_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty + s);  // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    p2r_mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const bool row_ok = row < M;
+    OutT* crow = C + (size_t)row * ldc;
+    const bool vec_ok = ((size_t)ldc * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const int col0 = n0 + c0;
+      if (row_ok && col0 < N) {  // (no `continue`: the next tcgen05.ld is warp-aligned)
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (!ATOMIC) {
+          if (bias != nullptr && col0 + j < N) x += __ldg(bias + col0 + j);
+          if (relu) x = fmaxf(x, 0.f);
+        }
+        f[j] = x;
+      }
+      if (ATOMIC) {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) atomicAdd(reinterpret_cast<float*>(crow) + col0 + j, f[j]);
+      } else if (vec_ok && col0 + 32 <= N) {
+        if (sizeof(OutT) == 2) {
+          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            dst[j] = pk;
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) {
+            if (sizeof(OutT) == 2) reinterpret_cast<__nv_bfloat16*>(crow)[col0 + j] = __float2bfloat16_rn(f[j]);
+            else reinterpret_cast<float*>(crow)[col0 + j] = f[j];
+          }
+      }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, `ld` elements between rows,
+// box {64 inner, box_outer}, 128-byte swizzle, zero fill outside the tensor.
+static int make_map(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { p2r_set_last_error("p2r_gemm_bf16: cuTensorMapEncodeTiled entry point unavailable", -1); return -1; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    p2r_set_last_error("p2r_gemm_bf16: cuTensorMapEncodeTiled failed (pointer must be 16-byte aligned, row pitch a multiple of 16 bytes)", -1);
+    return -1;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, int M, int N,
+                       int K, const float* bias, int relu, int splits, cudaStream_t st) {
+  using S = GemmSmem<BLOCK_N>;
+  CUtensorMap ma, mb;
+  // K-major: rows = M (or N), inner = K.   MN-major: rows = K, inner = M (or N).
+  if (make_map(&ma, A, A_MN ? M : K, A_MN ? K : M, lda, A_MN ? GEMM_BLOCK_K : GEMM_BLOCK_M)) return -1;
+  if (make_map(&mb, B, B_MN ? N : K, B_MN ? K : N, ldb, B_MN ? GEMM_BLOCK_K : BLOCK_N)) return -1;
+  const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  int kps = total_kb;
+  if (splits > 1) {
+    kps = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kps - 1) / kps;
+  } else splits = 1;
+  dim3 grid(p2r_ceil_div(N, BLOCK_N), p2r_ceil_div(M, GEMM_BLOCK_M), splits);
+#define GEMM_GO(OutT, ATOMIC)                                                                                   \
+  do {                                                                                                          \
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC>;                                            \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);                          \
+    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps);                \
+  } while (0)
+  if (splits > 1) GEMM_GO(float, true);
+  else if (c_dtype == 1) GEMM_GO(__nv_bfloat16, false);
+  else GEMM_GO(float, false);
+#undef GEMM_GO
+  P2R_RETURN_LAUNCH("p2r_gemm_bf16");
+}
+
+// C[M,N] (+)= op(A) . op(B)^T with bf16 operands (see file header).
+//   a_mn = 0: A is [M,K] row-major (lda);  a_mn = 1: A is [K,M] row-major (lda)
+//   b_mn = 0: B is [N,K] row-major (ldb);  b_mn = 1: B is [K,N] row-major (ldb)
+//   c_dtype 0 = fp32, 1 = bf16;  splits > 1: split-K, fp32 atomics into a zero-filled C (no bias / ReLU)
+//   block_n in {64, 128, 160, 256} (160 only with b_mn = 0); 0 = choose.
+extern "C" int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
+                             void* C, int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n,
+                             void* stream) {
+  P2R_CHECK_ARG(M > 0 && N > 0 && K > 0, "p2r_gemm_bf16");
+  P2R_CHECK_ARG(!(splits > 1 && (c_dtype != 0 || bias || relu)), "p2r_gemm_bf16 (split-K needs fp32 C, no epilogue)");
+  P2R_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "p2r_gemm_bf16 (row pitches must be multiples of 8 bf16 = 16 bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_n == 0) {
+    if (!b_mn && N % 160 == 0 && N >= 640) block_n = 160;
+    else if (N <= 64) block_n = 64;
+    else if (N <= 128 || (N % 256 != 0 && N % 128 == 0) || N < 512) block_n = 128;
+    else block_n = 256;
+  }
+  P2R_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256 || (block_n == 160 && !b_mn), "p2r_gemm_bf16 block_n");
+#define GEMM_DISPATCH(BN)                                                                                          \
+  do {                                                                                                             \
+    if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st); \
+    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);  \
+    if (a_mn && !b_mn) return launch_gemm<BN, true, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);  \
+    return launch_gemm<BN, true, true>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);          \
+  } while (0)
+  if (block_n == 64) GEMM_DISPATCH(64);
+  if (block_n == 128) GEMM_DISPATCH(128);
+  if (block_n == 256) GEMM_DISPATCH(256);
+  // 160: K-major B only
+  if (!a_mn) return launch_gemm<160, false, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);
+  return launch_gemm<160, true, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);
+#undef GEMM_DISPATCH
+}

@@ -1,0 +1,83 @@
+"""Throughput-mode GEMM backend: routes the dense layers' bf16 GEMMs to the tcgen05/TMA kernel of
+csrc/gemm_sm100.cu (C ABI `p2r_gemm_bf16`).  `install()` hooks it into pose2room_b200.ops.linear so that
+forward (x.W^T), input gradient (dy.W) and weight gradient (dy^T.x) of every layer with bf16 activations run on
+the tensor cores; layers the kernel cannot take (K or N not a multiple of 8, tiny K) stay on the SIMT kernel."""
+import torch
+
+from . import _lib, ops
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def available():
+    if not torch.cuda.is_available():
+        return False
+    major, _ = torch.cuda.get_device_capability()
+    return major == 10 and hasattr(_lib.load(), "p2r_gemm_bf16")
+
+
+def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bfloat16, splits=1, block_n=0):
+    """C[M,N] = op(a) @ op(b)^T.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); bf16, contiguous rows."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    k, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
+    kb, n = (b.shape[0], b.shape[1]) if b_mn else (b.shape[1], b.shape[0])
+    assert k == kb, (a.shape, b.shape, a_mn, b_mn)
+    if splits > 1:
+        c = torch.zeros(m, n, dtype=torch.float32, device=a.device)
+    else:
+        c = torch.empty(m, n, dtype=out_dtype, device=a.device)
+    if bias is not None:
+        bias = bias.float().contiguous()
+    with torch.cuda.device(a.device):
+        _lib.call("p2r_gemm_bf16", m, n, k, a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+                  c.data_ptr(), c.stride(0), 1 if c.dtype == torch.bfloat16 else 0,
+                  bias.data_ptr() if bias is not None else None, int(relu), int(splits), int(block_n), _stream())
+    return c
+
+
+class _Backend:
+    """Interface expected by ops._Linear (see ops._TC_GEMM)."""
+
+    @staticmethod
+    def supports(m, n, k):
+        # TMA needs 16-byte row pitches for every operand in every role (x:[M,K], w:[N,K], dy:[M,N])
+        return k % 8 == 0 and n % 8 == 0 and k >= 32 and m >= 128
+
+    @staticmethod
+    def linear_fwd(x, weight, bias, relu):
+        return gemm(x, weight.to(torch.bfloat16), False, False, bias, relu, out_dtype=torch.bfloat16)
+
+    @staticmethod
+    def linear_dx(dz, weight):
+        # dx[M,K] = dz[M,N] . W[N,K]:  A = dz (K-major over n), B = W viewed as [K_red = N, N_out = K] -> MN-major
+        w = weight.to(torch.bfloat16)
+        n_out = w.shape[1]
+        bn = 0 if n_out % 64 == 0 or n_out > 256 else 0
+        return gemm(dz, w, False, True, out_dtype=torch.bfloat16, block_n=bn)
+
+    @staticmethod
+    def linear_dw(dz, x):
+        # dW[N,K] = dz^T[N,M] . x[M,K]: both operands MN-major (reduction over the row index m)
+        m = dz.shape[0]
+        n, k = dz.shape[1], x.shape[1]
+        tiles = ((n + 127) // 128) * ((k + 127) // 128)
+        splits = max(1, min((296 + tiles - 1) // tiles, (m + 4095) // 4096))
+        return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits)
+
+    @staticmethod
+    def supports_tconv(shape, co):
+        return False
+
+
+def install():
+    if not available():
+        raise RuntimeError("pose2room_b200.gemm_sm100: needs an sm_100 device and libp2r_b200.so")
+    ops._TC_GEMM["fn"] = _Backend
+    return _Backend
+
+
+def uninstall():
+    ops._TC_GEMM["fn"] = None
