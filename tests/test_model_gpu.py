@@ -121,3 +121,33 @@ def test_cpu_input_fails_loudly(golden):
     net = H.make_product("small", "train", golden)
     with pytest.raises(RuntimeError, match="no CPU path"):
         net(H.make_data("small"))
+
+
+def test_bf16_throughput_mode_tracks_fp32_reference(cuda, golden):
+    """Throughput mode (bf16 activations, tcgen05 GEMMs, fp32 accumulate / BN statistics / losses) against the
+    fp32 reference goldens.  bf16 rounding (2^-9 relative per activation) makes this a statistical check: the seed
+    sampling is untouched (exact), the loss must agree to a few percent, every output must be finite, and the box
+    tensors must stay within 5e-2 wherever the FPS picks (which depend on vote_xyz) coincide."""
+    from pose2room_b200 import gemm_sm100
+    gemm_sm100.install()
+    try:
+        for name in ["small", "bl"]:
+            net = H.make_product(name, "train", golden, precision="bf16").to(cuda)
+            net.train()
+            data = H.make_data(name, cuda)
+            ep = net(data)
+            assert np.array_equal(ep["seed_inds"].cpu().numpy(), golden[name + "_train_seed_inds"])
+            loss = net.loss(ep, data)
+            want = float(golden["%s_loss_total" % name])
+            assert abs(loss["total"].item() - want) < 0.08 * abs(want), (name, loss["total"].item(), want)
+            loss["total"].backward()
+            for k, p in net.named_parameters():
+                assert p.grad is None or torch.isfinite(p.grad).all(), k
+            same = ep["aggregated_vote_inds"].cpu().numpy() == golden[name + "_train_aggregated_vote_inds"]
+            assert same.mean() > 0.5, same.mean()
+            if same.all():
+                for k in ["center", "size", "heading"]:
+                    err = np.abs(ep[k].detach().cpu().numpy() - golden["%s_train_%s" % (name, k)]).max()
+                    assert err < 5e-2, (name, k, err)
+    finally:
+        gemm_sm100.uninstall()
