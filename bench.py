@@ -179,11 +179,11 @@ def main():
     net = P2RNet(cfg)
     net.load_state_dict(synthetic.deterministic_state_dict(net.state_dict(), seed=7))
     net = net.to(dev).train()
-    model = net
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], bucket_cap_mb=16,
-                                                          gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, fused=True)
+    if world > 1:  # identical replicas (same seed); make it explicit like DDP's initial broadcast
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, 0)
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-3, fused=True, capturable=True)
 
     B = args.batch
     host = synthetic.make_batch(B, T_FRAMES, JOINTS, seed=1234 + rank, pin=True)
@@ -192,12 +192,53 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in tensors.values())
 
     def step(data):
+        """forward + loss + backward (+ ONE flat gradient all-reduce over NCCL, the reference's DDP axis) + AdamW."""
         opt.zero_grad(set_to_none=True)
-        ep = model(data)
+        ep = net(data)
         loss = net.loss(ep, data)["total"]
         loss.backward()
+        if world > 1:
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
         opt.step()
         return loss
+
+    # ---- whole-step CUDA graph: ~3000 launches per step would otherwise be bound by the Python launch path ------
+    static = {k: torch.empty_like(v) for k, v in resident.items()}
+    for k in static:
+        static[k].copy_(resident[k])
+    graph, static_loss, use_graph = None, None, os.environ.get("P2R_CUDA_GRAPH", "1") != "0"
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step(static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_loss = step(static)
+            torch.cuda.synchronize()
+        except Exception as e:  # report, do not hide: the bench line says whether the graph was used
+            print("bench.py: CUDA graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
+            graph, use_graph = None, False
+    eager_step = step
+
+    def step(data):  # noqa: F811  (graph replay with the batch copied into the captured buffers)
+        if graph is None:
+            return eager_step(data)
+        if data is not static:
+            for k in static:
+                static[k].copy_(data[k], non_blocking=True)
+        graph.replay()
+        return static_loss
+    launches_per_step = None
 
     def barrier():
         if world > 1:
@@ -211,28 +252,41 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if graph is None:
+        l0 = _lib.LAUNCHES["count"]
+        eager_step(resident)
+        launches_per_step = _lib.LAUNCHES["count"] - l0
+    else:  # count once, eagerly, what the captured step launches through the C ABI
+        l0 = _lib.LAUNCHES["count"]
+        eager_step(static)
+        launches_per_step = _lib.LAUNCHES["count"] - l0
     for _ in range(max(args.warmup, 3)):
-        step(resident)
+        step(static)
     barrier()
 
     # ---- device-resident throughput -------------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    ops.PROFILE["log"] = []
-    ops.PROFILE["on"] = True
-    launches0 = _lib.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(resident)
+        step(static)
     e1.record()
     barrier()
-    ops.PROFILE["on"] = False
-    launches = _lib.LAUNCHES["count"] - launches0
+    launches = launches_per_step * args.steps
     ms = max_over_ranks(e0.elapsed_time(e1))
-    sampler.stop_flag = True
     value = world * B * args.steps / (ms * 1e-3)
+
+    # per-GEMM device times: the same steps run eagerly with CUDA events around every GEMM launch (events cannot
+    # be read back from inside a replayed graph); the clock sampler keeps running over both regions
+    ops.PROFILE["log"] = []
+    ops.PROFILE["on"] = True
+    for _ in range(min(args.steps, 3)):
+        eager_step(static)
+    torch.cuda.synchronize()
+    ops.PROFILE["on"] = False
+    sampler.stop_flag = True
 
     # ---- roofline of the dominant kernel: the fused graph-convolution GEMM (forward) -------------------
     vj = JOINTS * 64
@@ -249,19 +303,17 @@ def main():
                     "traffic": None, "kernel": "graph-conv GEMM fwd (M=%d,N=K=%d) %s" % (gcn[0][1], vj, precision),
                     "avg_launch_ms": t_ms, "launches_timed": len(gcn), "executed_tflops": exec_flops / (t_ms * 1e-3) / 1e12,
                     "peak_source": peaks["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
-                    "share_of_step": t_ms * len(gcn) / ms}
+                    "share_of_step": t_ms * 6 / (ms / args.steps)}
     ops.PROFILE["log"] = []
 
     # ---- end to end: pinned host batch -> H2D -> step -> loss read back --------------------------------
     for _ in range(2):
-        data = {k: v.to(dev, non_blocking=True) for k, v in tensors.items()}
-        step(data).item()
+        step(tensors).item()          # pinned host tensors -> H2D into the step's input buffers -> step -> loss D2H
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        data = {k: v.to(dev, non_blocking=True) for k, v in tensors.items()}
-        step(data).item()
+        step(tensors).item()
     f1.record()
     barrier()
     ms_e2e = max_over_ranks(f0.elapsed_time(f1))
@@ -282,7 +334,7 @@ def main():
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "P2RNet train step fwd+loss+bwd+AdamW (+grad all-reduce), B=%d/GPU, T=1024, J=25, "
                                    "512 seeds, 128 proposals, 22 classes" % B,
-                       "parallelism": "dp%d" % world, "precision": precision,
+                       "parallelism": "dp%d" % world, "precision": precision, "cuda_graph": graph is not None,
                        "l2": "no flush needed: per-layer activations (105-420 MB) exceed the 126 MB L2"},
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

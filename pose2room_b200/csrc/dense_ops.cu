@@ -21,6 +21,43 @@ template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p,
   *p = __float2bfloat16_rn(v);
 }
 
+
+// 16-byte vector access: 4 floats or 8 bf16 per thread per load/store (HBM-bound elementwise kernels)
+template <typename T> struct VecN;
+template <> struct VecN<float> { static constexpr int N = 4; };
+template <> struct VecN<__nv_bfloat16> { static constexpr int N = 8; };
+__device__ __forceinline__ void vload(const float* p, float (&f)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void vload(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void vstore(float* p, const float (&f)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+__device__ __forceinline__ void vstore(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 v;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  *reinterpret_cast<uint4*>(p) = v;
+}
+template <typename T> static inline bool vec_ok(int C, const void* a, const void* b = nullptr, const void* c = nullptr,
+                                                const void* d = nullptr, const void* e = nullptr) {
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return C % VecN<T>::N == 0 && al(a) && al(b) && al(c) && al(d) && al(e);
+}
+
 // ================================================================================================
 // SIMT GEMM:  C[M,N] (+)= op(A)[M,K] . op(B)[K,N]  (+ bias[N]) (ReLU)
 //   TRANS_A = false: A is [M,K] row-major (lda);  true: A is [K,M] row-major (lda)
@@ -197,6 +234,67 @@ colreduce_kernel(long long M, int C, const T* __restrict__ x, const T* __restric
   }
 }
 
+// Vectorised variant: thread = VEC consecutive channels of one row lane; C % VEC == 0, 256 % (C/VEC) == 0.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int rows_per_cta,
+                     double* __restrict__ s1, double* __restrict__ s2) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sh1[256 * V], sh2[256 * V];
+  const int tpr = C / V;            // threads per row
+  const int rl = 256 / tpr;         // row lanes
+  const int cl = threadIdx.x % tpr, r_lane = threadIdx.x / tpr;
+  const int c0 = cl * V;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(M, r0 + rows_per_cta);
+  float a1[V], a2[V], mu[V], rs[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    a1[i] = a2[i] = 0.f;
+    mu[i] = 0.f;
+    rs[i] = 1.f;
+    if (MODE == 1 && mean != nullptr) { mu[i] = __ldg(mean + c0 + i); rs[i] = __ldg(rstd + c0 + i); }
+  }
+  for (long long r = r0 + r_lane; r < r1; r += rl) {
+    const size_t o = (size_t)r * C + c0;
+    if (MODE == 0) {
+      float v[V];
+      vload(x + o, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a1[i] += v[i]; a2[i] = fmaf(v[i], v[i], a2[i]); }
+    } else {
+      float dz[V];
+      vload(dy + o, dz);
+      if (relu) {
+        float yy[V];
+        vload(y + o, yy);
+#pragma unroll
+        for (int i = 0; i < V; ++i) if (!(yy[i] > 0.f)) dz[i] = 0.f;
+      }
+      if (x != nullptr) {
+        float xx[V];
+        vload(x + o, xx);
+#pragma unroll
+        for (int i = 0; i < V; ++i) a2[i] = fmaf(dz[i], (xx[i] - mu[i]) * rs[i], a2[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) a1[i] += dz[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sh1[threadIdx.x * V + i] = a1[i]; sh2[threadIdx.x * V + i] = a2[i]; }
+  __syncthreads();
+  // one thread per channel finishes the reduction over the row lanes
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int t = c / V, i = c % V;
+    double t1 = 0.0, t2 = 0.0;
+    for (int l = 0; l < rl; ++l) { t1 += (double)sh1[(l * tpr + t) * V + i]; t2 += (double)sh2[(l * tpr + t) * V + i]; }
+    atomicAdd(s1 + c, t1);
+    if (s2) atomicAdd(s2 + c, t2);
+  }
+}
+
 static int colreduce_grid(long long M, int* rows_per_cta) {
   // ~4 CTAs per SM, at least 64 rows each
   long long target = (M + (long long)P2R_SM_COUNT * 4 - 1) / ((long long)P2R_SM_COUNT * 4);
@@ -211,10 +309,17 @@ extern "C" int p2r_col_stats(const void* x, int dtype, long long M, int C, doubl
   if (M == 0) return 0;
   int rpc;
   const int grid = colreduce_grid(M, &rpc);
-  if (dtype == 0)
-    colreduce_kernel<float, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
-  else
-    colreduce_kernel<__nv_bfloat16, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+  if (dtype == 0) {
+    if (vec_ok<float>(C, x) && 256 % (C / 4) == 0)
+      colreduce_vec_kernel<float, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+    else
+      colreduce_kernel<float, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+  } else {
+    if (vec_ok<__nv_bfloat16>(C, x) && 256 % (C / 8) == 0)
+      colreduce_vec_kernel<__nv_bfloat16, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+    else
+      colreduce_kernel<__nv_bfloat16, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, 0, rpc, s1, s2);
+  }
   P2R_RETURN_LAUNCH("p2r_col_stats");
 }
 
@@ -226,10 +331,17 @@ extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, i
   if (M == 0) return 0;
   int rpc;
   const int grid = colreduce_grid(M, &rpc);
-  if (dtype == 0)
-    colreduce_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2);
-  else
-    colreduce_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2);
+  if (dtype == 0) {
+    if (vec_ok<float>(C, x, dy, y) && 256 % (C / 4) == 0)
+      colreduce_vec_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2);
+    else
+      colreduce_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2);
+  } else {
+    if (vec_ok<__nv_bfloat16>(C, x, dy, y) && 256 % (C / 8) == 0)
+      colreduce_vec_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2);
+    else
+      colreduce_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2);
+  }
   P2R_RETURN_LAUNCH("p2r_col_bwd_stats");
 }
 
@@ -282,13 +394,39 @@ affine_act_kernel(long long total, int C, const T* __restrict__ x, const float* 
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_act_vec_kernel(long long nvec, int C, const T* __restrict__ x, const float* __restrict__ scale,
+                      const float* __restrict__ shift, const T* __restrict__ residual, int relu, T* __restrict__ y) {
+  constexpr int V = VecN<T>::N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
+    const size_t o = (size_t)e * V;
+    const int c0 = (int)(o % C);
+    float v[V], r[V];
+    vload(x + o, v);
+    if (residual) vload(residual + o, r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float t = fmaf(v[i], __ldg(scale + c0 + i), __ldg(shift + c0 + i));
+      if (residual) t += r[i];
+      v[i] = relu ? fmaxf(t, 0.f) : t;
+    }
+    vstore(y + o, v);
+  }
+}
+
 extern "C" int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift,
                               const void* residual, int relu, void* y, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_affine_act");
   const long long total = M * C;
   if (total == 0) return 0;
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
-  if (dtype == 0)
+  if (dtype == 0 && vec_ok<float>(C, x, residual, y))
+    affine_act_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
+  else if (dtype == 1 && vec_ok<__nv_bfloat16>(C, x, residual, y))
+    affine_act_vec_kernel<__nv_bfloat16><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 8, C, (const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y);
+  else if (dtype == 0)
     affine_act_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
   else
     affine_act_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, (const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y);
@@ -320,6 +458,43 @@ bn_bwd_apply_kernel(long long total, int C, double inv_m, const T* __restrict__ 
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict__ dy, const T* __restrict__ x,
+                        const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
+                        int relu, T* __restrict__ dx, T* __restrict__ dres) {
+  constexpr int V = VecN<T>::N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
+    const size_t o = (size_t)e * V;
+    const int c0 = (int)(o % C);
+    float dz[V];
+    vload(dy + o, dz);
+    if (relu) {
+      float yy[V];
+      vload(y + o, yy);
+#pragma unroll
+      for (int i = 0; i < V; ++i) if (!(yy[i] > 0.f)) dz[i] = 0.f;
+    }
+    if (dres) vstore(dres + o, dz);
+    float g[V];
+    if (s1) {
+      float xx[V];
+      vload(x + o, xx);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xh = (xx[i] - __ldg(mean + c0 + i)) * __ldg(rstd + c0 + i);
+        g[i] = (dz[i] - (float)(s1[c0 + i] * inv_m) - xh * (float)(s2[c0 + i] * inv_m)) * __ldg(scale + c0 + i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] = dz[i] * __ldg(scale + c0 + i);
+    }
+    vstore(dx + o, g);
+  }
+}
+
 extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
                                 const float* mean, const float* rstd, const float* scale, const double* s1,
                                 const double* s2, int relu, void* dx, void* dres, void* stream) {
@@ -327,7 +502,11 @@ extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, in
   const long long total = M * C;
   if (total == 0) return 0;
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
-  if (dtype == 0)
+  if (dtype == 0 && vec_ok<float>(C, dy, x, y, dx, dres))
+    bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres);
+  else if (dtype == 1 && vec_ok<__nv_bfloat16>(C, dy, x, y, dx, dres))
+    bn_bwd_apply_vec_kernel<__nv_bfloat16><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 8, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
+  else if (dtype == 0)
     bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres);
   else
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);

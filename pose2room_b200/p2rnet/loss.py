@@ -38,8 +38,14 @@ class Null(BaseLoss):
 class BoxNetDetectionLoss(BaseLoss):
     def __init__(self, weight, device, cfg=None):
         super().__init__(weight, device, cfg)
-        self._obj_w = torch.tensor(OBJECTNESS_CLS_WEIGHTS)
+        self._obj_w = {}  # per-device copy of the class weights (made once: no H2D copy inside a captured step)
         self._sem_ce = nn.CrossEntropyLoss(reduction="none")
+
+    def _objectness_weights(self, device):
+        key = str(device)
+        if key not in self._obj_w:
+            self._obj_w[key] = torch.tensor(OBJECTNESS_CLS_WEIGHTS, device=device)
+        return self._obj_w[key]
 
     def compute_vote_loss(self, est, gt):
         """loss.py:90-115: supervise each vote with the GT vote closest to any body joint of its seed."""
@@ -71,7 +77,7 @@ class BoxNetDetectionLoss(BaseLoss):
         objectness_mask = (near | (dist > FAR_THRESHOLD)).float()
         scores = est["objectness_scores"]
         ce = nn.functional.cross_entropy(scores.transpose(2, 1), objectness_label,
-                                         weight=self._obj_w.to(scores.device), reduction="none")
+                                         weight=self._objectness_weights(scores.device), reduction="none")
         objectness_loss = torch.sum(ce * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
         return assignment, objectness_loss, objectness_label, objectness_mask
 
