@@ -232,6 +232,8 @@ def main():
 
     def step(data):  # noqa: F811  (graph replay with the batch copied into the captured buffers)
         if graph is None:
+            if data is not static:
+                data = {k: v.to(dev, non_blocking=True) for k, v in data.items()}
             return eager_step(data)
         if data is not static:
             for k in static:

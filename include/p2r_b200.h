@@ -153,6 +153,13 @@ int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg,
 int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                   int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n, void* stream);
 
+/* (KT x 1) temporal convolution (zero padding (KT-1)/2) as an implicit tensor-core GEMM over the 3-D activation tensor
+ * [B, rows = T*V, C], a tap shifting by V rows; no unfold buffer (ref: st_gcn_block.tcn conv, stgcn_layers.py:405-411).
+ * mode 0: y = conv(x, W2[Co, KT*Ci]) (+bias); mode 1: dx from dy and Wt[KT*Co, Ci]; mode 2: dW2[Co, KT*Ci] (fp32,
+ * zeroed by the caller when splits > 1) from x (act) and dy (other).  rows % 128 == 0, Ci = Co = 64.               */
+int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows, int Ci,
+                   int Co, int KT, int V, const float* bias, int splits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(p2r_smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          p2r_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(p2r_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -100,22 +107,31 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BLOCK_N>
+// Temporal-tap addressing (the (3x1) temporal convolution of st_gcn_block.tcn as an implicit GEMM, no unfold):
+//   TAP = 1: A is a 3-D tensor (C, rows_per_sample, samples); k-block i belongs to tap i / kb_per_tap and reads the
+//            A rows shifted by tap_shift0 + tap * tap_shift_step; rows outside a sample are zero-filled by TMA.
+//   TAP = 2: B (MN-major) is that 3-D tensor; the 64-wide n-block n selects tap n / C and channel offset n % C,
+//            and the reduction rows (k) are shifted per tap.
+struct TapArgs {
+  int kb_per_tap, rows_per_sample, channels, shift0, shift_step;
+};
+
+template <int BLOCK_N, int STAGES_OVERRIDE = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 3 : 4);
+  static constexpr int STAGES = STAGES_OVERRIDE > 0 ? STAGES_OVERRIDE : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 3 : 4));
   static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC>
+template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP = 0, int NSTAGE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  OutT* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ bias, int relu,
-                 int kblocks_per_split) {
-  using S = GemmSmem<BLOCK_N>;
+                 int kblocks_per_split, const TapArgs tap) {
+  using S = GemmSmem<BLOCK_N, NSTAGE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
@@ -159,14 +175,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint8_t* b_dst = a_dst + S::A_BYTES;
         p2r_mbar_expect_tx(full + s, S::STAGE_BYTES);
         const int k0 = (kb0 + i) * GEMM_BLOCK_K;
-        if (!A_MN) {
+        if (TAP == 1) {
+          const int t = (kb0 + i) / tap.kb_per_tap;
+          const int kc = ((kb0 + i) % tap.kb_per_tap) * GEMM_BLOCK_K;
+          tma_load_3d(a_dst, &tma_a, full + s, kc, (m0 % tap.rows_per_sample) + tap.shift0 + t * tap.shift_step,
+                      m0 / tap.rows_per_sample);                        // box {64 c, 128 rows, 1 sample}
+        } else if (!A_MN) {
           tma_load_2d(a_dst, &tma_a, full + s, k0, m0);                 // box {64 k, 128 m}
         } else {
 #pragma unroll
           for (int h = 0; h < GEMM_BLOCK_M / 64; ++h)                   // boxes {64 m, 64 k}
             tma_load_2d(a_dst + h * (GEMM_BLOCK_K * 128), &tma_a, full + s, m0 + h * 64, k0);
         }
-        if (!B_MN) {
+        if (TAP == 2) {
+#pragma unroll
+          for (int h = 0; h < BLOCK_N / 64; ++h) {                      // boxes {64 c, 64 rows, 1 sample}
+            const int n = n0 + h * 64;
+            const int t = n / tap.channels;
+            tma_load_3d(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, n % tap.channels,
+                        (k0 % tap.rows_per_sample) + tap.shift0 + t * tap.shift_step, k0 / tap.rows_per_sample);
+          }
+        } else if (!B_MN) {
           tma_load_2d(b_dst, &tma_b, full + s, k0, n0);                 // box {64 k, BLOCK_N n}
         } else {
 #pragma unroll
@@ -302,14 +331,26 @@ static int make_map(CUtensorMap* map, const void* ptr, long long inner, long lon
   return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, int M, int N,
-                       int K, const float* bias, int relu, int splits, cudaStream_t st) {
-  using S = GemmSmem<BLOCK_N>;
-  CUtensorMap ma, mb;
-  // K-major: rows = M (or N), inner = K.   MN-major: rows = K, inner = M (or N).
-  if (make_map(&ma, A, A_MN ? M : K, A_MN ? K : M, lda, A_MN ? GEMM_BLOCK_K : GEMM_BLOCK_M)) return -1;
-  if (make_map(&mb, B, B_MN ? N : K, B_MN ? K : N, ldb, B_MN ? GEMM_BLOCK_K : BLOCK_N)) return -1;
+// 3-D bf16 tensor map over activations [samples][rows][C]: box {64 channels, box_rows, 1 sample}; rows outside
+// [0, rows) of a sample are zero-filled -- exactly the zero padding of the temporal convolution.
+static int make_map3(CUtensorMap* map, const void* ptr, long long C, long long rows, long long samples, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { p2r_set_last_error("p2r_tconv_bf16: cuTensorMapEncodeTiled entry point unavailable", -1); return -1; }
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)samples};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { p2r_set_last_error("p2r_tconv_bf16: cuTensorMapEncodeTiled (3-D) failed", -1); return -1; }
+  return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int TAP, int NSTAGE>
+static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* C, int ldc, int c_dtype, int M, int N,
+                            int K, const float* bias, int relu, int splits, const TapArgs& tap, cudaStream_t st) {
+  using S = GemmSmem<BLOCK_N, NSTAGE>;
   const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   int kps = total_kb;
   if (splits > 1) {
@@ -319,15 +360,68 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, 
   dim3 grid(p2r_ceil_div(N, BLOCK_N), p2r_ceil_div(M, GEMM_BLOCK_M), splits);
 #define GEMM_GO(OutT, ATOMIC)                                                                                   \
   do {                                                                                                          \
-    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC>;                                            \
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE>;                               \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);                          \
-    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps);                \
+    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap);           \
   } while (0)
   if (splits > 1) GEMM_GO(float, true);
   else if (c_dtype == 1) GEMM_GO(__nv_bfloat16, false);
   else GEMM_GO(float, false);
 #undef GEMM_GO
   P2R_RETURN_LAUNCH("p2r_gemm_bf16");
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, int M, int N,
+                       int K, const float* bias, int relu, int splits, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  // K-major: rows = M (or N), inner = K.   MN-major: rows = K, inner = M (or N).
+  if (make_map(&ma, A, A_MN ? M : K, A_MN ? K : M, lda, A_MN ? GEMM_BLOCK_K : GEMM_BLOCK_M)) return -1;
+  if (make_map(&mb, B, B_MN ? N : K, B_MN ? K : N, ldb, B_MN ? GEMM_BLOCK_K : BLOCK_N)) return -1;
+  const TapArgs none = {1, 1, 1, 0, 0};
+  const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  // short reductions (the 64-channel point MLPs): fewer stages -> less smem -> more co-resident CTAs per SM to hide
+  // the per-tile latency chain (TMEM alloc, TMA, MMA, epilogue)
+  if (BLOCK_N == 64 && splits <= 1 && total_kb <= 1)
+    return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 1 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st);
+  if (BLOCK_N == 64 && splits <= 1 && total_kb <= 3)
+    return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 2 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st);
+  return launch_with_maps<BLOCK_N, A_MN, B_MN, 0, 0>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st);
+}
+
+// (KT x 1) temporal convolution, zero padding (KT-1)/2, as an IMPLICIT GEMM on the 3-D activation tensor
+// (ref: nn.Conv2d(C, C, (3,1), padding (1,0)) in st_gcn_block.tcn, stgcn_layers.py:405-411).  No unfold buffer.
+//   mode 0 (forward) : act = x  [B, rows, Ci] bf16, w = W2 [Co, KT*Ci] (column dt*Ci+ci)  -> out y  [B*rows, Co] bf16 (+bias)
+//   mode 1 (d input) : act = dy [B, rows, Co] bf16, w = Wt [KT*Co, Ci] (row dt*Co+co)     -> out dx [B*rows, Ci] bf16
+//   mode 2 (d weight): act = x  [B, rows, Ci] bf16, other = dy [B*rows, Co] bf16          -> out dW2 [Co, KT*Ci] fp32
+//                      (zero-filled by the caller when splits > 1)
+// rows = T*V rows per sample, a tap shifts by V rows; requires rows % 128 == 0, Ci % 64 == 0, Co % 64 == 0, Co,Ci <= 64*...
+extern "C" int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows,
+                              int Ci, int Co, int KT, int V, const float* bias, int splits, void* stream) {
+  P2R_CHECK_ARG(mode >= 0 && mode <= 2 && B > 0 && rows > 0 && (rows % 128) == 0 && (KT & 1) && KT >= 1,
+                "p2r_tconv_bf16");
+  P2R_CHECK_ARG(Ci == 64 && Co == 64, "p2r_tconv_bf16 (built for the 64 -> 64 channel temporal conv of the hot path)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (KT - 1) / 2;
+  const int M = B * rows;
+  CUtensorMap ma, mb;
+  if (mode == 0) {
+    if (make_map3(&ma, act, Ci, rows, B, GEMM_BLOCK_M)) return -1;
+    if (make_map(&mb, w, (long long)KT * Ci, Co, (long long)KT * Ci, 64)) return -1;
+    const TapArgs tap = {Ci / 64, rows, Ci, -pad * V, V};
+    return launch_with_maps<64, false, false, 1, 2>(ma, mb, out, Co, 1, M, Co, KT * Ci, bias, 0, 1, tap, st);
+  }
+  if (mode == 1) {
+    if (make_map3(&ma, act, Co, rows, B, GEMM_BLOCK_M)) return -1;
+    if (make_map(&mb, w, Ci, (long long)KT * Co, Ci, GEMM_BLOCK_K)) return -1;
+    const TapArgs tap = {Co / 64, rows, Co, pad * V, -V};
+    return launch_with_maps<64, false, true, 1, 2>(ma, mb, out, Ci, 1, M, Ci, KT * Co, nullptr, 0, 1, tap, st);
+  }
+  // mode 2: dW2[Co, KT*Ci] = dy^T . shifted(x)
+  if (make_map(&ma, other, Co, M, Co, GEMM_BLOCK_K)) return -1;          // dy as MN-major A: inner = Co, rows = m
+  if (make_map3(&mb, act, Ci, rows, B, GEMM_BLOCK_K)) return -1;         // x as MN-major B, 3-D
+  const TapArgs tap = {1, rows, Ci, -pad * V, V};
+  return launch_with_maps<64, true, true, 2, 0>(ma, mb, out, KT * Ci, 0, Co, KT * Ci, M, nullptr, 0, splits, tap, st);
 }
 
 // C[M,N] (+)= op(A) . op(B)^T with bf16 operands (see file header).

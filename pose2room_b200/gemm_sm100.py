@@ -38,6 +38,50 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bf
     return c
 
 
+class _TemporalConvTC(torch.autograd.Function):
+    """(KT x 1) temporal conv of st_gcn_block.tcn as implicit tensor-core GEMMs (forward, d input, d weight):
+    three row-shifted TMA views of the SAME activation tensor instead of an unfold buffer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        b, t, v, ci = x.shape
+        co, _, kt, _ = weight.shape
+        x = x if x.is_contiguous() else x.contiguous()
+        w2 = weight[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci).to(torch.bfloat16).contiguous()
+        y = torch.empty(b * t * v, co, dtype=torch.bfloat16, device=x.device)
+        bias_f = bias.float().contiguous() if bias is not None else None
+        with torch.cuda.device(x.device):
+            _lib.call("p2r_tconv_bf16", 0, x.data_ptr(), w2.data_ptr(), None, y.data_ptr(), b, t * v, ci, co, kt, v,
+                      bias_f.data_ptr() if bias_f is not None else None, 1, _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        b, t, v, ci = x.shape
+        co, _, kt, _ = weight.shape
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        dx = dw = db = None
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                wt = weight[:, :, :, 0].permute(2, 0, 1).reshape(kt * co, ci).to(torch.bfloat16).contiguous()
+                dx = torch.empty(b, t, v, ci, dtype=torch.bfloat16, device=x.device)
+                _lib.call("p2r_tconv_bf16", 1, dy.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), b, t * v, ci, co, kt, v,
+                          None, 1, _stream())
+            if ctx.needs_input_grad[1]:
+                m = b * t * v
+                splits = max(1, min(128, m // 8192))
+                dw2 = torch.zeros(co, kt * ci, dtype=torch.float32, device=x.device)
+                _lib.call("p2r_tconv_bf16", 2, x.data_ptr(), None, dy.data_ptr(), dw2.data_ptr(), b, t * v, ci, co, kt, v,
+                          None, splits, _stream())
+                dw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = ops._col_sum(dy)
+        return dx, dw, db
+
+
 class _Backend:
     """Interface expected by ops._Linear (see ops._TC_GEMM)."""
 
@@ -69,7 +113,12 @@ class _Backend:
 
     @staticmethod
     def supports_tconv(shape, co):
-        return False
+        b, t, v, ci = shape
+        return ci == 64 and co == 64 and (t * v) % 128 == 0
+
+    @staticmethod
+    def temporal_conv(x, weight, bias):
+        return _TemporalConvTC.apply(x, weight, bias)
 
 
 def install():

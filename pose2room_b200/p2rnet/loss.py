@@ -55,7 +55,7 @@ class BoxNetDetectionLoss(BaseLoss):
         o = self.origin_joint_id
         mask = torch.gather(gt["vote_label_mask"][..., o], 1, seed_inds)
         votes = torch.gather(gt["vote_label"][:, :, o], 1, seed_inds.view(b, s, 1).expand(b, s, 3 * GT_VOTE_FACTOR))
-        votes = est["seed_skeleton"][:, :, [o]] + votes.view(b, s, GT_VOTE_FACTOR, 3)
+        votes = est["seed_skeleton"][:, :, o:o + 1] + votes.view(b, s, GT_VOTE_FACTOR, 3)  # slice, not a list index (no H2D index copy)
         skeleton = est["seed_skeleton"].reshape(b * s, j, 3)
         _, _, dist2, ind2 = nn_distance(votes.view(b * s, GT_VOTE_FACTOR, 3), skeleton)
         pick = torch.gather(ind2, 1, dist2.argmin(-1, keepdim=True)).view(b, s, 1)

@@ -92,3 +92,32 @@ def test_linear_autograd_bf16_backend(cuda):
             _check(gb, dz.sum(0), tol=1e-3)
     finally:
         gemm_sm100.uninstall()
+
+
+def test_implicit_temporal_conv_fwd_dx_dw(cuda):
+    """The 3-tap temporal conv as implicit GEMMs (3-D TMA maps, zero fill at sequence ends) vs nn.Conv2d in fp32 on the
+    same bf16-rounded operands; integer-valued data makes the forward and the input gradient exact."""
+    import torch.nn as nn
+    from pose2room_b200 import gemm_sm100, ops
+    gemm_sm100.install()
+    try:
+        g = torch.Generator().manual_seed(3)
+        for (B, T, V) in [(2, 128, 25), (3, 64, 26), (1, 1024, 25)]:
+            C = 64
+            conv = nn.Conv2d(C, C, (3, 1), (1, 1), (1, 0)).to(cuda)
+            with torch.no_grad():
+                conv.weight.copy_(torch.randint(-2, 3, conv.weight.shape, generator=g).float())
+                conv.bias.copy_(torch.randint(-2, 3, (C,), generator=g).float())
+            x = torch.randint(-2, 3, (B, T, V, C), generator=g).float().to(cuda).bfloat16().requires_grad_(True)
+            assert gemm_sm100._Backend.supports_tconv(x.shape, C)
+            y = ops.temporal_conv(x, conv.weight, conv.bias)
+            xr = x.detach().float().requires_grad_(True)
+            ref = conv(xr.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).reshape(B * T * V, C)
+            assert torch.equal(y.float(), ref.detach()), (B, T, V)
+            go = torch.randint(-2, 3, (B * T * V, C), generator=g).float().to(cuda)
+            gx, gw, gb = torch.autograd.grad(y, [x, conv.weight, conv.bias], go.bfloat16())
+            rx, rw, rb = torch.autograd.grad(ref, [xr, conv.weight, conv.bias], go)
+            assert torch.equal(gx.float(), rx), (B, T, V)
+            assert torch.allclose(gw, rw, rtol=1e-5, atol=1e-2) and torch.allclose(gb, rb, rtol=1e-5, atol=1e-2)
+    finally:
+        gemm_sm100.uninstall()

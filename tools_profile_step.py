@@ -49,7 +49,14 @@ print("python-side ms/step (launch only): %.2f" % ((t1 - t0) / 3 * 1e3))
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
-rows = [(e.key, e.device_time_total, e.count) for e in prof.key_averages() if e.device_time_total > 0]
+from torch.autograd import DeviceType
+rows = {}
+for e in prof.events():
+    if e.device_type == DeviceType.CUDA:
+        k = e.name
+        t, c = rows.get(k, (0.0, 0))
+        rows[k] = (t + e.device_time, c + 1)
+rows = [(k, t, c) for k, (t, c) in rows.items()]
 rows.sort(key=lambda r: -r[1])
 tot = sum(r[1] for r in rows)
 print("total device time %.2f ms over %d kernel names" % (tot / 1e3, len(rows)))
