@@ -117,9 +117,11 @@ int p2r_sgemm(int M, int N, int K, const void* A, int lda, int trans_a, int a_dt
               int splits, void* stream);
 /* column sums of x[M,C]: s1 = sum x, s2 = sum x^2 (f64[C], zeroed by caller)                       */
 int p2r_col_stats(const void* x, int dtype, long long M, int C, double* s1, double* s2, void* stream);
-/* backward column sums: dz = relu ? dy*(y>0) : dy; s1 = sum dz, s2 = sum dz*(x-mean)*rstd (s2/x may be NULL) */
+/* backward column sums: dz = dy masked by the ReLU (relu = 0 none, 1: y > 0, 2: x*scale+shift > 0, recomputed);
+ * s1 = sum dz, s2 = sum dz*(x-mean)*rstd (s2/x may be NULL)                                                       */
 int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
-                      const float* rstd, int relu, double* s1, double* s2, void* stream);
+                      const float* rstd, int relu, double* s1, double* s2, const float* scale, const float* shift,
+                      void* stream);
 /* training-mode BatchNorm statistics -> mean, rstd, fused scale/shift; updates running stats like torch */
 int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
@@ -130,7 +132,7 @@ int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* sc
 /* BN(+ReLU)(+residual) backward, elementwise part (s1 == NULL: eval-mode BN)                       */
 int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
                      const float* rstd, const float* scale, const double* s1, const double* s2, int relu, void* dx,
-                     void* dres, void* stream);
+                     void* dres, const float* shift, void* stream);
 /* dz = dy * (y > 0)                                                                                */
 int p2r_relu_bwd(const void* dy, const void* y, int dtype, long long total, void* dz, void* stream);
 /* (KT x 1) temporal conv as GEMM: x[B,T,V,C] -> col[B*T*V, KT*C] (zero padded), and its adjoint    */
@@ -144,6 +146,12 @@ int p2r_group_rows_grad(const void* grad, int dtype, const int* idx, int B, int 
 int p2r_maxpool_rows(const void* x, int dtype, long long R, int S, int C, void* out, unsigned char* arg, void* stream);
 int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg, long long R, int S, int C, void* dx,
                           void* stream);
+
+/* x[f,j,:] = sk[f,j,:] + mean_k pos[f,k,:] and its backward dpos[f,k,:] = (1/K) sum_j dx[f,j,:]
+ * (ref: models/p2rnet/modules/stgcn.py:121,129)                                                                 */
+int p2r_embed_sum(const void* sk, const void* pos, int dtype, long long frames, int J, int K, int C, void* x,
+                  void* stream);
+int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, int J, int K, int C, void* dpos, void* stream);
 
 /* bf16 tensor-core GEMM (tcgen05 + TMA + TMEM), the throughput-mode backend of every dense layer, above all the
  * fused graph-convolution GEMM that replaces conv 64->704 + einsum (ref: stgcn_layers.py:58-67).

@@ -196,7 +196,8 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(long long M, int C, const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
                  const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int rows_per_cta,
-                 double* __restrict__ s1, double* __restrict__ s2) {
+                 double* __restrict__ s1, double* __restrict__ s2, const float* __restrict__ scale = nullptr,
+                 const float* __restrict__ shift = nullptr) {
   __shared__ float sh1[256], sh2[256];
   const int cp = C < 256 ? C : 256;
   const int rl = 256 / cp;
@@ -216,7 +217,8 @@ colreduce_kernel(long long M, int C, const T* __restrict__ x, const T* __restric
         a2 = fmaf(v, v, a2);
       } else {
         float dz = ldf<T>(dy + o);
-        if (relu && !(ldf<T>(y + o) > 0.f)) dz = 0.f;
+        if (relu == 1 && !(ldf<T>(y + o) > 0.f)) dz = 0.f;
+        if (relu == 2 && !(fmaf(ldf<T>(x + o), __ldg(scale + c), __ldg(shift + c)) > 0.f)) dz = 0.f;
         a1 += dz;
         if (x) a2 = fmaf(dz, (ldf<T>(x + o) - mu) * rs, a2);
       }
@@ -239,7 +241,8 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int rows_per_cta,
-                     double* __restrict__ s1, double* __restrict__ s2) {
+                     double* __restrict__ s1, double* __restrict__ s2, const float* __restrict__ scale = nullptr,
+                     const float* __restrict__ shift = nullptr) {
   constexpr int V = VecN<T>::N;
   __shared__ float sh1[256 * V], sh2[256 * V];
   const int tpr = C / V;            // threads per row
@@ -266,7 +269,7 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
     } else {
       float dz[V];
       vload(dy + o, dz);
-      if (relu) {
+      if (relu == 1) {
         float yy[V];
         vload(y + o, yy);
 #pragma unroll
@@ -275,6 +278,11 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
       if (x != nullptr) {
         float xx[V];
         vload(x + o, xx);
+        if (relu == 2) {  // ReLU mask recomputed from the pre-BN input: no read of the activation output
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            if (!(fmaf(xx[i], __ldg(scale + c0 + i), __ldg(shift + c0 + i)) > 0.f)) dz[i] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) a2[i] = fmaf(dz[i], (xx[i] - mu[i]) * rs[i], a2[i]);
       }
@@ -325,22 +333,24 @@ extern "C" int p2r_col_stats(const void* x, int dtype, long long M, int C, doubl
 
 // backward column sums: s1 = sum dz, s2 = sum dz*xhat (s2/x/mean/rstd may be NULL -> only s1, e.g. a bias grad)
 extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
-                                 const float* mean, const float* rstd, int relu, double* s1, double* s2, void* stream) {
+                                 const float* mean, const float* rstd, int relu, double* s1, double* s2,
+                                 const float* scale, const float* shift, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "p2r_col_bwd_stats");
-  P2R_CHECK_ARG(!(relu && y == nullptr), "p2r_col_bwd_stats (relu needs y)");
+  P2R_CHECK_ARG(!(relu == 1 && y == nullptr), "p2r_col_bwd_stats (relu = 1 needs y)");
+  P2R_CHECK_ARG(!(relu == 2 && (x == nullptr || scale == nullptr || shift == nullptr)), "p2r_col_bwd_stats (relu = 2 needs x, scale, shift)");
   if (M == 0) return 0;
   int rpc;
   const int grid = colreduce_grid(M, &rpc);
   if (dtype == 0) {
     if (vec_ok<float>(C, x, dy, y) && 256 % (C / 4) == 0)
-      colreduce_vec_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2);
+      colreduce_vec_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2, scale, shift);
     else
-      colreduce_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2);
+      colreduce_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)x, (const float*)dy, (const float*)y, mean, rstd, relu, rpc, s1, s2, scale, shift);
   } else {
     if (vec_ok<__nv_bfloat16>(C, x, dy, y) && 256 % (C / 8) == 0)
-      colreduce_vec_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2);
+      colreduce_vec_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2, scale, shift);
     else
-      colreduce_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2);
+      colreduce_kernel<__nv_bfloat16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, mean, rstd, relu, rpc, s1, s2, scale, shift);
   }
   P2R_RETURN_LAUNCH("p2r_col_bwd_stats");
 }
@@ -442,12 +452,13 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(long long total, int C, double inv_m, const T* __restrict__ dy, const T* __restrict__ x,
                     const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
-                    int relu, T* __restrict__ dx, T* __restrict__ dres) {
+                    int relu, T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ shift = nullptr) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int c = (int)(e % C);
     float dz = ldf<T>(dy + e);
-    if (relu && !(ldf<T>(y + e) > 0.f)) dz = 0.f;
+    if (relu == 1 && !(ldf<T>(y + e) > 0.f)) dz = 0.f;
+    if (relu == 2 && !(fmaf(ldf<T>(x + e), __ldg(scale + c), __ldg(shift + c)) > 0.f)) dz = 0.f;
     if (dres) stf<T>(dres + e, dz);
     float g = dz;
     if (s1) {
@@ -463,7 +474,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict__ dy, const T* __restrict__ x,
                         const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
-                        int relu, T* __restrict__ dx, T* __restrict__ dres) {
+                        int relu, T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ shift = nullptr) {
   constexpr int V = VecN<T>::N;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
@@ -471,17 +482,22 @@ bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict
     const int c0 = (int)(o % C);
     float dz[V];
     vload(dy + o, dz);
-    if (relu) {
+    if (relu == 1) {
       float yy[V];
       vload(y + o, yy);
 #pragma unroll
       for (int i = 0; i < V; ++i) if (!(yy[i] > 0.f)) dz[i] = 0.f;
     }
+    float xx[V];
+    if (s1 || relu == 2) vload(x + o, xx);
+    if (relu == 2) {
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (!(fmaf(xx[i], __ldg(scale + c0 + i), __ldg(shift + c0 + i)) > 0.f)) dz[i] = 0.f;
+    }
     if (dres) vstore(dres + o, dz);
     float g[V];
     if (s1) {
-      float xx[V];
-      vload(x + o, xx);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const float xh = (xx[i] - __ldg(mean + c0 + i)) * __ldg(rstd + c0 + i);
@@ -497,19 +513,19 @@ bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict
 
 extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
                                 const float* mean, const float* rstd, const float* scale, const double* s1,
-                                const double* s2, int relu, void* dx, void* dres, void* stream) {
+                                const double* s2, int relu, void* dx, void* dres, const float* shift, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_bn_bwd_apply");
   const long long total = M * C;
   if (total == 0) return 0;
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, dy, x, y, dx, dres))
-    bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres);
+    bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);
   else if (dtype == 1 && vec_ok<__nv_bfloat16>(C, dy, x, y, dx, dres))
-    bn_bwd_apply_vec_kernel<__nv_bfloat16><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 8, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
+    bn_bwd_apply_vec_kernel<__nv_bfloat16><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 8, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, shift);
   else if (dtype == 0)
-    bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres);
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);
   else
-    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, shift);
   P2R_RETURN_LAUNCH("p2r_bn_bwd_apply");
 }
 
@@ -720,4 +736,63 @@ extern "C" int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned
   else
     maxpool_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(R, S, C, (const __nv_bfloat16*)dout, const_cast<unsigned char*>(arg), (__nv_bfloat16*)dx);
   P2R_RETURN_LAUNCH("p2r_maxpool_rows_grad");
+}
+
+
+// ================================================================================================
+// embed_sum: x[f,j,:] = sk[f,j,:] + mean_k pos[f,k,:]   (models/p2rnet/modules/stgcn.py:121,129: the relative-position
+// embedding averaged over the 20-frame window is broadcast onto every joint feature of the frame).
+// One warp per frame f = (b,t); fp32 accumulation, one rounding.  Backward: dsk = dx (aliased by the caller),
+// dpos[f,k,:] = (1/K) sum_j dx[f,j,:].
+// ================================================================================================
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+embed_sum_kernel(long long frames, int J, int K, int C, const T* __restrict__ a, const T* __restrict__ b_in,
+                 T* __restrict__ out) {
+  const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  const float inv_k = 1.f / (float)K;
+  for (int c = lane; c < C; c += 32) {
+    if (!BWD) {
+      // a = sk [frames,J,C], b_in = pos [frames,K,C], out = x [frames,J,C]
+      float m = 0.f;
+      for (int k = 0; k < K; ++k) m += ldf<T>(b_in + ((size_t)f * K + k) * C + c);
+      m *= inv_k;
+      for (int j = 0; j < J; ++j) {
+        const size_t o = ((size_t)f * J + j) * C + c;
+        stf<T>(out + o, ldf<T>(a + o) + m);
+      }
+    } else {
+      // a = dx [frames,J,C], out = dpos [frames,K,C]
+      float sum = 0.f;
+      for (int j = 0; j < J; ++j) sum += ldf<T>(a + ((size_t)f * J + j) * C + c);
+      sum *= inv_k;
+      for (int k = 0; k < K; ++k) stf<T>(out + ((size_t)f * K + k) * C + c, sum);
+    }
+  }
+}
+
+extern "C" int p2r_embed_sum(const void* sk, const void* pos, int dtype, long long frames, int J, int K, int C, void* x,
+                             void* stream) {
+  P2R_CHECK_ARG(frames >= 0 && J > 0 && K > 0 && C > 0, "p2r_embed_sum");
+  if (frames == 0) return 0;
+  const int grid = p2r_ceil_div(frames * 32, 256);
+  if (dtype == 0)
+    embed_sum_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const float*)sk, (const float*)pos, (float*)x);
+  else
+    embed_sum_kernel<__nv_bfloat16, false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const __nv_bfloat16*)sk, (const __nv_bfloat16*)pos, (__nv_bfloat16*)x);
+  P2R_RETURN_LAUNCH("p2r_embed_sum");
+}
+
+extern "C" int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, int J, int K, int C, void* dpos,
+                                  void* stream) {
+  P2R_CHECK_ARG(frames >= 0 && J > 0 && K > 0 && C > 0, "p2r_embed_sum_grad");
+  if (frames == 0) return 0;
+  const int grid = p2r_ceil_div(frames * 32, 256);
+  if (dtype == 0)
+    embed_sum_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const float*)dx, nullptr, (float*)dpos);
+  else
+    embed_sum_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const __nv_bfloat16*)dx, nullptr, (__nv_bfloat16*)dpos);
+  P2R_RETURN_LAUNCH("p2r_embed_sum_grad");
 }

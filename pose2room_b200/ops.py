@@ -89,7 +89,7 @@ def _col_sum(dy, y=None, relu=False):
     s1 = torch.zeros(c, dtype=torch.float64, device=dy.device)
     with torch.cuda.device(dy.device):
         _lib.call("p2r_col_bwd_stats", dy.data_ptr(), None, _ptr(y), _DT[dy.dtype], m, c, None, None, int(relu),
-                  s1.data_ptr(), None, _stream())
+                  s1.data_ptr(), None, None, None, _stream())
     return s1.float()
 
 
@@ -172,8 +172,10 @@ class _BatchNormAct(Function):
                 residual = residual if residual.is_contiguous() else residual.contiguous()
             _lib.call("p2r_affine_act", x.data_ptr(), dt, m, c, stats[2].data_ptr(), stats[3].data_ptr(),
                       _ptr(residual), int(relu), y.data_ptr(), _stream())
-        ctx.save_for_backward(x, y if relu else None, stats)
-        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
+        # ReLU mask in the backward: recomputed from x (relu mode 2) unless a residual was added (mode 1 reads y)
+        ctx.relu_mode = 0 if not relu else (1 if residual is not None else 2)
+        ctx.save_for_backward(x, y if ctx.relu_mode == 1 else None, stats)
+        ctx.training, ctx.has_res = training, residual is not None
         return y
 
     @staticmethod
@@ -188,10 +190,12 @@ class _BatchNormAct(Function):
         sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
-                      stats[1].data_ptr(), int(ctx.relu), sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+                      stats[1].data_ptr(), ctx.relu_mode, sums[0].data_ptr(), sums[1].data_ptr(), stats[2].data_ptr(),
+                      stats[3].data_ptr(), _stream())
             _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
                       stats[1].data_ptr(), stats[2].data_ptr(), sums[0].data_ptr() if ctx.training else None,
-                      sums[1].data_ptr() if ctx.training else None, int(ctx.relu), dx.data_ptr(), _ptr(dres), _stream())
+                      sums[1].data_ptr() if ctx.training else None, ctx.relu_mode, dx.data_ptr(), _ptr(dres),
+                      stats[3].data_ptr(), _stream())
         dgamma = sums[1].float() if ctx.needs_input_grad[1] else None
         dbeta = sums[0].float() if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
@@ -300,3 +304,31 @@ class _MaxPoolRows(Function):
 def maxpool_rows(x):
     """x [R,S,C] -> max over S -> [R,C] (F.max_pool2d over nsample, pointnet2_modules.py:243-247)."""
     return _MaxPoolRows.apply(x)
+
+
+class _EmbedSum(Function):
+    @staticmethod
+    def forward(ctx, sk, pos):
+        f, j, c = sk.shape
+        k = pos.shape[1]
+        sk = sk if sk.is_contiguous() else sk.contiguous()
+        pos = pos if pos.is_contiguous() else pos.contiguous()
+        x = torch.empty_like(sk)
+        with torch.cuda.device(sk.device):
+            _lib.call("p2r_embed_sum", sk.data_ptr(), pos.data_ptr(), _DT[sk.dtype], f, j, k, c, x.data_ptr(), _stream())
+        ctx.shape = (f, j, k, c)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        f, j, k, c = ctx.shape
+        dx = dx if dx.is_contiguous() else dx.contiguous()
+        dpos = torch.empty(f, k, c, dtype=dx.dtype, device=dx.device)
+        with torch.cuda.device(dx.device):
+            _lib.call("p2r_embed_sum_grad", dx.data_ptr(), _DT[dx.dtype], f, j, k, c, dpos.data_ptr(), _stream())
+        return dx, dpos
+
+
+def embed_sum(sk, pos):
+    """sk [F,J,C] joint features, pos [F,K,C] window embeddings -> sk + mean_k(pos) broadcast over joints."""
+    return _EmbedSum.apply(sk, pos)

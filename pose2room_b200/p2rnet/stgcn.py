@@ -141,10 +141,10 @@ class STGCN(nn.Module):
         hip = input_joints[:, :, self.origin_joint_id]                       # (B,T,3)
         x0 = input_joints - hip[:, :, None]                                  # joints relative to the hip
         rel = hip[:, self._window_idx(t, hip.device)] - hip[:, :, None]      # (B,T,20,3): stgcn.py:109-117
-        pos = run_rows(self.pos_embed, rel.reshape(b * t * self.knn, 3).to(act))
-        pos = pos.reshape(b, t, self.knn, 64).float().mean(dim=2)            # (B,T,64)
-        sk = run_rows(self.sk_feat, x0.reshape(b * t * j, 3).to(act)).reshape(b, t, j, 64)
-        x = (sk.float() + pos[:, :, None]).to(act)                           # (B,T,J,64) channel-last
+        pos = run_rows(self.pos_embed, rel.reshape(b * t * self.knn, 3).to(act))   # (B*T*20, 64)
+        sk = run_rows(self.sk_feat, x0.reshape(b * t * j, 3).to(act))              # (B*T*J, 64)
+        # x = sk + mean_k(pos) broadcast over the joints of the frame (stgcn.py:121,129), one fused kernel
+        x = ops.embed_sum(sk.reshape(b * t, j, 64), pos.reshape(b * t, self.knn, 64)).reshape(b, t, j, 64)
 
         for blk, importance in zip(self.st_gcn_networks, self.edge_importance):
             x = blk.forward_rows(x, self.A * importance)

@@ -4,6 +4,7 @@ Module surface / state-dict of /root/reference/models/p2rnet/modules/vote_center
 conv_input = 3 x SingleConv (256->256 'cbr', 256->256 'cbr', 256->(3+256)*vote_factor 'c').
 Runs on channel-last rows (B*S, 256) with the B200 GEMM / BatchNorm kernels.
 """
+import torch
 import torch.nn as nn
 
 from .registers import MODULES
@@ -31,7 +32,8 @@ class CenterVoteModule(nn.Module):
         seed_xyz = seed_xyz[:, :, self.origin_joint_id]
         b, s, _ = seed_xyz.shape
         num_vote = s * self.vote_factor
-        rows = seed_features.reshape(b * s, -1)
+        act = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        rows = seed_features.reshape(b * s, -1).to(act)
         net = run_rows(self.conv_input, rows).float()
         net = net.reshape(b, s, self.vote_factor, 3 + self.out_dim)
         vote_xyz = (seed_xyz.unsqueeze(2) + net[..., 0:3]).contiguous().reshape(b, num_vote, 3)
