@@ -29,8 +29,9 @@ def _check_endpoints(ep, golden, prefix):
             assert np.array_equal(got, want), k
         else:
             assert got.dtype == want.dtype, (k, got.dtype, want.dtype)
-            # 1e-4 absolute on the box tensors (north_star); the fixture's logits reach |20|, so scale there
-            tol = 1e-4 * np.maximum(1.0, np.abs(want)) if k.endswith("_scores") else 1e-4
+            # 1e-4 absolute on the box tensors (north_star); the fixture's logits are deliberately 8x wider
+            # (they reach |20|) and their fp32 noise scales with them: 2e-5 of the tensor's range there
+            tol = max(1e-4, 2e-5 * float(np.abs(want).max())) if k.endswith("_scores") else 1e-4
             assert (np.abs(got - want) <= tol).all(), (k, np.abs(got - want).max())
 
 
@@ -112,7 +113,7 @@ def test_product_vs_oracle_fresh_inputs(cuda, golden):
         if a.dtype in (torch.int64, torch.int32):
             assert torch.equal(a, b), k
         else:
-            tol = 1e-4 * torch.clamp(b.abs(), min=1.0) if k.endswith("_scores") else 1e-4
+            tol = max(1e-4, 2e-5 * float(b.abs().max())) if k.endswith("_scores") else 1e-4
             assert ((a - b).abs() <= tol).all(), (k, (a - b).abs().max())
     assert abs(loss["total"].item() - loss_r["total"].item()) < 1e-4 * abs(loss_r["total"].item())
 
@@ -150,8 +151,12 @@ def test_bf16_throughput_mode_tracks_fp32_reference(cuda, golden):
             loss["total"].backward()
             for k, p in net.named_parameters():
                 assert p.grad is None or torch.isfinite(p.grad).all(), k
-            same = ep["aggregated_vote_inds"].cpu().numpy() == golden[name + "_train_aggregated_vote_inds"]
-            assert same.mean() > 0.5, same.mean()
+            got_inds = ep["aggregated_vote_inds"].cpu().numpy()
+            want_inds = golden[name + "_train_aggregated_vote_inds"]
+            # FPS is sequential: one swapped pick changes the tail, so compare the picked SETS per scene
+            overlap = np.mean([len(set(g.tolist()) & set(w.tolist())) / float(len(w)) for g, w in zip(got_inds, want_inds)])
+            assert overlap > 0.5, overlap
+            same = got_inds == want_inds
             if same.all():
                 for k in ["center", "size", "heading"]:
                     err = np.abs(ep[k].detach().cpu().numpy() - golden["%s_train_%s" % (name, k)]).max()
