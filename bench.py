@@ -179,9 +179,8 @@ def main():
     net = P2RNet(cfg)
     net.load_state_dict(synthetic.deterministic_state_dict(net.state_dict(), seed=7))
     net = net.to(dev).train()
-    if world > 1:  # identical replicas (same seed); make it explicit like DDP's initial broadcast
-        for t in list(net.parameters()) + list(net.buffers()):
-            dist.broadcast(t.data, 0)
+    from pose2room_b200 import parallel
+    parallel.broadcast_parameters(net)  # identical replicas, like DDP's initial broadcast
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-3, fused=True, capturable=True)
 
@@ -197,12 +196,7 @@ def main():
         ep = net(data)
         loss = net.loss(ep, data)["total"]
         loss.backward()
-        if world > 1:
-            grads = [p.grad for p in params if p.grad is not None]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(f)
+        parallel.allreduce_gradients(params)
         opt.step()
         return loss
 
