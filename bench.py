@@ -160,6 +160,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
     _lib.load()
 
     precision = args.precision
@@ -190,15 +191,28 @@ def main():
     resident = {k: v.to(dev) for k, v in tensors.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in tensors.values())
 
-    def step(data):
-        """forward + loss + backward (+ ONE flat gradient all-reduce over NCCL, the reference's DDP axis) + AdamW."""
+    dbg = (lambda *a: print("[bench rank %d]" % rank, *a, file=sys.stderr, flush=True)) if os.environ.get("P2R_BENCH_DEBUG") else (lambda *a: None)
+
+    def fwd_bwd(data):
         opt.zero_grad(set_to_none=True)
         ep = net(data)
         loss = net.loss(ep, data)["total"]
         loss.backward()
+        return loss
+
+    def finish():
+        """ONE flat gradient all-reduce over NCCL (the reference's DDP axis; no-op on one GPU) + AdamW."""
         parallel.allreduce_gradients(params)
         opt.step()
+
+    def step(data):
+        loss = fwd_bwd(data)
+        finish()
         return loss
+
+    # On one GPU the whole step is captured; with several ranks the graph holds forward + loss + backward and the
+    # all-reduce + fused AdamW (3 launches) run eagerly right after the replay (no NCCL call inside a capture).
+    captured = step if world == 1 else fwd_bwd
 
     # ---- whole-step CUDA graph: ~3000 launches per step would otherwise be bound by the Python launch path ------
     static = {k: torch.empty_like(v) for k, v in resident.items()}
@@ -214,11 +228,13 @@ def main():
                     step(static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            dbg("eager warm-up done, capturing")
             graph = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
-                static_loss = step(static)
+                static_loss = captured(static)
             torch.cuda.synchronize()
+            dbg("captured")
         except Exception as e:  # report, do not hide: the bench line says whether the graph was used
             print("bench.py: CUDA graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
             graph, use_graph = None, False
@@ -233,6 +249,8 @@ def main():
             for k in static:
                 static[k].copy_(data[k], non_blocking=True)
         graph.replay()
+        if world > 1:
+            finish()
         return static_loss
     launches_per_step = None
 
