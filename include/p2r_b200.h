@@ -153,6 +153,12 @@ int p2r_embed_sum(const void* sk, const void* pos, int dtype, long long frames, 
                   void* stream);
 int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, int J, int K, int C, void* dpos, void* stream);
 
+/* K <= 4 linear layers (3 -> 64 first layers, ref: stgcn.py:45-50) as memory-bound maps: y = x.W^T (+bias) and
+ * dW[N,K] (f32, zeroed by the caller) = dz^T.x.  N % VEC == 0, (256*VEC) % N == 0 (VEC = 4 f32 / 8 bf16).          */
+int p2r_smallk_linear(const void* x, const float* W, const float* bias, int dtype, long long M, int N, int K, void* y,
+                      void* stream);
+int p2r_smallk_dw(const void* dz, const void* x, int dtype, long long M, int N, int K, float* dW, void* stream);
+
 /* bf16 tensor-core GEMM (tcgen05 + TMA + TMEM), the throughput-mode backend of every dense layer, above all the
  * fused graph-convolution GEMM that replaces conv 64->704 + einsum (ref: stgcn_layers.py:58-67).
  * C[M,N] (+)= op(A).op(B)^T, fp32 accumulate.  a_mn = 0: A is [M,K] row-major, 1: [K,M]; b_mn = 0: B is [N,K]

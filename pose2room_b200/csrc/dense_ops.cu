@@ -55,7 +55,7 @@ __device__ __forceinline__ void vstore(__nv_bfloat16* p, const float (&f)[8]) {
 template <typename T> static inline bool vec_ok(int C, const void* a, const void* b = nullptr, const void* c = nullptr,
                                                 const void* d = nullptr, const void* e = nullptr) {
   auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  return C % VecN<T>::N == 0 && al(a) && al(b) && al(c) && al(d) && al(e);
+  return C % VecN<T>::N == 0 && (256 * VecN<T>::N) % C == 0 && al(a) && al(b) && al(c) && al(d) && al(e);
 }
 
 // ================================================================================================
@@ -251,13 +251,15 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
   const int c0 = cl * V;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(M, r0 + rows_per_cta);
-  float a1[V], a2[V], mu[V], rs[V];
+  float a1[V], a2[V], mu[V], rs[V], sc[V], sh[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     a1[i] = a2[i] = 0.f;
     mu[i] = 0.f;
     rs[i] = 1.f;
+    sc[i] = sh[i] = 0.f;
     if (MODE == 1 && mean != nullptr) { mu[i] = __ldg(mean + c0 + i); rs[i] = __ldg(rstd + c0 + i); }
+    if (MODE == 1 && relu == 2) { sc[i] = __ldg(scale + c0 + i); sh[i] = __ldg(shift + c0 + i); }
   }
   for (long long r = r0 + r_lane; r < r1; r += rl) {
     const size_t o = (size_t)r * C + c0;
@@ -281,7 +283,7 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
         if (relu == 2) {  // ReLU mask recomputed from the pre-BN input: no read of the activation output
 #pragma unroll
           for (int i = 0; i < V; ++i)
-            if (!(fmaf(xx[i], __ldg(scale + c0 + i), __ldg(shift + c0 + i)) > 0.f)) dz[i] = 0.f;
+            if (!(fmaf(xx[i], sc[i], sh[i]) > 0.f)) dz[i] = 0.f;
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) a2[i] = fmaf(dz[i], (xx[i] - mu[i]) * rs[i], a2[i]);
@@ -304,8 +306,8 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
 }
 
 static int colreduce_grid(long long M, int* rows_per_cta) {
-  // ~4 CTAs per SM, at least 64 rows each
-  long long target = (M + (long long)P2R_SM_COUNT * 4 - 1) / ((long long)P2R_SM_COUNT * 4);
+  // ~8 CTAs per SM, at least 64 rows each
+  long long target = (M + (long long)P2R_SM_COUNT * 8 - 1) / ((long long)P2R_SM_COUNT * 8);
   if (target < 64) target = 64;
   *rows_per_cta = (int)target;
   return (int)((M + target - 1) / target);
@@ -404,21 +406,26 @@ affine_act_kernel(long long total, int C, const T* __restrict__ x, const float* 
   }
 }
 
+// Vectorised variants require (256 * VEC) % C == 0, so a thread's channel offset is the same in every iteration of
+// the grid-stride loop and the per-channel coefficients live in registers (no per-element parameter loads).
 template <typename T>
 __global__ void __launch_bounds__(256)
 affine_act_vec_kernel(long long nvec, int C, const T* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ shift, const T* __restrict__ residual, int relu, T* __restrict__ y) {
   constexpr int V = VecN<T>::N;
+  const int c0 = (threadIdx.x * V) % C;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sc[i] = __ldg(scale + c0 + i); sh[i] = __ldg(shift + c0 + i); }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
     const size_t o = (size_t)e * V;
-    const int c0 = (int)(o % C);
     float v[V], r[V];
     vload(x + o, v);
     if (residual) vload(residual + o, r);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float t = fmaf(v[i], __ldg(scale + c0 + i), __ldg(shift + c0 + i));
+      float t = fmaf(v[i], sc[i], sh[i]);
       if (residual) t += r[i];
       v[i] = relu ? fmaxf(t, 0.f) : t;
     }
@@ -476,36 +483,47 @@ bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict
                         const float* __restrict__ scale, const double* __restrict__ s1, const double* __restrict__ s2,
                         int relu, T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ shift = nullptr) {
   constexpr int V = VecN<T>::N;
+  const int c0 = (threadIdx.x * V) % C;
+  // dx = scale * (dz - k1 - xhat * k2),  xhat = (x - mean) * rstd   ==>   dx = dz * A + x * B + D
+  float A[V], Bc[V], D[V], sc[V], sh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = c0 + i;
+    sc[i] = __ldg(scale + c);
+    sh[i] = shift ? __ldg(shift + c) : 0.f;
+    A[i] = sc[i];
+    Bc[i] = 0.f;
+    D[i] = 0.f;
+    if (s1) {
+      const float k1 = (float)(s1[c] * inv_m), k2 = (float)(s2[c] * inv_m);
+      const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+      Bc[i] = -rs * k2 * sc[i];
+      D[i] = (-k1 + mu * rs * k2) * sc[i];
+    }
+  }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
     const size_t o = (size_t)e * V;
-    const int c0 = (int)(o % C);
-    float dz[V];
+    float dz[V], xx[V];
     vload(dy + o, dz);
+    if (s1 || relu == 2) vload(x + o, xx);
     if (relu == 1) {
       float yy[V];
       vload(y + o, yy);
 #pragma unroll
       for (int i = 0; i < V; ++i) if (!(yy[i] > 0.f)) dz[i] = 0.f;
-    }
-    float xx[V];
-    if (s1 || relu == 2) vload(x + o, xx);
-    if (relu == 2) {
+    } else if (relu == 2) {
 #pragma unroll
-      for (int i = 0; i < V; ++i)
-        if (!(fmaf(xx[i], __ldg(scale + c0 + i), __ldg(shift + c0 + i)) > 0.f)) dz[i] = 0.f;
+      for (int i = 0; i < V; ++i) if (!(fmaf(xx[i], sc[i], sh[i]) > 0.f)) dz[i] = 0.f;
     }
     if (dres) vstore(dres + o, dz);
     float g[V];
     if (s1) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (xx[i] - __ldg(mean + c0 + i)) * __ldg(rstd + c0 + i);
-        g[i] = (dz[i] - (float)(s1[c0 + i] * inv_m) - xh * (float)(s2[c0 + i] * inv_m)) * __ldg(scale + c0 + i);
-      }
+      for (int i = 0; i < V; ++i) g[i] = fmaf(dz[i], A[i], fmaf(xx[i], Bc[i], D[i]));
     } else {
 #pragma unroll
-      for (int i = 0; i < V; ++i) g[i] = dz[i] * __ldg(scale + c0 + i);
+      for (int i = 0; i < V; ++i) g[i] = dz[i] * A[i];
     }
     vstore(dx + o, g);
   }
@@ -795,4 +813,113 @@ extern "C" int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, i
   else
     embed_sum_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const __nv_bfloat16*)dx, nullptr, (__nv_bfloat16*)dpos);
   P2R_RETURN_LAUNCH("p2r_embed_sum_grad");
+}
+
+
+// ================================================================================================
+// small-K linear layers (the 3 -> 64 first layers of pos_embed / sk_feat, stgcn.py:45-50): K <= 4 input channels,
+// so the layer is a memory-bound elementwise map, not a GEMM.
+//   forward : y[m, n] = sum_c x[m, c] * W[n, c] (+ bias[n])        thread = VEC outputs of one row, W in registers
+//   d weight: dW[n, c] = sum_m dz[m, n] * x[m, c]                  column reduction with K accumulators per channel
+// (no input gradient: the inputs are data).  N % VEC == 0 and (256 * VEC) % N == 0.
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+smallk_linear_kernel(long long M, int N, int K, const T* __restrict__ x, const float* __restrict__ W,
+                     const float* __restrict__ bias, T* __restrict__ y) {
+  constexpr int V = VecN<T>::N;
+  const int n0 = (threadIdx.x * V) % N;
+  const int tpr = N / V;
+  float w[V][4], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    b[i] = bias ? __ldg(bias + n0 + i) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) w[i][c] = c < K ? __ldg(W + (size_t)(n0 + i) * K + c) : 0.f;
+  }
+  const long long nvec = M * tpr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
+    const long long m = e / tpr;
+    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < K; ++c) xv[c] = ldf<T>(x + (size_t)m * K + c);
+    float o[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float t = b[i];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) t = fmaf(xv[c], w[i][c], t);
+      o[i] = t;
+    }
+    vstore(y + (size_t)m * N + n0, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+smallk_dw_kernel(long long M, int N, int K, const T* __restrict__ dz, const T* __restrict__ x, int rows_per_cta,
+                 float* __restrict__ dW) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sh[256 * V];
+  const int tpr = N / V, rl = 256 / tpr;
+  const int cl = threadIdx.x % tpr, r_lane = threadIdx.x / tpr;
+  const int n0 = cl * V;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[4][V];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[c][i] = 0.f;
+  for (long long r = r0 + r_lane; r < r1; r += rl) {
+    float g[V];
+    vload(dz + (size_t)r * N + n0, g);
+    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < K; ++c) xv[c] = ldf<T>(x + (size_t)r * K + c);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[c][i] = fmaf(g[i], xv[c], acc[c][i]);
+  }
+  for (int c = 0; c < K; ++c) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) sh[threadIdx.x * V + i] = acc[c][i];
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += 256) {
+      const int t = n / V, i = n % V;
+      float tot = 0.f;
+      for (int l = 0; l < rl; ++l) tot += sh[(l * tpr + t) * V + i];
+      atomicAdd(dW + (size_t)n * K + c, tot);
+    }
+  }
+}
+
+extern "C" int p2r_smallk_linear(const void* x, const float* W, const float* bias, int dtype, long long M, int N, int K,
+                                 void* y, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && K >= 1 && K <= 4 && N > 0, "p2r_smallk_linear");
+  const int V = dtype == 0 ? 4 : 8;
+  P2R_CHECK_ARG(N % V == 0 && (256 * V) % N == 0, "p2r_smallk_linear (N must divide 256*VEC)");
+  if (M == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (M * (N / V) + 255) / 256);
+  if (dtype == 0)
+    smallk_linear_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const float*)x, W, bias, (float*)y);
+  else
+    smallk_linear_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)x, W, bias, (__nv_bfloat16*)y);
+  P2R_RETURN_LAUNCH("p2r_smallk_linear");
+}
+
+// dW f32[N,K] must be zero-filled by the caller.
+extern "C" int p2r_smallk_dw(const void* dz, const void* x, int dtype, long long M, int N, int K, float* dW,
+                             void* stream) {
+  P2R_CHECK_ARG(M >= 0 && K >= 1 && K <= 4 && N > 0, "p2r_smallk_dw");
+  const int V = dtype == 0 ? 4 : 8;
+  P2R_CHECK_ARG(N % V == 0 && 256 % (N / V) == 0, "p2r_smallk_dw");
+  if (M == 0) return 0;
+  int rpc;
+  const int grid = colreduce_grid(M, &rpc);
+  if (dtype == 0)
+    smallk_dw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const float*)dz, (const float*)x, rpc, dW);
+  else
+    smallk_dw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)dz, (const __nv_bfloat16*)x, rpc, dW);
+  P2R_RETURN_LAUNCH("p2r_smallk_dw");
 }

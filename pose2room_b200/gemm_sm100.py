@@ -99,8 +99,10 @@ class _Backend:
         # dx[M,K] = dz[M,N] . W[N,K]:  A = dz (K-major over n), B = W viewed as [K_red = N, N_out = K] -> MN-major
         w = weight.to(torch.bfloat16)
         n_out = w.shape[1]
-        bn = 0 if n_out % 64 == 0 or n_out > 256 else 0
-        return gemm(dz, w, False, True, out_dtype=torch.bfloat16, block_n=bn)
+        if n_out % 160 == 0 and n_out >= 640:
+            # graph-conv sized layers: a 5 MB transpose of W_eff buys the zero-waste 128x160 K-major tiling
+            return gemm(dz, w.t().contiguous(), False, False, out_dtype=torch.bfloat16, block_n=160)
+        return gemm(dz, w, False, True, out_dtype=torch.bfloat16)
 
     @staticmethod
     def linear_dw(dz, x):
@@ -109,7 +111,8 @@ class _Backend:
         n, k = dz.shape[1], x.shape[1]
         tiles = ((n + 127) // 128) * ((k + 127) // 128)
         splits = max(1, min((296 + tiles - 1) // tiles, (m + 4095) // 4096))
-        return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits)
+        # >= 148 tiles of 128x128 (graph-conv: 13 x 13 = 169) fill the chip without split-K
+        return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits, block_n=128 if tiles >= 148 else 0)
 
     @staticmethod
     def supports_tconv(shape, co):

@@ -93,13 +93,25 @@ def _col_sum(dy, y=None, relu=False):
     return s1.float()
 
 
+def _smallk_ok(x, n, k, relu):
+    v = 8 if x.dtype == torch.bfloat16 else 4
+    return k <= 4 and not relu and n % v == 0 and (256 * v) % n == 0 and 256 % (n // v) == 0
+
+
 class _Linear(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
         x = x if x.is_contiguous() else x.contiguous()
         tc = _TC_GEMM["fn"]
         with _Timed("fwd", x.shape[0], weight.shape[0], x.shape[1]):
-            if tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
+            if _smallk_ok(x, weight.shape[0], x.shape[1], relu):
+                y = torch.empty(x.shape[0], weight.shape[0], dtype=x.dtype, device=x.device)
+                wf = weight.float().contiguous()
+                bf = bias.float().contiguous() if bias is not None else None
+                with torch.cuda.device(x.device):
+                    _lib.call("p2r_smallk_linear", x.data_ptr(), wf.data_ptr(), _ptr(bf), _DT[x.dtype], x.shape[0],
+                              weight.shape[0], x.shape[1], y.data_ptr(), _stream())
+            elif tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
                 y = tc.linear_fwd(x, weight, bias, relu)
             else:
                 y = sgemm(x, weight, False, True, bias, relu, out_dtype=x.dtype)
@@ -128,7 +140,12 @@ class _Linear(Function):
                 dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
         if ctx.needs_input_grad[1]:
             with _Timed("dw", m, n, k):
-                if use_tc:
+                if _smallk_ok(x, n, k, ctx.relu):
+                    dw = torch.zeros(n, k, dtype=torch.float32, device=x.device)
+                    with torch.cuda.device(x.device):
+                        _lib.call("p2r_smallk_dw", dz.data_ptr(), x.data_ptr(), _DT[x.dtype], m, n, k, dw.data_ptr(),
+                                  _stream())
+                elif use_tc:
                     dw = tc.linear_dw(dz, x)
                 else:
                     dw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
