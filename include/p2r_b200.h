@@ -122,6 +122,9 @@ int p2r_col_stats(const void* x, int dtype, long long M, int C, double* s1, doub
 int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
                       const float* rstd, int relu, double* s1, double* s2, const float* scale, const float* shift,
                       void* stream);
+/* column sums of a wide [M,C] matrix (any C % VEC == 0), e.g. the 1600-wide graph-conv bias gradient; s1 zeroed by caller */
+int p2r_col_sum_wide(const void* dy, int dtype, long long M, int C, double* s1, void* stream);
+
 /* training-mode BatchNorm statistics -> mean, rstd, fused scale/shift; updates running stats like torch */
 int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,

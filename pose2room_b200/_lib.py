@@ -45,6 +45,7 @@ SIGNATURES = {
     "p2r_embed_sum_grad": [_vp, _c_int, _c_ll, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_linear": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_dw": [_vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],
+    "p2r_col_sum_wide": [_vp, _c_int, _c_ll, _c_int, _vp, _vp],
     "p2r_col_stats": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp],
     "p2r_col_bwd_stats": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
     "p2r_bn_finalize": [_c_int, _c_ll, _vp, _vp, _vp, _vp, _c_float, _c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -261,6 +261,7 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
     if (MODE == 1 && mean != nullptr) { mu[i] = __ldg(mean + c0 + i); rs[i] = __ldg(rstd + c0 + i); }
     if (MODE == 1 && relu == 2) { sc[i] = __ldg(scale + c0 + i); sh[i] = __ldg(shift + c0 + i); }
   }
+#pragma unroll 4
   for (long long r = r0 + r_lane; r < r1; r += rl) {
     const size_t o = (size_t)r * C + c0;
     if (MODE == 0) {
@@ -922,4 +923,58 @@ extern "C" int p2r_smallk_dw(const void* dz, const void* x, int dtype, long long
   else
     smallk_dw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)dz, (const __nv_bfloat16*)x, rpc, dW);
   P2R_RETURN_LAUNCH("p2r_smallk_dw");
+}
+
+
+// column sums of a WIDE matrix [M, C] (C a multiple of VEC, any size: the 1600-wide graph-conv output whose bias
+// gradient is needed): grid.x tiles the columns (32 vectors per CTA), grid.y tiles the rows; s1 zero-filled by the caller.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_wide_kernel(long long M, int C, const T* __restrict__ dy, int rows_per_cta, double* __restrict__ s1) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sh[256 * V];
+  const int cv = threadIdx.x & 31, r_lane = threadIdx.x >> 5;   // 32 column vectors x 8 row lanes
+  const int c0 = (blockIdx.x * 32 + cv) * V;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  if (c0 < C) {
+#pragma unroll 4
+    for (long long r = r0 + r_lane; r < r1; r += 8) {
+      float v[V];
+      vload(dy + (size_t)r * C + c0, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sh[threadIdx.x * V + i] = acc[i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * V; e += 256) {
+    const int t = e / V, i = e % V;
+    const int c = (blockIdx.x * 32 + t) * V + i;
+    if (c < C) {
+      double tot = 0.0;
+      for (int l = 0; l < 8; ++l) tot += (double)sh[(l * 32 + t) * V + i];
+      atomicAdd(s1 + c, tot);
+    }
+  }
+}
+
+extern "C" int p2r_col_sum_wide(const void* dy, int dtype, long long M, int C, double* s1, void* stream) {
+  const int V = dtype == 0 ? 4 : 8;
+  P2R_CHECK_ARG(M >= 0 && C > 0 && C % V == 0, "p2r_col_sum_wide");
+  if (M == 0) return 0;
+  const int col_tiles = p2r_ceil_div(C, 32 * V);
+  int row_tiles = (P2R_SM_COUNT * 8 + col_tiles - 1) / col_tiles;
+  long long rpc = (M + row_tiles - 1) / row_tiles;
+  if (rpc < 64) rpc = 64;
+  row_tiles = (int)((M + rpc - 1) / rpc);
+  dim3 grid(col_tiles, row_tiles);
+  if (dtype == 0)
+    colsum_wide_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const float*)dy, (int)rpc, s1);
+  else
+    colsum_wide_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, (const __nv_bfloat16*)dy, (int)rpc, s1);
+  P2R_RETURN_LAUNCH("p2r_col_sum_wide");
 }

@@ -110,9 +110,10 @@ class _Backend:
         m = dz.shape[0]
         n, k = dz.shape[1], x.shape[1]
         tiles = ((n + 127) // 128) * ((k + 127) // 128)
+        if tiles >= 148:  # graph-conv: 13 x 13 = 169 tiles of 128x128 fill the chip without split-K / atomics
+            return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128)
         splits = max(1, min((296 + tiles - 1) // tiles, (m + 4095) // 4096))
-        # >= 148 tiles of 128x128 (graph-conv: 13 x 13 = 169) fill the chip without split-K
-        return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits, block_n=128 if tiles >= 148 else 0)
+        return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits)
 
     @staticmethod
     def supports_tconv(shape, co):

@@ -84,6 +84,12 @@ def sgemm(a, b, trans_a=False, trans_b=True, bias=None, relu=False, out_dtype=No
 def _col_sum(dy, y=None, relu=False):
     """sum over rows of dz = relu ? dy*(y>0) : dy -> float32 [C] (bias gradients)."""
     m, c = dy.shape
+    vec = 8 if dy.dtype == torch.bfloat16 else 4
+    if not relu and c > 256 and c % vec == 0:     # wide matrices (the 1600-column graph-conv output)
+        s1 = torch.zeros(c, dtype=torch.float64, device=dy.device)
+        with torch.cuda.device(dy.device):
+            _lib.call("p2r_col_sum_wide", dy.data_ptr(), _DT[dy.dtype], m, c, s1.data_ptr(), _stream())
+        return s1.float()
     if c > 256 and c % 256 or c <= 256 and 256 % c:
         return (dy.float() if not relu else dy.float() * (y > 0)).sum(0)  # odd channel counts (259, 100, 24): tiny tensors
     s1 = torch.zeros(c, dtype=torch.float64, device=dy.device)

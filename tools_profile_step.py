@@ -46,7 +46,7 @@ for _ in range(3):
 t1 = time.perf_counter()
 torch.cuda.synchronize()
 print("python-side ms/step (launch only): %.2f" % ((t1 - t0) / 3 * 1e3))
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
 from torch.autograd import DeviceType
@@ -62,3 +62,10 @@ tot = sum(r[1] for r in rows)
 print("total device time %.2f ms over %d kernel names" % (tot / 1e3, len(rows)))
 for k, t, c in rows[:45]:
     print("%8.3f ms %5.1f%% x%-4d %s" % (t / 1e3, 100 * t / tot, c, k[:110]))
+
+print("---- largest torch glue ops by device time (with shapes)")
+glue = [(e.key, str(e.input_shapes)[:90], e.device_time_total, e.count) for e in prof.key_averages(group_by_input_shape=True)
+        if e.device_time_total > 0 and e.key.startswith("aten::")]
+glue.sort(key=lambda r: -r[2])
+for k, sh, t, c in glue[:28]:
+    print("%8.3f ms x%-3d %-28s %s" % (t / 1e3, c, k, sh))
