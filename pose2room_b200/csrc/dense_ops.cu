@@ -9,6 +9,7 @@
 //
 // Storage type T is float or __nv_bfloat16; arithmetic is always fp32 (double for BN column sums).
 #include "p2r_common.cuh"
+#include <stdlib.h>
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
@@ -237,8 +238,10 @@ colreduce_kernel(long long M, int C, const T* __restrict__ x, const T* __restric
 }
 
 // Vectorised variant: thread = VEC consecutive channels of one row lane; C % VEC == 0, 256 % (C/VEC) == 0.
+// MODE 1 accumulates b = sum dz*x and folds s2 = rstd * (b - mean * s1) when the CTA's partials are combined (in
+// double), so mean / rstd never sit in registers inside the streaming loop; two rows are in flight per iteration.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int rows_per_cta,
                      double* __restrict__ s1, double* __restrict__ s2, const float* __restrict__ scale = nullptr,
@@ -251,47 +254,58 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
   const int c0 = cl * V;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(M, r0 + rows_per_cta);
-  float a1[V], a2[V], mu[V], rs[V], sc[V], sh[V];
+  float a1[V], a2[V], sc[V], sh[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     a1[i] = a2[i] = 0.f;
-    mu[i] = 0.f;
-    rs[i] = 1.f;
     sc[i] = sh[i] = 0.f;
-    if (MODE == 1 && mean != nullptr) { mu[i] = __ldg(mean + c0 + i); rs[i] = __ldg(rstd + c0 + i); }
     if (MODE == 1 && relu == 2) { sc[i] = __ldg(scale + c0 + i); sh[i] = __ldg(shift + c0 + i); }
   }
-#pragma unroll 4
-  for (long long r = r0 + r_lane; r < r1; r += rl) {
-    const size_t o = (size_t)r * C + c0;
+  auto body = [&](const float (&p)[V], const float (&q)[V], const float (&w)[V]) {
+    // MODE 0: p = x.   MODE 1: p = dy, q = x (if any), w = y (relu == 1)
     if (MODE == 0) {
-      float v[V];
-      vload(x + o, v);
 #pragma unroll
-      for (int i = 0; i < V; ++i) { a1[i] += v[i]; a2[i] = fmaf(v[i], v[i], a2[i]); }
+      for (int i = 0; i < V; ++i) { a1[i] += p[i]; a2[i] = fmaf(p[i], p[i], a2[i]); }
     } else {
-      float dz[V];
-      vload(dy + o, dz);
-      if (relu == 1) {
-        float yy[V];
-        vload(y + o, yy);
 #pragma unroll
-        for (int i = 0; i < V; ++i) if (!(yy[i] > 0.f)) dz[i] = 0.f;
+      for (int i = 0; i < V; ++i) {
+        float dz = p[i];
+        if (relu == 1 && !(w[i] > 0.f)) dz = 0.f;
+        if (relu == 2 && !(fmaf(q[i], sc[i], sh[i]) > 0.f)) dz = 0.f;
+        a1[i] += dz;
+        a2[i] = fmaf(dz, q[i], a2[i]);
       }
-      if (x != nullptr) {
-        float xx[V];
-        vload(x + o, xx);
-        if (relu == 2) {  // ReLU mask recomputed from the pre-BN input: no read of the activation output
-#pragma unroll
-          for (int i = 0; i < V; ++i)
-            if (!(fmaf(xx[i], sc[i], sh[i]) > 0.f)) dz[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < V; ++i) a2[i] = fmaf(dz[i], (xx[i] - mu[i]) * rs[i], a2[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < V; ++i) a1[i] += dz[i];
     }
+  };
+  const bool need_x = MODE == 1 && x != nullptr;
+  long long r = r0 + r_lane;
+  for (; r + rl < r1; r += 2 * rl) {   // two rows per iteration, all loads issued before use
+    const size_t o0 = (size_t)r * C + c0, o1 = (size_t)(r + rl) * C + c0;
+    float p0[V], p1[V], q0[V], q1[V], w0[V], w1[V];
+    if (MODE == 0) { vload(x + o0, p0); vload(x + o1, p1); }
+    else { vload(dy + o0, p0); vload(dy + o1, p1); }
+    if (need_x) { vload(x + o0, q0); vload(x + o1, q1); }
+    else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) q0[i] = q1[i] = 0.f;
+    }
+    if (MODE == 1 && relu == 1) { vload(y + o0, w0); vload(y + o1, w1); }
+    else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) w0[i] = w1[i] = 1.f;
+    }
+    body(p0, q0, w0);
+    body(p1, q1, w1);
+  }
+  for (; r < r1; r += rl) {
+    const size_t o0 = (size_t)r * C + c0;
+    float p0[V], q0[V], w0[V];
+    if (MODE == 0) vload(x + o0, p0); else vload(dy + o0, p0);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { q0[i] = 0.f; w0[i] = 1.f; }
+    if (need_x) vload(x + o0, q0);
+    if (MODE == 1 && relu == 1) vload(y + o0, w0);
+    body(p0, q0, w0);
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) { sh1[threadIdx.x * V + i] = a1[i]; sh2[threadIdx.x * V + i] = a2[i]; }
@@ -302,13 +316,27 @@ colreduce_vec_kernel(long long M, int C, const T* __restrict__ x, const T* __res
     double t1 = 0.0, t2 = 0.0;
     for (int l = 0; l < rl; ++l) { t1 += (double)sh1[(l * tpr + t) * V + i]; t2 += (double)sh2[(l * tpr + t) * V + i]; }
     atomicAdd(s1 + c, t1);
-    if (s2) atomicAdd(s2 + c, t2);
+    if (s2) {
+      if (MODE == 1 && mean != nullptr) t2 = (double)__ldg(rstd + c) * (t2 - (double)__ldg(mean + c) * t1);
+      atomicAdd(s2 + c, t2);
+    }
   }
+}
+
+static int colreduce_ctas_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("P2R_COLREDUCE_CTAS_PER_SM");  // tuning knob (default 8)
+    v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
+  }
+  return v;
 }
 
 static int colreduce_grid(long long M, int* rows_per_cta) {
   // ~8 CTAs per SM, at least 64 rows each
-  long long target = (M + (long long)P2R_SM_COUNT * 8 - 1) / ((long long)P2R_SM_COUNT * 8);
+  const long long ctas = (long long)P2R_SM_COUNT * colreduce_ctas_per_sm();
+  long long target = (M + ctas - 1) / ctas;
   if (target < 64) target = 64;
   *rows_per_cta = (int)target;
   return (int)((M + target - 1) / target);

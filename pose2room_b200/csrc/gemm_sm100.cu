@@ -122,7 +122,9 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = STAGES_OVERRIDE > 0 ? STAGES_OVERRIDE : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 3 : 4));
-  static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+  static constexpr int ACC_STAGES = BLOCK_N <= 128 ? 2 : 1;   // double-buffered accumulator when 2 x 2 CTAs fit in TMEM
+  static constexpr int ACC_COLS = ACC_STAGES * BLOCK_N;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -130,28 +132,36 @@ template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  OutT* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ bias, int relu,
-                 int kblocks_per_split, const TapArgs tap) {
+                 int kblocks_per_split, const TapArgs tap, int tiles_per_cta) {
   using S = GemmSmem<BLOCK_N, NSTAGE>;
+  constexpr int ACC = S::ACC_STAGES;   // accumulator buffers in TMEM (2: the epilogue of tile t overlaps the MMAs of t+1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
   uint64_t* empty = full + S::STAGES;
-  uint64_t* tmem_full = empty + S::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + S::STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GEMM_BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int n0 = blockIdx.x * BLOCK_N;
   const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int kb0 = blockIdx.z * kblocks_per_split;
   const int kb1 = min(total_kb, kb0 + kblocks_per_split);
   const int nkb = kb1 - kb0;
+  const int tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int ntiles = min(tiles_per_cta, tiles_m - tile0);   // m-tiles this CTA walks through
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
       p2r_mbar_init(full + s, 1);
       p2r_mbar_init(empty + s, 1);
     }
-    p2r_mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      p2r_mbar_init(tmem_full + a, 1);
+      p2r_mbar_init(tmem_empty + a, 4);   // one arrival per epilogue warp
+    }
     p2r_fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -167,40 +177,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % S::STAGES;
-        const uint32_t ph = (uint32_t)(i / S::STAGES) & 1u;
-        p2r_mbar_wait(empty + s, ph ^ 1u);
-        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + S::A_BYTES;
-        p2r_mbar_expect_tx(full + s, S::STAGE_BYTES);
-        const int k0 = (kb0 + i) * GEMM_BLOCK_K;
-        if (TAP == 1) {
-          const int t = (kb0 + i) / tap.kb_per_tap;
-          const int kc = ((kb0 + i) % tap.kb_per_tap) * GEMM_BLOCK_K;
-          tma_load_3d(a_dst, &tma_a, full + s, kc, (m0 % tap.rows_per_sample) + tap.shift0 + t * tap.shift_step,
-                      m0 / tap.rows_per_sample);                        // box {64 c, 128 rows, 1 sample}
-        } else if (!A_MN) {
-          tma_load_2d(a_dst, &tma_a, full + s, k0, m0);                 // box {64 k, 128 m}
-        } else {
+      int it = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int m0 = (tile0 + t) * GEMM_BLOCK_M;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (uint32_t)(it / S::STAGES) & 1u;
+          p2r_mbar_wait(empty + s, ph ^ 1u);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          p2r_mbar_expect_tx(full + s, S::STAGE_BYTES);
+          const int k0 = (kb0 + i) * GEMM_BLOCK_K;
+          if (TAP == 1) {
+            const int tp = (kb0 + i) / tap.kb_per_tap;
+            const int kc = ((kb0 + i) % tap.kb_per_tap) * GEMM_BLOCK_K;
+            tma_load_3d(a_dst, &tma_a, full + s, kc, (m0 % tap.rows_per_sample) + tap.shift0 + tp * tap.shift_step,
+                        m0 / tap.rows_per_sample);                        // box {64 c, 128 rows, 1 sample}
+          } else if (!A_MN) {
+            tma_load_2d(a_dst, &tma_a, full + s, k0, m0);                 // box {64 k, 128 m}
+          } else {
 #pragma unroll
-          for (int h = 0; h < GEMM_BLOCK_M / 64; ++h)                   // boxes {64 m, 64 k}
-            tma_load_2d(a_dst + h * (GEMM_BLOCK_K * 128), &tma_a, full + s, m0 + h * 64, k0);
-        }
-        if (TAP == 2) {
-#pragma unroll
-          for (int h = 0; h < BLOCK_N / 64; ++h) {                      // boxes {64 c, 64 rows, 1 sample}
-            const int n = n0 + h * 64;
-            const int t = n / tap.channels;
-            tma_load_3d(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, n % tap.channels,
-                        (k0 % tap.rows_per_sample) + tap.shift0 + t * tap.shift_step, k0 / tap.rows_per_sample);
+            for (int h = 0; h < GEMM_BLOCK_M / 64; ++h)                   // boxes {64 m, 64 k}
+              tma_load_2d(a_dst + h * (GEMM_BLOCK_K * 128), &tma_a, full + s, m0 + h * 64, k0);
           }
-        } else if (!B_MN) {
-          tma_load_2d(b_dst, &tma_b, full + s, k0, n0);                 // box {64 k, BLOCK_N n}
-        } else {
+          if (TAP == 2) {
 #pragma unroll
-          for (int h = 0; h < BLOCK_N / 64; ++h)                        // boxes {64 n, 64 k}
-            tma_load_2d(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, n0 + h * 64, k0);
+            for (int h = 0; h < BLOCK_N / 64; ++h) {                      // boxes {64 c, 64 rows, 1 sample}
+              const int n = n0 + h * 64;
+              const int tp = n / tap.channels;
+              tma_load_3d(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, n % tap.channels,
+                          (k0 % tap.rows_per_sample) + tap.shift0 + tp * tap.shift_step, k0 / tap.rows_per_sample);
+            }
+          } else if (!B_MN) {
+            tma_load_2d(b_dst, &tma_b, full + s, k0, n0);                 // box {64 k, BLOCK_N n}
+          } else {
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / 64; ++h)                        // boxes {64 n, 64 k}
+              tma_load_2d(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, n0 + h * 64, k0);
+          }
         }
       }
     }
@@ -208,83 +222,100 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(GEMM_BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % S::STAGES;
-        const uint32_t ph = (uint32_t)(i / S::STAGES) & 1u;
-        p2r_mbar_wait(full + s, ph);
-        tc_fence_after();
-        const uint32_t a_addr = p2r_smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + S::A_BYTES;
-#pragma unroll
-        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-          const uint64_t adesc = A_MN ? make_desc(a_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
-                                      : make_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? make_desc(b_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
-                                      : make_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+      int it = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int as = t % ACC;
+        if (t >= ACC) {   // the epilogue must have drained this accumulator buffer
+          p2r_mbar_wait(tmem_empty + as, (uint32_t)((t / ACC) - 1) & 1u);
+          tc_fence_after();
         }
-        umma_commit(empty + s);  // stage reusable once these MMAs have read it
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (uint32_t)(it / S::STAGES) & 1u;
+          p2r_mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = p2r_smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_desc(a_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
+                                        : make_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_desc(b_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
+                                        : make_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_acc, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty + s);        // stage reusable once these MMAs have read it
+        }
+        umma_commit(tmem_full + as);     // accumulator of tile t complete
       }
-      umma_commit(tmem_full);    // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    p2r_mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const bool row_ok = row < M;
-    OutT* crow = C + (size_t)row * ldc;
     const bool vec_ok = ((size_t)ldc * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int as = t % ACC;
+      const int row = (tile0 + t) * GEMM_BLOCK_M + q * 32 + lane;
+      p2r_mbar_wait(tmem_full + as, (uint32_t)(t / ACC) & 1u);
+      tc_fence_after();
+      const bool row_ok = row < M;
+      OutT* crow = C + (size_t)row * ldc;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int col0 = n0 + c0;
-      if (row_ok && col0 < N) {  // (no `continue`: the next tcgen05.ld is warp-aligned)
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (!ATOMIC) {
-          if (bias != nullptr && col0 + j < N) x += __ldg(bias + col0 + j);
-          if (relu) x = fmaxf(x, 0.f);
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
+        if (c0 + 32 >= BLOCK_N) {   // last read of this accumulator buffer: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) p2r_mbar_arrive(tmem_empty + as);
         }
-        f[j] = x;
-      }
-      if (ATOMIC) {
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) atomicAdd(reinterpret_cast<float*>(crow) + col0 + j, f[j]);
-      } else if (vec_ok && col0 + 32 <= N) {
-        if (sizeof(OutT) == 2) {
-          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+        const int col0 = n0 + c0;
+        if (row_ok && col0 < N) {  // (no `continue`: the next tcgen05.ld is warp-aligned)
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            dst[j] = pk;
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (!ATOMIC) {
+              if (bias != nullptr && col0 + j < N) x += __ldg(bias + col0 + j);
+              if (relu) x = fmaxf(x, 0.f);
+            }
+            f[j] = x;
           }
-        } else {
-          float4* dst = reinterpret_cast<float4*>(crow + col0);
+          if (ATOMIC) {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) atomicAdd(reinterpret_cast<float*>(crow) + col0 + j, f[j]);
+          } else if (vec_ok && col0 + 32 <= N) {
+            if (sizeof(OutT) == 2) {
+              uint4* dst = reinterpret_cast<uint4*>(crow + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                dst[j] = pk;
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(crow + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) {
+                if (sizeof(OutT) == 2) reinterpret_cast<__nv_bfloat16*>(crow)[col0 + j] = __float2bfloat16_rn(f[j]);
+                else reinterpret_cast<float*>(crow)[col0 + j] = f[j];
+              }
+          }
         }
-      } else {
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) {
-            if (sizeof(OutT) == 2) reinterpret_cast<__nv_bfloat16*>(crow)[col0 + j] = __float2bfloat16_rn(f[j]);
-            else reinterpret_cast<float*>(crow)[col0 + j] = f[j];
-          }
+        __syncwarp();
       }
-      }
-      __syncwarp();
     }
     tc_fence_before();
   }
@@ -357,12 +388,22 @@ static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* 
     kps = (total_kb + splits - 1) / splits;
     splits = (total_kb + kps - 1) / kps;
   } else splits = 1;
-  dim3 grid(p2r_ceil_div(N, BLOCK_N), p2r_ceil_div(M, GEMM_BLOCK_M), splits);
+  // several m-tiles per CTA when there are many more tiles than CTA slots: barrier / TMEM set-up is amortised and the
+  // next tile's TMA loads and MMAs run under the current tile's epilogue (double-buffered accumulator)
+  const long long tiles_m = p2r_ceil_div(M, GEMM_BLOCK_M), tiles_n = p2r_ceil_div(N, BLOCK_N);
+  int tpc = 1;
+  if (splits == 1 && S::ACC_STAGES == 2) {
+    const long long slots = (long long)P2R_SM_COUNT * 8;
+    tpc = (int)((tiles_m * tiles_n) / slots);
+    if (tpc < 1) tpc = 1;
+    if (tpc > 8) tpc = 8;
+  }
+  dim3 grid((unsigned)tiles_n, (unsigned)p2r_ceil_div(tiles_m, tpc), splits);
 #define GEMM_GO(OutT, ATOMIC)                                                                                   \
   do {                                                                                                          \
     auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE>;                               \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);                          \
-    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap);           \
+    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc);      \
   } while (0)
   if (splits > 1) GEMM_GO(float, true);
   else if (c_dtype == 1) GEMM_GO(__nv_bfloat16, false);
