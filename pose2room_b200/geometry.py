@@ -71,6 +71,27 @@ def get_graph_offset(x, k=20, idx=None, x_coord=None):
     return _GraphOffset.apply(x, idx.contiguous().long())
 
 
+def get_graph_feature(x, k=20, idx=None, x_coord=None):
+    """vn_dgcnn_util.py:13-40: x (B,d,3,N) -> (B,2d,3,N,k) = cat(x[idx]-x, x) (edge features of the VN-DGCNN stage)."""
+    b, n = x.size(0), x.size(3)
+    flat = x.reshape(b, -1, n)
+    off = get_graph_offset(flat, k=k, idx=idx, x_coord=x_coord)            # (B,N,k,d,3)
+    d = flat.size(1) // 3
+    centre = flat.transpose(2, 1).reshape(b, n, 1, d, 3).expand(b, n, off.size(2), d, 3)
+    return torch.cat((off, centre), dim=3).permute(0, 3, 4, 1, 2).contiguous()
+
+
+def get_graph_feature_cross(x, k=20, idx=None):
+    """vn_dgcnn_util.py:97-121: as get_graph_feature plus the cross product (x[idx] x x) as a third block."""
+    b, n = x.size(0), x.size(3)
+    flat = x.reshape(b, -1, n)
+    off = get_graph_offset(flat, k=k, idx=idx)
+    d = flat.size(1) // 3
+    centre = flat.transpose(2, 1).reshape(b, n, 1, d, 3).expand(b, n, off.size(2), d, 3)
+    cross = torch.cross(off + centre, centre, dim=-1)
+    return torch.cat((off, centre, cross), dim=3).permute(0, 3, 4, 1, 2).contiguous()
+
+
 # ----------------------------------------------------------------------------------------- losses
 def huber_loss(error, delta=1.0):
     """nn_distance.py:15-32 (elementwise torch; tiny tensors)."""
@@ -172,6 +193,21 @@ def _nms_numpy_front(boxes, thr, old_type, with_cls):
     keep, order = nms3d_batched(t[None, :, 0:6], t[None, :, 6], None, cls, thr, old_type)
     order = order[0].cpu().numpy()
     return [int(i) for i in order if i >= 0]
+
+
+def nms_2d_faster(boxes, overlap_threshold, old_type=False):
+    """nms.py:7-39: boxes (K,5) [x1,y1,x2,y2,score].  Runs on the 3-D kernel with unit z extent: area*(1-0) and
+    (w*h)*1 are the same fp64 values as the reference's 2-D products, so the selection is identical."""
+    boxes = np.asarray(boxes, dtype=np.float64)
+    if boxes.shape[0] == 0:
+        return []
+    k = boxes.shape[0]
+    b3 = np.zeros((k, 7))
+    b3[:, 0:2] = boxes[:, 0:2]
+    b3[:, 3:5] = boxes[:, 2:4]
+    b3[:, 5] = 1.0
+    b3[:, 6] = boxes[:, 4]
+    return _nms_numpy_front(b3, overlap_threshold, old_type, False)
 
 
 def nms_3d_faster(boxes, overlap_threshold, old_type=False):

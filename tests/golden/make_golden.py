@@ -75,6 +75,7 @@ def geometry(ns):
         out["nms%d_pick" % t] = np.array(ns.nms.nms_3d_faster(boxes[:, :7], 0.10), np.int64)
         out["nms%d_pick_old" % t] = np.array(ns.nms.nms_3d_faster(boxes[:, :7], 0.25, old_type=True), np.int64)
         out["nms%d_pick_cls" % t] = np.array(ns.nms.nms_3d_faster_samecls(boxes, 0.10), np.int64)
+        out["nms%d_pick_2d" % t] = np.array(ns.nms.nms_2d_faster(boxes[:, [0, 1, 3, 4, 6]], 0.10), np.int64)
     # --- parse_predictions (reference: scipy Delaunay far-box test + numpy NMS) on synthetic network outputs
     B, K, T, J = 4, 128, 256, 25
     data = synthetic.make_batch(B, T, J, seed=99)
@@ -180,6 +181,18 @@ def pointnet2(ns):
     kidx = ns.vn_dgcnn_util.knn(xk, 8)
     goff = ns.vn_dgcnn_util.get_graph_offset(xk, k=8, idx=kidx)
     out.update(knn_x=xk.numpy(), knn_idx=kidx.numpy(), knn_offset=goff.numpy())
+    xg = torch.from_numpy(rng.normal(size=(2, 2, 3, 64)).astype(np.float32))        # (B, d, 3, N)
+    gidx = ns.vn_dgcnn_util.knn(xg.view(2, -1, 64), 8)
+    out.update(gf_x=xg.numpy(), gf_idx=gidx.numpy(),
+               gf_feature=ns.vn_dgcnn_util.get_graph_feature(xg, k=8, idx=gidx).numpy(),
+               gf_cross=ns.vn_dgcnn_util.get_graph_feature_cross(xg, k=8, idx=gidx).numpy())
+    # feature-propagation module (three_nn + three_interpolate + shared MLP without BN)
+    torch.manual_seed(6)
+    fp = ns.pointnet2_modules.PointnetFPModule(mlp=[C + C, 16, 8], bn=False)
+    fp_out = fp(unknown, known, feats.detach(), kfeat.detach())
+    out.update(fp_w0=fp.mlp[0].weight.detach().numpy(), fp_b0=fp.mlp[0].bias.detach().numpy(),
+               fp_w1=fp.mlp[2].weight.detach().numpy(), fp_b1=fp.mlp[2].bias.detach().numpy(),
+               fp_out=fp_out.detach().numpy())
     np.savez_compressed(osp.join(OUT, "pointnet2.npz"), **out)
     print("pointnet2.npz:", len(out), "arrays")
 

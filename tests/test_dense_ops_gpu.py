@@ -63,9 +63,13 @@ def test_batchnorm_act_train_fwd_bwd(cuda, M, C, relu, res):
     go = torch.randn(M, C, generator=g).to(cuda)
     y.backward(go)
     ref.backward(go.double())
-    _close(x.grad, xr.grad, rtol=1e-3, atol=1e-5)
-    _close(bn.weight.grad, bn_ref.weight.grad, rtol=1e-3, atol=1e-4)
-    _close(bn.bias.grad, bn_ref.bias.grad, rtol=1e-3, atol=1e-4)
+    # fp32 partial sums + atomics in arbitrary order: compare against the fp64 reference relative to each tensor's scale
+    def close_scaled(a, b, tol):
+        scale = b.abs().max().item() + 1e-12
+        assert (a.double() - b).abs().max().item() <= tol * scale, ((a.double() - b).abs().max().item(), scale)
+    close_scaled(x.grad, xr.grad, 2e-4)
+    close_scaled(bn.weight.grad, bn_ref.weight.grad, 2e-4)
+    close_scaled(bn.bias.grad, bn_ref.bias.grad, 2e-4)
     if res:
         _close(r.grad, rr.grad, rtol=1e-5, atol=1e-6)
 

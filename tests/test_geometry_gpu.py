@@ -121,6 +121,7 @@ def test_nms_selection_exact_vs_reference_goldens(cuda, golden_geometry, t):
     assert geometry.nms_3d_faster(boxes[:, :7], 0.10) == g["nms%d_pick" % t].tolist()
     assert geometry.nms_3d_faster(boxes[:, :7], 0.25, old_type=True) == g["nms%d_pick_old" % t].tolist()
     assert geometry.nms_3d_faster_samecls(boxes, 0.10) == g["nms%d_pick_cls" % t].tolist()
+    assert geometry.nms_2d_faster(boxes[:, [0, 1, 3, 4, 6]], 0.10) == g["nms%d_pick_2d" % t].tolist()
 
 
 def test_nms_random_vs_oracle_many(cuda):
@@ -172,3 +173,26 @@ def test_parse_predictions_and_map_vs_reference_goldens(cuda, golden_geometry):
             else:
                 assert abs(m[key] - want[c]) < 1e-6, (thr, c, m[key], want[c])
         assert abs(m["mAP"] - np.nanmean(want)) < 1e-6
+
+
+def test_graph_features_and_fp_module_vs_reference_goldens(cuda, golden_pointnet2):
+    """get_graph_feature / get_graph_feature_cross (VN-DGCNN edge features) and PointnetFPModule against outputs of the
+    reference's own code (dead in the live P2RNet path, named by north_star)."""
+    import torch.nn as nn
+    from pose2room_b200 import geometry
+    from pose2room_b200.pointnet2_modules import PointnetFPModule
+    g = golden_pointnet2
+    x = torch.from_numpy(g["gf_x"]).to(cuda)
+    idx = torch.from_numpy(g["gf_idx"]).to(cuda)
+    assert np.array_equal(geometry.get_graph_feature(x, k=8, idx=idx).cpu().numpy(), g["gf_feature"])
+    assert np.allclose(geometry.get_graph_feature_cross(x, k=8, idx=idx).cpu().numpy(), g["gf_cross"], atol=1e-6)
+    C = g["feats"].shape[1]
+    fp = PointnetFPModule(mlp=[C + C, 16, 8], bn=False).to(cuda)
+    with torch.no_grad():
+        fp.mlp[0].weight.copy_(torch.from_numpy(g["fp_w0"]))
+        fp.mlp[0].bias.copy_(torch.from_numpy(g["fp_b0"]))
+        fp.mlp[2].weight.copy_(torch.from_numpy(g["fp_w1"]))
+        fp.mlp[2].bias.copy_(torch.from_numpy(g["fp_b1"]))
+    out = fp(torch.from_numpy(g["xyz"]).to(cuda), torch.from_numpy(g["new_xyz"]).to(cuda),
+             torch.from_numpy(g["feats"]).to(cuda), torch.from_numpy(g["ti_kfeat"]).to(cuda))
+    assert np.allclose(out.detach().cpu().numpy(), g["fp_out"], rtol=1e-4, atol=1e-5)

@@ -66,6 +66,7 @@ def test_nms_selection_exact_vs_reference_goldens(golden_geometry, t):
     assert G.nms_3d_faster(boxes[:, :7], 0.10) == g["nms%d_pick" % t].tolist()
     assert G.nms_3d_faster(boxes[:, :7], 0.25, old_type=True) == g["nms%d_pick_old" % t].tolist()
     assert G.nms_3d_faster_samecls(boxes, 0.10) == g["nms%d_pick_cls" % t].tolist()
+    assert G.nms_2d_faster(boxes[:, [0, 1, 3, 4, 6]], 0.10) == g["nms%d_pick_2d" % t].tolist()
 
 
 def test_parse_predictions_vs_reference_goldens(golden_geometry):

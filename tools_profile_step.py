@@ -60,8 +60,12 @@ rows = [(k, t, c) for k, (t, c) in rows.items()]
 rows.sort(key=lambda r: -r[1])
 tot = sum(r[1] for r in rows)
 print("total device time %.2f ms over %d kernel names" % (tot / 1e3, len(rows)))
-for k, t, c in rows[:45]:
+for k, t, c in rows[:int(sys.argv[3]) if len(sys.argv) > 3 else 45]:
     print("%8.3f ms %5.1f%% x%-4d %s" % (t / 1e3, 100 * t / tot, c, k[:110]))
+mine = sum(t for k, t, c in rows if any(s in k for s in ["gemm_bf16", "colreduce", "bn_", "affine_act", "sgemm_kernel", "smallk",
+           "embed_sum", "fps_kernel", "ball_query", "group_", "maxpool", "nn_distance", "uniform_seed", "gather_points",
+           "relu_bwd", "colsum_wide", "temporal_unfold", "decode_boxes", "nms3d"]))
+print("hand-written kernels: %.2f ms (%.1f%%), torch/library glue: %.2f ms" % (mine / 1e3, 100 * mine / tot, (tot - mine) / 1e3))
 
 print("---- largest torch glue ops by device time (with shapes)")
 glue = [(e.key, str(e.input_shapes)[:90], e.device_time_total, e.count) for e in prof.key_averages(group_by_input_shape=True)
