@@ -191,13 +191,18 @@ def main():
     resident = {k: v.to(dev) for k, v in tensors.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in tensors.values())
 
+    overlap = os.environ.get("P2R_OVERLAP_DW", "1") != "0"
     dbg = (lambda *a: print("[bench rank %d]" % rank, *a, file=sys.stderr, flush=True)) if os.environ.get("P2R_BENCH_DEBUG") else (lambda *a: None)
 
     def fwd_bwd(data):
         opt.zero_grad(set_to_none=True)
         ep = net(data)
         loss = net.loss(ep, data)["total"]
-        loss.backward()
+        if overlap:
+            with ops.overlap_weight_grads():   # dW GEMMs on a side stream, joined before the optimiser
+                loss.backward()
+        else:
+            loss.backward()
         return loss
 
     def finish():
@@ -348,7 +353,7 @@ def main():
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "P2RNet train step fwd+loss+bwd+AdamW (+grad all-reduce), B=%d/GPU, T=1024, J=25, "
                                    "512 seeds, 128 proposals, 22 classes" % B,
-                       "parallelism": "dp%d" % world, "precision": precision, "cuda_graph": graph is not None,
+                       "parallelism": "dp%d" % world, "precision": precision, "cuda_graph": graph is not None, "overlap_dw": overlap,
                        "l2": "no flush needed: per-layer activations (105-420 MB) exceed the 126 MB L2"},
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

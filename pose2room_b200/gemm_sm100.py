@@ -55,6 +55,7 @@ class _TemporalConvTC(torch.autograd.Function):
                       bias_f.data_ptr() if bias_f is not None else None, 1, _stream())
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         return y
 
     @staticmethod
@@ -70,6 +71,22 @@ class _TemporalConvTC(torch.autograd.Function):
                 dx = torch.empty(b, t, v, ci, dtype=torch.bfloat16, device=x.device)
                 _lib.call("p2r_tconv_bf16", 1, dy.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), b, t * v, ci, co, kt, v,
                           None, 1, _stream())
+            if ops.DEFER["on"]:
+                need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+
+                def weight_grads():
+                    gw = gb = None
+                    if need_w:
+                        m = b * t * v
+                        dw2 = torch.zeros(co, kt * ci, dtype=torch.float32, device=x.device)
+                        _lib.call("p2r_tconv_bf16", 2, x.data_ptr(), None, dy.data_ptr(), dw2.data_ptr(), b, t * v, ci, co,
+                                  kt, v, None, max(1, min(128, m // 8192)), _stream())
+                        gw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
+                    if need_b:
+                        gb = ops._col_sum(dy)
+                    return [gw, gb]
+                ops._defer(weight_grads, [weight if need_w else None, ctx.bias_ref if need_b else None], (dy, x))
+                return dx, None, None
             if ctx.needs_input_grad[1]:
                 m = b * t * v
                 splits = max(1, min(128, m // 8192))

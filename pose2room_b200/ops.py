@@ -39,6 +39,47 @@ _TC_GEMM = {"fn": None}
 PROFILE = {"on": False, "log": []}
 
 
+# ---- optional overlap of weight-gradient work with the rest of the backward pass -------------------------------
+# The input-gradient chain (dX GEMM -> BatchNorm backward -> ...) is the critical path of the backward pass and is
+# mostly HBM-bound; the weight-gradient GEMMs (dW = dz^T.x) are tensor-bound and nobody needs their result before
+# the optimiser.  Inside `with overlap_weight_grads():` every dW / db is launched on a side stream and handed to
+# autograd only when the context exits (one join), so the two kinds of work share the GPU.  Off by default: a plain
+# `loss.backward()` (what the reference's trainer calls, models/training.py:34) behaves exactly as before.
+DEFER = {"on": False, "stream": None, "items": []}
+
+
+class overlap_weight_grads:
+    def __enter__(self):
+        if DEFER["stream"] is None:
+            DEFER["stream"] = torch.cuda.Stream()
+        DEFER["items"] = []
+        DEFER["on"] = True
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        DEFER["on"] = False
+        items, DEFER["items"] = DEFER["items"], []
+        torch.cuda.current_stream().wait_stream(DEFER["stream"])      # join: every deferred dW / db is complete
+        if exc_type is None and items:
+            tensors = [t for t, g, _ in items]
+            grads = [g for t, g, _ in items]
+            torch.autograd.backward(tensors, grads)                    # views / einsum backward -> leaf .grad
+        return False
+
+
+def _defer(fn, targets, keep):
+    """Run fn() -> list of gradients on the side stream; `targets` are the autograd-connected tensors they belong to;
+    `keep` are the operands the side-stream kernels read (kept alive until the join so the caching allocator cannot
+    hand their memory to main-stream tensors in the meantime)."""
+    side = DEFER["stream"]
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        grads = fn()
+    for t, g in zip(targets, grads):
+        if t is not None and g is not None:
+            DEFER["items"].append((t, g.to(t.dtype) if g.dtype != t.dtype else g, keep))
+
+
 class _Timed:
     def __init__(self, tag, m, n, k):
         self.rec = (tag, m, n, k)
@@ -124,6 +165,7 @@ class _Linear(Function):
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.relu = relu
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias     # autograd-connected handle for the deferred bias gradient (no data is read from it)
         return y
 
     @staticmethod
@@ -144,6 +186,26 @@ class _Linear(Function):
         if ctx.needs_input_grad[0]:
             with _Timed("dx", m, n, k):
                 dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
+        if DEFER["on"] and not PROFILE["on"] and m >= 4096:
+            need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+
+            def weight_grads():
+                gw = gb = None
+                if need_w:
+                    if _smallk_ok(x, n, k, ctx.relu):
+                        gw = torch.zeros(n, k, dtype=torch.float32, device=x.device)
+                        with torch.cuda.device(x.device):
+                            _lib.call("p2r_smallk_dw", dz.data_ptr(), x.data_ptr(), _DT[x.dtype], m, n, k,
+                                      gw.data_ptr(), _stream())
+                    elif use_tc:
+                        gw = tc.linear_dw(dz, x)
+                    else:
+                        gw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
+                if need_b:
+                    gb = _col_sum(dz)
+                return [gw, gb]
+            _defer(weight_grads, [weight if need_w else None, ctx.bias_ref if need_b else None], (dz, x))
+            return dx, None, None, None
         if ctx.needs_input_grad[1]:
             with _Timed("dw", m, n, k):
                 if _smallk_ok(x, n, k, ctx.relu):

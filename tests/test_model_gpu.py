@@ -163,3 +163,32 @@ def test_bf16_throughput_mode_tracks_fp32_reference(cuda, golden):
                     assert err < 5e-2, (name, k, err)
     finally:
         gemm_sm100.uninstall()
+
+
+def test_overlapped_weight_gradients_match_plain_backward(cuda, golden):
+    """ops.overlap_weight_grads() (dW / db on a side stream, handed to autograd at the join) must give the same
+    gradients as a plain loss.backward(): same kernels, different schedule."""
+    from pose2room_b200 import gemm_sm100, ops
+    gemm_sm100.install()
+    try:
+        grads = []
+        for use_overlap in [False, True]:
+            net = H.make_product("bl", "train", golden, precision="bf16").to(cuda)
+            net.train()
+            data = H.make_data("bl", cuda)
+            ep = net(data)
+            loss = net.loss(ep, data)["total"]
+            if use_overlap:
+                with ops.overlap_weight_grads():
+                    loss.backward()
+            else:
+                loss.backward()
+            torch.cuda.synchronize()
+            grads.append({k: p.grad.detach().double().clone() for k, p in net.named_parameters() if p.grad is not None})
+        assert set(grads[0]) == set(grads[1])
+        for k in grads[0]:
+            a, b = grads[0][k], grads[1][k]
+            scale = a.abs().max().item() + 1e-12
+            assert (a - b).abs().max().item() <= 2e-3 * scale, (k, (a - b).abs().max().item(), scale)
+    finally:
+        gemm_sm100.uninstall()
