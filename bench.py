@@ -196,12 +196,14 @@ def main():
 
     def fwd_bwd(data):
         opt.zero_grad(set_to_none=True)
-        ep = net(data)
-        loss = net.loss(ep, data)["total"]
         if overlap:
             with ops.overlap_weight_grads():   # dW GEMMs on a side stream, joined before the optimiser
+                ep = net(data)
+                loss = net.loss(ep, data)["total"]
                 loss.backward()
         else:
+            ep = net(data)
+            loss = net.loss(ep, data)["total"]
             loss.backward()
         return loss
 

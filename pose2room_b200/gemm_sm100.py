@@ -43,7 +43,8 @@ class _TemporalConvTC(torch.autograd.Function):
     three row-shifted TMA views of the SAME activation tensor instead of an unfold buffer."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, targets=None):
+        ctx.targets = targets
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
         x = x if x.is_contiguous() else x.contiguous()
@@ -55,7 +56,6 @@ class _TemporalConvTC(torch.autograd.Function):
                       bias_f.data_ptr() if bias_f is not None else None, 1, _stream())
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        ctx.bias_ref = bias
         return y
 
     @staticmethod
@@ -71,8 +71,10 @@ class _TemporalConvTC(torch.autograd.Function):
                 dx = torch.empty(b, t, v, ci, dtype=torch.bfloat16, device=x.device)
                 _lib.call("p2r_tconv_bf16", 1, dy.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), b, t * v, ci, co, kt, v,
                           None, 1, _stream())
-            if ops.DEFER["on"]:
-                need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+            if ctx.targets is not None:
+                tw, tb = ctx.targets
+                need_w = tw is not None and tw.requires_grad
+                need_b = tb is not None and tb.requires_grad
 
                 def weight_grads():
                     gw = gb = None
@@ -85,8 +87,8 @@ class _TemporalConvTC(torch.autograd.Function):
                     if need_b:
                         gb = ops._col_sum(dy)
                     return [gw, gb]
-                ops._defer(weight_grads, [weight if need_w else None, ctx.bias_ref if need_b else None], (dy, x))
-                return dx, None, None
+                ops._defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dy, x))
+                return dx, None, None, None
             if ctx.needs_input_grad[1]:
                 m = b * t * v
                 splits = max(1, min(128, m // 8192))
@@ -96,7 +98,7 @@ class _TemporalConvTC(torch.autograd.Function):
                 dw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = ops._col_sum(dy)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class _Backend:
@@ -139,6 +141,8 @@ class _Backend:
 
     @staticmethod
     def temporal_conv(x, weight, bias):
+        if ops.DEFER["on"] and torch.is_grad_enabled():
+            return _TemporalConvTC.apply(x, weight.detach(), bias.detach() if bias is not None else None, (weight, bias))
         return _TemporalConvTC.apply(x, weight, bias)
 
 

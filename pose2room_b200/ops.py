@@ -43,8 +43,11 @@ PROFILE = {"on": False, "log": []}
 # The input-gradient chain (dX GEMM -> BatchNorm backward -> ...) is the critical path of the backward pass and is
 # mostly HBM-bound; the weight-gradient GEMMs (dW = dz^T.x) are tensor-bound and nobody needs their result before
 # the optimiser.  Inside `with overlap_weight_grads():` every dW / db is launched on a side stream and handed to
-# autograd only when the context exits (one join), so the two kinds of work share the GPU.  Off by default: a plain
-# `loss.backward()` (what the reference's trainer calls, models/training.py:34) behaves exactly as before.
+# autograd only when the context exits (one join), so the two kinds of work share the GPU.  The context must span
+# forward AND backward: inside it the layers hand autograd a DETACHED weight (so the main backward never walks -- and
+# frees -- the graph behind the weight, e.g. the einsum that builds W_eff) and remember the real one as the target of
+# the deferred gradient.  Off by default: a plain forward + `loss.backward()` (what the reference's trainer does,
+# models/training.py:25-43) behaves exactly as before.
 DEFER = {"on": False, "stream": None, "items": []}
 
 
@@ -147,7 +150,8 @@ def _smallk_ok(x, n, k, relu):
 
 class _Linear(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):
+    def forward(ctx, x, weight, bias, relu, targets=None):
+        ctx.targets = targets      # (weight, bias) with their autograd history when the gradient is deferred
         x = x if x.is_contiguous() else x.contiguous()
         tc = _TC_GEMM["fn"]
         with _Timed("fwd", x.shape[0], weight.shape[0], x.shape[1]):
@@ -165,7 +169,6 @@ class _Linear(Function):
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.relu = relu
         ctx.has_bias = bias is not None
-        ctx.bias_ref = bias     # autograd-connected handle for the deferred bias gradient (no data is read from it)
         return y
 
     @staticmethod
@@ -186,8 +189,10 @@ class _Linear(Function):
         if ctx.needs_input_grad[0]:
             with _Timed("dx", m, n, k):
                 dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
-        if DEFER["on"] and not PROFILE["on"] and m >= 4096:
-            need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.targets is not None:
+            tw, tb = ctx.targets
+            need_w = tw is not None and tw.requires_grad
+            need_b = tb is not None and tb.requires_grad
 
             def weight_grads():
                 gw = gb = None
@@ -204,8 +209,8 @@ class _Linear(Function):
                 if need_b:
                     gb = _col_sum(dz)
                 return [gw, gb]
-            _defer(weight_grads, [weight if need_w else None, ctx.bias_ref if need_b else None], (dz, x))
-            return dx, None, None, None
+            _defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dz, x))
+            return dx, None, None, None, None
         if ctx.needs_input_grad[1]:
             with _Timed("dw", m, n, k):
                 if _smallk_ok(x, n, k, ctx.relu):
@@ -219,11 +224,13 @@ class _Linear(Function):
                     dw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _col_sum(dz)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 def linear(x, weight, bias=None, relu=False):
     """y[M,N] = x[M,K] @ weight[N,K]^T (+bias)(ReLU): a 1x1 Conv1d/Conv2d in channel-last form."""
+    if DEFER["on"] and not PROFILE["on"] and x.shape[0] >= 4096 and torch.is_grad_enabled():
+        return _Linear.apply(x, weight.detach(), bias.detach() if bias is not None else None, relu, (weight, bias))
     return _Linear.apply(x, weight, bias, relu)
 
 

@@ -173,15 +173,19 @@ def test_overlapped_weight_gradients_match_plain_backward(cuda, golden):
     try:
         grads = []
         for use_overlap in [False, True]:
+            from pose2room_b200 import synthetic
             net = H.make_product("bl", "train", golden, precision="bf16").to(cuda)
             net.train()
-            data = H.make_data("bl", cuda)
-            ep = net(data)
-            loss = net.loss(ep, data)["total"]
+            data = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v)
+                    for k, v in synthetic.make_batch(4, 1024, 25, seed=3).items()}   # B=4: every layer is large enough to defer
             if use_overlap:
                 with ops.overlap_weight_grads():
+                    ep = net(data)
+                    loss = net.loss(ep, data)["total"]
                     loss.backward()
             else:
+                ep = net(data)
+                loss = net.loss(ep, data)["total"]
                 loss.backward()
             torch.cuda.synchronize()
             grads.append({k: p.grad.detach().double().clone() for k, p in net.named_parameters() if p.grad is not None})
