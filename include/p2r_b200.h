@@ -125,10 +125,11 @@ int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, l
 /* column sums of a wide [M,C] matrix (any C % VEC == 0), e.g. the 1600-wide graph-conv bias gradient; s1 zeroed by caller */
 int p2r_col_sum_wide(const void* dy, int dtype, long long M, int C, double* s1, void* stream);
 
-/* training-mode BatchNorm statistics -> mean, rstd, fused scale/shift; updates running stats like torch */
-int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, const float* gamma, const float* beta,
-                    float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
-                    float* scale, float* shift, void* stream);
+/* training-mode BatchNorm statistics -> mean, rstd, fused scale/shift; updates running stats like torch.
+ * s1 / s2 may be `copies` partial sums, `copy_stride` doubles apart (the GEMM-epilogue statistics of p2r_gemm_bf16_ex) */
+int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, int copies, long long copy_stride,
+                    const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                    float* running_var, float* mean, float* rstd, float* scale, float* shift, void* stream);
 /* y = x*scale[c] + shift[c] (+residual) (ReLU)                                                     */
 int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift,
                    const void* residual, int relu, void* y, void* stream);
@@ -169,13 +170,26 @@ int p2r_smallk_dw(const void* dz, const void* x, int dtype, long long M, int N, 
  * atomics into zeroed C.  block_n in {0 = auto, 64, 128, 160, 256}.  Pointers 16-byte aligned, pitches % 8 == 0. */
 int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                   int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n, void* stream);
+/* The same GEMM with the three extras the graph convolution of st_gcn_block uses (stgcn_layers.py:58-67 computes
+ * conv 64 -> 11*64 then einsum 'nkctv,kvw->nctw'; here it is ONE GEMM against W_eff = sum_k W_k (x) A_k):
+ *   kb_list [tiles_n][kb_stride] int: entry 0 = how many 64-wide k-blocks n-tile i visits, entries 1.. their indices --
+ *     W_eff is zero in every 64x64 block whose joints are further apart than the adjacency's max hop;
+ *   tile_mask [tiles_m][tiles_n] bytes: 0 = structurally-zero output tile, skipped (C left untouched; weight gradient);
+ *   stats [stat_copies][2][64] double, zeroed by the caller: per channel (column % 64) sum and sum of squares of the
+ *     stored output = the statistics of the BatchNorm that follows (stgcn_layers.py:403), so it needs no extra pass.
+ * Extras need splits <= 1 and an explicit block_n (the tables are indexed by this launch's tiling); NULL = off.     */
+int p2r_gemm_bf16_ex(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                     int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n, const int* kb_list,
+                     int kb_stride, const unsigned char* tile_mask, double* stats, int stat_copies, void* stream);
 
 /* (KT x 1) temporal convolution (zero padding (KT-1)/2) as an implicit tensor-core GEMM over the 3-D activation tensor
  * [B, rows = T*V, C], a tap shifting by V rows; no unfold buffer (ref: st_gcn_block.tcn conv, stgcn_layers.py:405-411).
  * mode 0: y = conv(x, W2[Co, KT*Ci]) (+bias); mode 1: dx from dy and Wt[KT*Co, Ci]; mode 2: dW2[Co, KT*Ci] (fp32,
- * zeroed by the caller when splits > 1) from x (act) and dy (other).  rows % 128 == 0, Ci = Co = 64.               */
+ * zeroed by the caller when splits > 1) from x (act) and dy (other).  rows % 128 == 0, Ci = Co = 64.
+ * stats (mode 0 only, optional): [stat_copies][2][64] double, zeroed by the caller -- per-channel sum / sum of squares
+ * of y, i.e. the statistics of the BatchNorm2d that follows the conv (stgcn_layers.py:412).                        */
 int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows, int Ci,
-                   int Co, int KT, int V, const float* bias, int splits, void* stream);
+                   int Co, int KT, int V, const float* bias, int splits, double* stats, int stat_copies, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,10 @@ SIGNATURES = {
                   _c_int, _vp, _c_int, _c_int, _c_int, _vp],
     "p2r_gemm_bf16": [_c_int, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int,
                       _c_int, _c_int, _vp],
-    "p2r_tconv_bf16": [_c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
+    "p2r_gemm_bf16_ex": [_c_int, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int,
+                         _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp],
+    "p2r_tconv_bf16": [_c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp,
+                       _c_int, _vp],
     "p2r_embed_sum": [_vp, _vp, _c_int, _c_ll, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_embed_sum_grad": [_vp, _c_int, _c_ll, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_linear": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],
@@ -48,7 +51,7 @@ SIGNATURES = {
     "p2r_col_sum_wide": [_vp, _c_int, _c_ll, _c_int, _vp, _vp],
     "p2r_col_stats": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp],
     "p2r_col_bwd_stats": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
-    "p2r_bn_finalize": [_c_int, _c_ll, _vp, _vp, _vp, _vp, _c_float, _c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "p2r_bn_finalize": [_c_int, _c_ll, _vp, _vp, _c_int, _c_ll, _vp, _vp, _c_float, _c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "p2r_affine_act": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp],
     "p2r_bn_bwd_apply": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp],
     "p2r_relu_bwd": [_vp, _vp, _c_int, _c_ll, _vp, _vp],

@@ -9,6 +9,7 @@
 //
 // Storage type T is float or __nv_bfloat16; arithmetic is always fp32 (double for BN column sums).
 #include "p2r_common.cuh"
+#include "stream_bn.cuh"
 #include <stdlib.h>
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
@@ -346,6 +347,7 @@ static int colreduce_grid(long long M, int* rows_per_cta) {
 extern "C" int p2r_col_stats(const void* x, int dtype, long long M, int C, double* s1, double* s2, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "p2r_col_stats");
   if (M == 0) return 0;
+  if (p2r_stream_bn_ok(dtype, M, C, x)) return p2r_stream_col_stats(x, M, s1, s2, (cudaStream_t)stream);
   int rpc;
   const int grid = colreduce_grid(M, &rpc);
   if (dtype == 0) {
@@ -370,6 +372,8 @@ extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, i
   P2R_CHECK_ARG(!(relu == 1 && y == nullptr), "p2r_col_bwd_stats (relu = 1 needs y)");
   P2R_CHECK_ARG(!(relu == 2 && (x == nullptr || scale == nullptr || shift == nullptr)), "p2r_col_bwd_stats (relu = 2 needs x, scale, shift)");
   if (M == 0) return 0;
+  if ((x != nullptr || relu == 0) && (s2 == nullptr || x != nullptr) && p2r_stream_bn_ok(dtype, M, C, dy, x, y))
+    return p2r_stream_col_bwd_stats(dy, x, relu == 1 ? y : nullptr, M, mean, rstd, relu, s1, s2, scale, shift, (cudaStream_t)stream);
   int rpc;
   const int grid = colreduce_grid(M, &rpc);
   if (dtype == 0) {
@@ -388,7 +392,8 @@ extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, i
 
 // BatchNorm finalize (training): mean/var from the column sums, running-stat update exactly like
 // torch.nn.BatchNorm (momentum, unbiased variance for the running estimate), fused affine scale/shift.
-__global__ void bn_finalize_kernel(int C, double inv_m, double unbias, const double* __restrict__ s1,
+__global__ void bn_finalize_kernel(int C, double inv_m, double unbias, int copies, long long copy_stride,
+                                   const double* __restrict__ s1,
                                    const double* __restrict__ s2, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -396,8 +401,10 @@ __global__ void bn_finalize_kernel(int C, double inv_m, double unbias, const dou
                                    float* __restrict__ shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mu = s1[c] * inv_m;
-  double var = s2[c] * inv_m - mu * mu;
+  double t1 = 0.0, t2 = 0.0;
+  for (int k = 0; k < copies; ++k) { t1 += s1[k * copy_stride + c]; t2 += s2[k * copy_stride + c]; }
+  const double mu = t1 * inv_m;
+  double var = t2 * inv_m - mu * mu;
   if (var < 0.0) var = 0.0;
   const float rs = (float)(1.0 / sqrt(var + (double)eps));
   mean[c] = (float)mu;
@@ -411,12 +418,14 @@ __global__ void bn_finalize_kernel(int C, double inv_m, double unbias, const dou
   }
 }
 
-extern "C" int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, const float* gamma,
+// s1 / s2 may be given as `copies` partial sums `copy_stride` doubles apart (the fused GEMM-epilogue statistics).
+extern "C" int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, int copies,
+                               long long copy_stride, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                float* mean, float* rstd, float* scale, float* shift, void* stream) {
-  P2R_CHECK_ARG(C > 0 && M > 0, "p2r_bn_finalize");
+  P2R_CHECK_ARG(C > 0 && M > 0 && copies >= 1, "p2r_bn_finalize");
   const double unbias = M > 1 ? (double)M / (double)(M - 1) : 1.0;
-  bn_finalize_kernel<<<p2r_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, 1.0 / (double)M, unbias, s1, s2, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
+  bn_finalize_kernel<<<p2r_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, 1.0 / (double)M, unbias, copies, copy_stride, s1, s2, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
   P2R_RETURN_LAUNCH("p2r_bn_finalize");
 }
 
@@ -467,6 +476,8 @@ extern "C" int p2r_affine_act(const void* x, int dtype, long long M, int C, cons
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_affine_act");
   const long long total = M * C;
   if (total == 0) return 0;
+  if (p2r_stream_bn_ok(dtype, M, C, x, residual, y))
+    return p2r_stream_affine_act(x, M, scale, shift, residual, relu, y, (cudaStream_t)stream);
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, x, residual, y))
     affine_act_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
@@ -564,6 +575,10 @@ extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, in
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_bn_bwd_apply");
   const long long total = M * C;
   if (total == 0) return 0;
+  if (x != nullptr && (relu != 1 || y != nullptr) && (relu != 2 || shift != nullptr) &&
+      p2r_stream_bn_ok(dtype, M, C, dy, x, y, dx, dres))
+    return p2r_stream_bn_bwd_apply(dy, x, relu == 1 ? y : nullptr, M, mean, rstd, scale, s1, s2, relu, dx, dres, shift,
+                                   (cudaStream_t)stream);
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, dy, x, y, dx, dres))
     bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);

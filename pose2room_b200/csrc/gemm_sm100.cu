@@ -116,6 +116,39 @@ struct TapArgs {
   int kb_per_tap, rows_per_sample, channels, shift0, shift_step;
 };
 
+// Optional extras of one launch (all NULL / 0 = plain dense GEMM):
+//   kb_list   : block-sparse reduction.  Row n_tile of an int table [tiles_n][kb_stride]: entry 0 = number of 64-wide
+//               k-blocks this n-tile visits, entries 1.. = their indices (ascending).  The graph-convolution weight
+//               W_eff = sum_k W_k (x) A_k is zero in every 64x64 block (w,v) whose joints are further apart than the
+//               adjacency's max hop, so only the listed k-blocks are loaded and multiplied.
+//   tile_mask : [tiles_m][tiles_n] bytes, 0 = this output tile is structurally zero: the CTA exits (C untouched).
+//   stats     : fused BatchNorm statistics of the OUTPUT: per channel c = column % 64, sum and sum of squares of the
+//               values as stored (after bias / rounding to the output type), accumulated with double atomics into
+//               stats[copy][0][c] / stats[copy][1][c], copy = CTA index % stat_copies (spreads the atomic traffic).
+struct GemmExtra {
+  const int* kb_list;
+  int kb_stride;
+  const unsigned char* tile_mask;
+  double* stats;
+  int stat_copies;
+};
+
+// Sum over the 32 lanes of a warp of 32 per-lane values, transposed: on return lane l holds sum_lanes v[l].
+// 31 shuffles (16 + 8 + 4 + 2 + 1) instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 template <int BLOCK_N, int STAGES_OVERRIDE = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
@@ -128,12 +161,13 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP = 0, int NSTAGE = 0>
+template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP = 0, int NSTAGE = 0, bool STATS = false>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  OutT* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ bias, int relu,
-                 int kblocks_per_split, const TapArgs tap, int tiles_per_cta) {
+                 int kblocks_per_split, const TapArgs tap, int tiles_per_cta, const GemmExtra ex) {
   using S = GemmSmem<BLOCK_N, NSTAGE>;
+  if (ex.tile_mask != nullptr && ex.tile_mask[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // whole CTA, uniform
   constexpr int ACC = S::ACC_STAGES;   // accumulator buffers in TMEM (2: the epilogue of tile t overlaps the MMAs of t+1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -148,7 +182,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int kb0 = blockIdx.z * kblocks_per_split;
   const int kb1 = min(total_kb, kb0 + kblocks_per_split);
-  const int nkb = kb1 - kb0;
+  const int* kbl = ex.kb_list != nullptr ? ex.kb_list + (size_t)blockIdx.x * ex.kb_stride + 1 : nullptr;
+  const int nkb = kbl != nullptr ? __ldg(kbl - 1) : kb1 - kb0;
   const int tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int tile0 = blockIdx.y * tiles_per_cta;
   const int ntiles = min(tiles_per_cta, tiles_m - tile0);   // m-tiles this CTA walks through
@@ -187,10 +222,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
           p2r_mbar_expect_tx(full + s, S::STAGE_BYTES);
-          const int k0 = (kb0 + i) * GEMM_BLOCK_K;
+          const int kbi = kbl != nullptr ? __ldg(kbl + i) : kb0 + i;
+          const int k0 = kbi * GEMM_BLOCK_K;
           if (TAP == 1) {
-            const int tp = (kb0 + i) / tap.kb_per_tap;
-            const int kc = ((kb0 + i) % tap.kb_per_tap) * GEMM_BLOCK_K;
+            const int tp = kbi / tap.kb_per_tap;
+            const int kc = (kbi % tap.kb_per_tap) * GEMM_BLOCK_K;
             tma_load_3d(a_dst, &tma_a, full + s, kc, (m0 % tap.rows_per_sample) + tap.shift0 + tp * tap.shift_step,
                         m0 / tap.rows_per_sample);                        // box {64 c, 128 rows, 1 sample}
           } else if (!A_MN) {
@@ -254,6 +290,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const bool vec_ok = ((size_t)ldc * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
+    constexpr bool do_stats = STATS && !ATOMIC;   // (a template flag: the extra registers stay out of the plain kernels)
+    // statistics accumulators: st[h][r] belongs to channel 32 h + 16 r + (lane & 15); lanes < 16 hold the sum, lanes
+    // >= 16 the sum of squares
+    float st00 = 0.f, st01 = 0.f, st10 = 0.f, st11 = 0.f;
     for (int t = 0; t < ntiles; ++t) {
       const int as = t % ACC;
       const int row = (tile0 + t) * GEMM_BLOCK_M + q * 32 + lane;
@@ -271,17 +311,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (lane == 0) p2r_mbar_arrive(tmem_empty + as);
         }
         const int col0 = n0 + c0;
-        if (row_ok && col0 < N) {  // (no `continue`: the next tcgen05.ld is warp-aligned)
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (!ATOMIC) {
-              if (bias != nullptr && col0 + j < N) x += __ldg(bias + col0 + j);
-              if (relu) x = fmaxf(x, 0.f);
-            }
-            f[j] = x;
+        for (int j = 0; j < 32; ++j) {
+          float x = nkb > 0 ? __uint_as_float(v[j]) : 0.f;   // an n-tile without k-blocks is all zero
+          if (!ATOMIC) {
+            if (bias != nullptr && col0 + j < N) x += __ldg(bias + col0 + j);
+            if (relu) x = fmaxf(x, 0.f);
+            if (sizeof(OutT) == 2) x = __bfloat162float(__float2bfloat16_rn(x));   // the value as stored
           }
+          f[j] = x;
+        }
+        if (row_ok && col0 < N) {  // (no `continue`: the next tcgen05.ld is warp-aligned)
           if (ATOMIC) {
             for (int j = 0; j < 32; ++j)
               if (col0 + j < N) atomicAdd(reinterpret_cast<float*>(crow) + col0 + j, f[j]);
@@ -314,8 +355,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               }
           }
         }
+        if (do_stats) {   // warp-uniform: column sums of this 32 x 32 block (rows / columns outside the matrix count 0)
+          // two rounds of 16 columns: c = {16 values, their 16 squares} -> one transposed 32-lane reduction leaves the
+          // column sum on lane l < 16 and the sum of squares of the same column on lane l + 16
+          const bool hi = (col0 >> 5) & 1;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float c[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = (row_ok && col0 + 16 * r + j < N) ? f[16 * r + j] : 0.f;
+              c[j] = x;
+              c[16 + j] = x * x;
+            }
+            const float tot = warp_transpose_sum32(c, lane);
+            if (hi) { if (r) st11 += tot; else st10 += tot; }
+            else { if (r) st01 += tot; else st00 += tot; }
+          }
+        }
         __syncwarp();
       }
+    }
+    tc_fence_before();
+    if (do_stats) {
+      // every MMA of this CTA has completed (tmem_full of the last tile), so the pipeline stages are free: combine
+      // the four epilogue warps there, then 128 double atomics per CTA into this CTA's copy of the statistics
+      float* red = reinterpret_cast<float*>(smem);   // [4 warps][4 values][32 lanes]
+      red[(q * 4 + 0) * 32 + lane] = st00;
+      red[(q * 4 + 1) * 32 + lane] = st01;
+      red[(q * 4 + 2) * 32 + lane] = st10;
+      red[(q * 4 + 3) * 32 + lane] = st11;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      const int k = q;   // warp q finishes accumulator k = 2 h + r
+      const float tot = red[(0 * 4 + k) * 32 + lane] + red[(1 * 4 + k) * 32 + lane] + red[(2 * 4 + k) * 32 + lane] +
+                        red[(3 * 4 + k) * 32 + lane];
+      const int copy = (int)((blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)ex.stat_copies);
+      atomicAdd(ex.stats + ((size_t)copy * 2 + (lane >> 4)) * 64 + k * 16 + (lane & 15), (double)tot);
     }
     tc_fence_before();
   }
@@ -380,7 +455,8 @@ static int make_map3(CUtensorMap* map, const void* ptr, long long C, long long r
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int TAP, int NSTAGE>
 static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* C, int ldc, int c_dtype, int M, int N,
-                            int K, const float* bias, int relu, int splits, const TapArgs& tap, cudaStream_t st) {
+                            int K, const float* bias, int relu, int splits, const TapArgs& tap, cudaStream_t st,
+                            const GemmExtra& ex = GemmExtra{nullptr, 0, nullptr, nullptr, 1}) {
   using S = GemmSmem<BLOCK_N, NSTAGE>;
   const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   int kps = total_kb;
@@ -392,29 +468,35 @@ static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* 
   // next tile's TMA loads and MMAs run under the current tile's epilogue (double-buffered accumulator)
   const long long tiles_m = p2r_ceil_div(M, GEMM_BLOCK_M), tiles_n = p2r_ceil_div(N, BLOCK_N);
   int tpc = 1;
-  if (splits == 1 && S::ACC_STAGES == 2) {
+  if (splits == 1 && S::ACC_STAGES == 2 && ex.tile_mask == nullptr) {
     const long long slots = (long long)P2R_SM_COUNT * 8;
     tpc = (int)((tiles_m * tiles_n) / slots);
     if (tpc < 1) tpc = 1;
     if (tpc > 8) tpc = 8;
   }
   dim3 grid((unsigned)tiles_n, (unsigned)p2r_ceil_div(tiles_m, tpc), splits);
-#define GEMM_GO(OutT, ATOMIC)                                                                                   \
+#define GEMM_GO(OutT, ATOMIC, STATS)                                                                            \
   do {                                                                                                          \
-    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE>;                               \
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE, STATS>;                        \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);                          \
-    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc);      \
+    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc, ex);  \
   } while (0)
-  if (splits > 1) GEMM_GO(float, true);
-  else if (c_dtype == 1) GEMM_GO(__nv_bfloat16, false);
-  else GEMM_GO(float, false);
+  if (ex.stats != nullptr) {
+    if (A_MN || B_MN || TAP == 2 || splits > 1 || c_dtype != 1) {
+      p2r_set_last_error("p2r_gemm_bf16_ex: fused statistics need K-major operands, bf16 output, no split-K", -1);
+      return -1;
+    }
+    if (!A_MN && !B_MN && TAP != 2) GEMM_GO(__nv_bfloat16, false, true);
+  } else if (splits > 1) GEMM_GO(float, true, false);
+  else if (c_dtype == 1) GEMM_GO(__nv_bfloat16, false, false);
+  else GEMM_GO(float, false, false);
 #undef GEMM_GO
   P2R_RETURN_LAUNCH("p2r_gemm_bf16");
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, int M, int N,
-                       int K, const float* bias, int relu, int splits, cudaStream_t st) {
+                       int K, const float* bias, int relu, int splits, cudaStream_t st, const GemmExtra& ex) {
   CUtensorMap ma, mb;
   // K-major: rows = M (or N), inner = K.   MN-major: rows = K, inner = M (or N).
   if (make_map(&ma, A, A_MN ? M : K, A_MN ? K : M, lda, A_MN ? GEMM_BLOCK_K : GEMM_BLOCK_M)) return -1;
@@ -424,10 +506,10 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, 
   // short reductions (the 64-channel point MLPs): fewer stages -> less smem -> more co-resident CTAs per SM to hide
   // the per-tile latency chain (TMEM alloc, TMA, MMA, epilogue)
   if (BLOCK_N == 64 && splits <= 1 && total_kb <= 1)
-    return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 1 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st);
+    return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 1 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
   if (BLOCK_N == 64 && splits <= 1 && total_kb <= 3)
-    return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 2 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st);
-  return launch_with_maps<BLOCK_N, A_MN, B_MN, 0, 0>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st);
+    return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 2 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
+  return launch_with_maps<BLOCK_N, A_MN, B_MN, 0, 0>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
 }
 
 // (KT x 1) temporal convolution, zero padding (KT-1)/2, as an IMPLICIT GEMM on the 3-D activation tensor
@@ -438,7 +520,9 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, 
 //                      (zero-filled by the caller when splits > 1)
 // rows = T*V rows per sample, a tap shifts by V rows; requires rows % 128 == 0, Ci % 64 == 0, Co % 64 == 0, Co,Ci <= 64*...
 extern "C" int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows,
-                              int Ci, int Co, int KT, int V, const float* bias, int splits, void* stream) {
+                              int Ci, int Co, int KT, int V, const float* bias, int splits, double* stats,
+                              int stat_copies, void* stream) {
+  P2R_CHECK_ARG(stats == nullptr || (mode == 0 && stat_copies >= 1), "p2r_tconv_bf16 (fused output statistics: forward only)");
   P2R_CHECK_ARG(mode >= 0 && mode <= 2 && B > 0 && rows > 0 && (rows % 128) == 0 && (KT & 1) && KT >= 1,
                 "p2r_tconv_bf16");
   P2R_CHECK_ARG(Ci == 64 && Co == 64, "p2r_tconv_bf16 (built for the 64 -> 64 channel temporal conv of the hot path)");
@@ -450,7 +534,8 @@ extern "C" int p2r_tconv_bf16(int mode, const void* act, const void* w, const vo
     if (make_map3(&ma, act, Ci, rows, B, GEMM_BLOCK_M)) return -1;
     if (make_map(&mb, w, (long long)KT * Ci, Co, (long long)KT * Ci, 64)) return -1;
     const TapArgs tap = {Ci / 64, rows, Ci, -pad * V, V};
-    return launch_with_maps<64, false, false, 1, 2>(ma, mb, out, Co, 1, M, Co, KT * Ci, bias, 0, 1, tap, st);
+    const GemmExtra ex = {nullptr, 0, nullptr, stats, stat_copies};
+    return launch_with_maps<64, false, false, 1, 2>(ma, mb, out, Co, 1, M, Co, KT * Ci, bias, 0, 1, tap, st, ex);
   }
   if (mode == 1) {
     if (make_map3(&ma, act, Co, rows, B, GEMM_BLOCK_M)) return -1;
@@ -470,10 +555,18 @@ extern "C" int p2r_tconv_bf16(int mode, const void* act, const void* w, const vo
 //   b_mn = 0: B is [N,K] row-major (ldb);  b_mn = 1: B is [K,N] row-major (ldb)
 //   c_dtype 0 = fp32, 1 = bf16;  splits > 1: split-K, fp32 atomics into a zero-filled C (no bias / ReLU)
 //   block_n in {64, 128, 160, 256} (160 only with b_mn = 0); 0 = choose.
-extern "C" int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
-                             void* C, int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n,
-                             void* stream) {
+//   kb_list / kb_stride, tile_mask, stats / stat_copies: see GemmExtra (all optional; need splits <= 1 and an explicit
+//   block_n, because the tables are indexed by this launch's tiling; stats need N % 64 == 0 channels-last columns).
+extern "C" int p2r_gemm_bf16_ex(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
+                                void* C, int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n,
+                                const int* kb_list, int kb_stride, const unsigned char* tile_mask, double* stats,
+                                int stat_copies, void* stream) {
   P2R_CHECK_ARG(M > 0 && N > 0 && K > 0, "p2r_gemm_bf16");
+  const bool extras = kb_list != nullptr || tile_mask != nullptr || stats != nullptr;
+  P2R_CHECK_ARG(!extras || (splits <= 1 && block_n != 0), "p2r_gemm_bf16_ex (extras need splits <= 1 and an explicit block_n)");
+  P2R_CHECK_ARG(kb_list == nullptr || kb_stride >= 1, "p2r_gemm_bf16_ex kb_stride");
+  P2R_CHECK_ARG(stats == nullptr || (stat_copies >= 1 && N % 64 == 0), "p2r_gemm_bf16_ex stats");
+  const GemmExtra ex = {kb_list, kb_stride, tile_mask, stats, stat_copies < 1 ? 1 : stat_copies};
   P2R_CHECK_ARG(!(splits > 1 && (c_dtype != 0 || bias || relu)), "p2r_gemm_bf16 (split-K needs fp32 C, no epilogue)");
   P2R_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "p2r_gemm_bf16 (row pitches must be multiples of 8 bf16 = 16 bytes)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -486,16 +579,23 @@ extern "C" int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_
   P2R_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256 || (block_n == 160 && !b_mn), "p2r_gemm_bf16 block_n");
 #define GEMM_DISPATCH(BN)                                                                                          \
   do {                                                                                                             \
-    if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st); \
-    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);  \
-    if (a_mn && !b_mn) return launch_gemm<BN, true, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);  \
-    return launch_gemm<BN, true, true>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);          \
+    if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st, ex); \
+    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st, ex);  \
+    if (a_mn && !b_mn) return launch_gemm<BN, true, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st, ex);  \
+    return launch_gemm<BN, true, true>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st, ex);      \
   } while (0)
   if (block_n == 64) GEMM_DISPATCH(64);
   if (block_n == 128) GEMM_DISPATCH(128);
   if (block_n == 256) GEMM_DISPATCH(256);
   // 160: K-major B only
-  if (!a_mn) return launch_gemm<160, false, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);
-  return launch_gemm<160, true, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st);
+  if (!a_mn) return launch_gemm<160, false, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st, ex);
+  return launch_gemm<160, true, false>(A, lda, B, ldb, C, ldc, c_dtype, M, N, K, bias, relu, splits, st, ex);
 #undef GEMM_DISPATCH
+}
+
+extern "C" int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
+                             void* C, int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n,
+                             void* stream) {
+  return p2r_gemm_bf16_ex(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, c_dtype, bias, relu, splits, block_n, nullptr, 0,
+                          nullptr, nullptr, 1, stream);
 }

@@ -2,9 +2,66 @@
 csrc/gemm_sm100.cu (C ABI `p2r_gemm_bf16`).  `install()` hooks it into pose2room_b200.ops.linear so that
 forward (x.W^T), input gradient (dy.W) and weight gradient (dy^T.x) of every layer with bf16 activations run on
 the tensor cores; layers the kernel cannot take (K or N not a multiple of 8, tiny K) stay on the SIMT kernel."""
+import os
+
+import numpy as np
 import torch
 
 from . import _lib, ops
+
+# tiling of the block-sparse graph-convolution GEMMs (forward / input gradient) and number of partial-statistics copies
+GCN_BLOCK_N = int(os.environ.get("P2R_GCN_BLOCK_N", "160"))
+STAT_COPIES = int(os.environ.get("P2R_STAT_COPIES", "16"))
+USE_SPARSITY = os.environ.get("P2R_GCN_SPARSE", "1") != "0"
+USE_FUSED_STATS = os.environ.get("P2R_FUSED_STATS", "1") != "0"
+
+
+class BlockSparsity:
+    """64x64 block pattern of a weight W[N,K] (nn.Linear layout): nz[nb, kb] is False where the block is structurally
+    zero.  For the graph convolution W_eff[(w,co),(v,ci)] = sum_k W_k[co,ci] A_k[v,w] (ref: stgcn_layers.py:58-67 with
+    A from Graph.get_adjacency, :163-208) block (w,v) is zero whenever joints v and w are more than max_hop apart in
+    the skeleton -- 48 % of the blocks of the 25-joint layout.  Produces the k-block lists / tile masks that
+    p2r_gemm_bf16_ex consumes, cached per device."""
+
+    def __init__(self, nz):
+        self.nz = np.asarray(nz, dtype=bool)
+        self._cache = {}
+
+    @property
+    def density(self):
+        return float(self.nz.mean())
+
+    def kb_list(self, block_n, transposed, device):
+        """int32 [tiles_n, 1 + kblocks]: row i = (count, k-block indices...) of n-tile i.  transposed=False: forward,
+        n runs over W's rows; True: input gradient dx = dz.W, n runs over W's columns and k over its rows."""
+        key = ("kb", block_n, transposed, str(device))
+        if key not in self._cache:
+            nz = self.nz.T if transposed else self.nz          # [n blocks, k blocks]
+            n_cols = nz.shape[0] * 64
+            tiles_n = -(-n_cols // block_n)
+            tab = np.zeros((tiles_n, 1 + nz.shape[1]), dtype=np.int32)
+            for i in range(tiles_n):
+                b0, b1 = (i * block_n) // 64, (min(n_cols, (i + 1) * block_n) - 1) // 64
+                ks = np.nonzero(nz[b0:b1 + 1].any(0))[0]
+                tab[i, 0] = len(ks)
+                tab[i, 1:1 + len(ks)] = ks
+            self._cache[key] = torch.from_numpy(tab).to(device)
+        return self._cache[key]
+
+    def tile_mask(self, block_m, block_n, device):
+        """uint8 [tiles_m, tiles_n] for the weight gradient dW[N,K] tiled block_m x block_n."""
+        key = ("mask", block_m, block_n, str(device))
+        if key not in self._cache:
+            n, k = self.nz.shape[0] * 64, self.nz.shape[1] * 64
+            tm, tn = -(-n // block_m), -(-k // block_n)
+            mask = np.zeros((tm, tn), dtype=np.uint8)
+            for i in range(tm):
+                for j in range(tn):
+                    r0, r1 = (i * block_m) // 64, (min(n, (i + 1) * block_m) - 1) // 64
+                    c0, c1 = (j * block_n) // 64, (min(k, (j + 1) * block_n) - 1) // 64
+                    mask[i, j] = self.nz[r0:r1 + 1, c0:c1 + 1].any()
+            self._cache[key] = torch.from_numpy(mask).to(device)
+        return self._cache[key]
 
 
 def _stream():
@@ -18,8 +75,11 @@ def available():
     return major == 10 and hasattr(_lib.load(), "p2r_gemm_bf16")
 
 
-def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bfloat16, splits=1, block_n=0):
-    """C[M,N] = op(a) @ op(b)^T.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); bf16, contiguous rows."""
+def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bfloat16, splits=1, block_n=0,
+         kb_list=None, tile_mask=None, stats=None):
+    """C[M,N] = op(a) @ op(b)^T.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); bf16, contiguous rows.
+    kb_list / tile_mask / stats: the extras of p2r_gemm_bf16_ex (block-sparse reduction, skipped output tiles --
+    those stay zero --, fused per-channel output statistics [copies, 2, 64] float64, zero-filled here by the caller)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
     assert a.stride(1) == 1 and b.stride(1) == 1
     k, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
@@ -27,14 +87,33 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bf
     assert k == kb, (a.shape, b.shape, a_mn, b_mn)
     if splits > 1:
         c = torch.zeros(m, n, dtype=torch.float32, device=a.device)
+    elif tile_mask is not None:
+        c = torch.zeros(m, n, dtype=out_dtype, device=a.device)
     else:
         c = torch.empty(m, n, dtype=out_dtype, device=a.device)
     if bias is not None:
         bias = bias.float().contiguous()
     with torch.cuda.device(a.device):
-        _lib.call("p2r_gemm_bf16", m, n, k, a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
-                  c.data_ptr(), c.stride(0), 1 if c.dtype == torch.bfloat16 else 0,
-                  bias.data_ptr() if bias is not None else None, int(relu), int(splits), int(block_n), _stream())
+        if kb_list is None and tile_mask is None and stats is None:
+            _lib.call("p2r_gemm_bf16", m, n, k, a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+                      c.data_ptr(), c.stride(0), 1 if c.dtype == torch.bfloat16 else 0,
+                      bias.data_ptr() if bias is not None else None, int(relu), int(splits), int(block_n), _stream())
+        else:
+            if kb_list is not None:
+                assert kb_list.dtype == torch.int32 and kb_list.is_contiguous() and kb_list.shape[0] == -(-n // block_n)
+            if tile_mask is not None:
+                assert tile_mask.dtype == torch.uint8 and tile_mask.is_contiguous()
+                assert tuple(tile_mask.shape) == (-(-m // 128), -(-n // block_n))
+            if stats is not None:
+                assert stats.dtype == torch.float64 and stats.is_contiguous() and tuple(stats.shape[1:]) == (2, 64)
+            _lib.call("p2r_gemm_bf16_ex", m, n, k, a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0),
+                      int(b_mn), c.data_ptr(), c.stride(0), 1 if c.dtype == torch.bfloat16 else 0,
+                      bias.data_ptr() if bias is not None else None, int(relu), int(splits), int(block_n),
+                      kb_list.data_ptr() if kb_list is not None else None,
+                      int(kb_list.shape[1]) if kb_list is not None else 0,
+                      tile_mask.data_ptr() if tile_mask is not None else None,
+                      stats.data_ptr() if stats is not None else None, int(stats.shape[0]) if stats is not None else 1,
+                      _stream())
     return c
 
 
@@ -43,7 +122,7 @@ class _TemporalConvTC(torch.autograd.Function):
     three row-shifted TMA views of the SAME activation tensor instead of an unfold buffer."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, targets=None):
+    def forward(ctx, x, weight, bias, targets=None, want_stats=False):
         ctx.targets = targets
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
@@ -51,15 +130,24 @@ class _TemporalConvTC(torch.autograd.Function):
         w2 = weight[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci).to(torch.bfloat16).contiguous()
         y = torch.empty(b * t * v, co, dtype=torch.bfloat16, device=x.device)
         bias_f = bias.float().contiguous() if bias is not None else None
+        sums = None
+        if want_stats and USE_FUSED_STATS and co == 64:
+            sums = torch.zeros(STAT_COPIES, 2, 64, dtype=torch.float64, device=x.device)
         with torch.cuda.device(x.device):
             _lib.call("p2r_tconv_bf16", 0, x.data_ptr(), w2.data_ptr(), None, y.data_ptr(), b, t * v, ci, co, kt, v,
-                      bias_f.data_ptr() if bias_f is not None else None, 1, _stream())
+                      bias_f.data_ptr() if bias_f is not None else None, 1,
+                      sums.data_ptr() if sums is not None else None, STAT_COPIES, _stream())
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        if want_stats:
+            if sums is None:
+                sums = torch.empty(0, dtype=torch.float64, device=x.device)
+            ctx.mark_non_differentiable(sums)
+            return y, sums
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         x, weight = ctx.saved_tensors
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
@@ -70,7 +158,7 @@ class _TemporalConvTC(torch.autograd.Function):
                 wt = weight[:, :, :, 0].permute(2, 0, 1).reshape(kt * co, ci).to(torch.bfloat16).contiguous()
                 dx = torch.empty(b, t, v, ci, dtype=torch.bfloat16, device=x.device)
                 _lib.call("p2r_tconv_bf16", 1, dy.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), b, t * v, ci, co, kt, v,
-                          None, 1, _stream())
+                          None, 1, None, 1, _stream())
             if ctx.targets is not None:
                 tw, tb = ctx.targets
                 need_w = tw is not None and tw.requires_grad
@@ -82,23 +170,23 @@ class _TemporalConvTC(torch.autograd.Function):
                         m = b * t * v
                         dw2 = torch.zeros(co, kt * ci, dtype=torch.float32, device=x.device)
                         _lib.call("p2r_tconv_bf16", 2, x.data_ptr(), None, dy.data_ptr(), dw2.data_ptr(), b, t * v, ci, co,
-                                  kt, v, None, max(1, min(128, m // 8192)), _stream())
+                                  kt, v, None, max(1, min(128, m // 8192)), None, 1, _stream())
                         gw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
                     if need_b:
                         gb = ops._col_sum(dy)
                     return [gw, gb]
                 ops._defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dy, x))
-                return dx, None, None, None
+                return dx, None, None, None, None
             if ctx.needs_input_grad[1]:
                 m = b * t * v
                 splits = max(1, min(128, m // 8192))
                 dw2 = torch.zeros(co, kt * ci, dtype=torch.float32, device=x.device)
                 _lib.call("p2r_tconv_bf16", 2, x.data_ptr(), None, dy.data_ptr(), dw2.data_ptr(), b, t * v, ci, co, kt, v,
-                          None, splits, _stream())
+                          None, splits, None, 1, _stream())
                 dw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = ops._col_sum(dy)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 class _Backend:
@@ -114,23 +202,43 @@ class _Backend:
         return gemm(x, weight.to(torch.bfloat16), False, False, bias, relu, out_dtype=torch.bfloat16)
 
     @staticmethod
-    def linear_dx(dz, weight):
+    def linear_fwd_ex(x, weight, bias, relu, sparsity, want_stats):
+        """forward with the block-sparse reduction and / or the fused BatchNorm statistics of the output."""
+        n = weight.shape[0]
+        sums = None
+        if want_stats and USE_FUSED_STATS and n % 64 == 0:
+            sums = torch.zeros(STAT_COPIES, 2, 64, dtype=torch.float64, device=x.device)
+        sp = sparsity if USE_SPARSITY else None
+        if sp is None and sums is None:
+            return _Backend.linear_fwd(x, weight, bias, relu), None
+        bn = GCN_BLOCK_N if (n % 160 == 0 or GCN_BLOCK_N != 160) else (64 if n <= 64 else 128)
+        kbl = sp.kb_list(bn, False, x.device) if sp is not None else None
+        y = gemm(x, weight.to(torch.bfloat16), False, False, bias, relu, out_dtype=torch.bfloat16, block_n=bn,
+                 kb_list=kbl, stats=sums)
+        return y, sums
+
+    @staticmethod
+    def linear_dx(dz, weight, sparsity=None):
         # dx[M,K] = dz[M,N] . W[N,K]:  A = dz (K-major over n), B = W viewed as [K_red = N, N_out = K] -> MN-major
         w = weight.to(torch.bfloat16)
         n_out = w.shape[1]
-        if n_out % 160 == 0 and n_out >= 640:
+        sp = sparsity if USE_SPARSITY else None
+        if (n_out % 160 == 0 and n_out >= 640) or sp is not None:
             # graph-conv sized layers: a 5 MB transpose of W_eff buys the zero-waste 128x160 K-major tiling
-            return gemm(dz, w.t().contiguous(), False, False, out_dtype=torch.bfloat16, block_n=160)
+            bn = GCN_BLOCK_N if sp is not None else 160
+            kbl = sp.kb_list(bn, True, dz.device) if sp is not None else None
+            return gemm(dz, w.t().contiguous(), False, False, out_dtype=torch.bfloat16, block_n=bn, kb_list=kbl)
         return gemm(dz, w, False, True, out_dtype=torch.bfloat16)
 
     @staticmethod
-    def linear_dw(dz, x):
+    def linear_dw(dz, x, sparsity=None):
         # dW[N,K] = dz^T[N,M] . x[M,K]: both operands MN-major (reduction over the row index m)
         m = dz.shape[0]
         n, k = dz.shape[1], x.shape[1]
         tiles = ((n + 127) // 128) * ((k + 127) // 128)
         if tiles >= 148:  # graph-conv: 13 x 13 = 169 tiles of 128x128 fill the chip without split-K / atomics
-            return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128)
+            mask = sparsity.tile_mask(128, 128, dz.device) if (sparsity is not None and USE_SPARSITY) else None
+            return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128, tile_mask=mask)
         splits = max(1, min((296 + tiles - 1) // tiles, (m + 4095) // 4096))
         return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits)
 
@@ -140,10 +248,11 @@ class _Backend:
         return ci == 64 and co == 64 and (t * v) % 128 == 0
 
     @staticmethod
-    def temporal_conv(x, weight, bias):
-        if ops.DEFER["on"] and torch.is_grad_enabled():
-            return _TemporalConvTC.apply(x, weight.detach(), bias.detach() if bias is not None else None, (weight, bias))
-        return _TemporalConvTC.apply(x, weight, bias)
+    def temporal_conv(x, weight, bias, want_stats=False):
+        if ops.DEFER["on"] and torch.is_grad_enabled() and x.requires_grad:
+            return _TemporalConvTC.apply(x, weight.detach(), bias.detach() if bias is not None else None, (weight, bias),
+                                         want_stats)
+        return _TemporalConvTC.apply(x, weight, bias, None, want_stats)
 
 
 def install():

@@ -150,10 +150,12 @@ def _smallk_ok(x, n, k, relu):
 
 class _Linear(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, targets=None):
+    def forward(ctx, x, weight, bias, relu, targets=None, sparsity=None, want_stats=False):
         ctx.targets = targets      # (weight, bias) with their autograd history when the gradient is deferred
+        ctx.sparsity = sparsity    # 64x64 block pattern of `weight` (gemm_sm100.BlockSparsity) or None
         x = x if x.is_contiguous() else x.contiguous()
         tc = _TC_GEMM["fn"]
+        sums = None
         with _Timed("fwd", x.shape[0], weight.shape[0], x.shape[1]):
             if _smallk_ok(x, weight.shape[0], x.shape[1], relu):
                 y = torch.empty(x.shape[0], weight.shape[0], dtype=x.dtype, device=x.device)
@@ -163,17 +165,26 @@ class _Linear(Function):
                     _lib.call("p2r_smallk_linear", x.data_ptr(), wf.data_ptr(), _ptr(bf), _DT[x.dtype], x.shape[0],
                               weight.shape[0], x.shape[1], y.data_ptr(), _stream())
             elif tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
-                y = tc.linear_fwd(x, weight, bias, relu)
+                if sparsity is not None or want_stats:
+                    y, sums = tc.linear_fwd_ex(x, weight, bias, relu, sparsity, want_stats)
+                else:
+                    y = tc.linear_fwd(x, weight, bias, relu)
             else:
                 y = sgemm(x, weight, False, True, bias, relu, out_dtype=x.dtype)
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.relu = relu
         ctx.has_bias = bias is not None
+        if want_stats:
+            if sums is None:     # kernels without the fused epilogue statistics: the caller runs its own pass
+                sums = torch.empty(0, dtype=torch.float64, device=x.device)
+            ctx.mark_non_differentiable(sums)
+            return y, sums
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         x, weight, y = ctx.saved_tensors
+        sp = ctx.sparsity
         dy = dy if dy.is_contiguous() else dy.contiguous()
         if ctx.relu:
             dz = torch.empty_like(dy)
@@ -188,7 +199,7 @@ class _Linear(Function):
         use_tc = tc is not None and x.dtype == torch.bfloat16 and tc.supports(m, n, k)
         if ctx.needs_input_grad[0]:
             with _Timed("dx", m, n, k):
-                dx = tc.linear_dx(dz, weight) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
+                dx = tc.linear_dx(dz, weight, sp) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
         if ctx.targets is not None:
             tw, tb = ctx.targets
             need_w = tw is not None and tw.requires_grad
@@ -203,14 +214,14 @@ class _Linear(Function):
                             _lib.call("p2r_smallk_dw", dz.data_ptr(), x.data_ptr(), _DT[x.dtype], m, n, k,
                                       gw.data_ptr(), _stream())
                     elif use_tc:
-                        gw = tc.linear_dw(dz, x)
+                        gw = tc.linear_dw(dz, x, sp)
                     else:
                         gw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
                 if need_b:
                     gb = _col_sum(dz)
                 return [gw, gb]
             _defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dz, x))
-            return dx, None, None, None, None
+            return dx, None, None, None, None, None, None
         if ctx.needs_input_grad[1]:
             with _Timed("dw", m, n, k):
                 if _smallk_ok(x, n, k, ctx.relu):
@@ -219,19 +230,24 @@ class _Linear(Function):
                         _lib.call("p2r_smallk_dw", dz.data_ptr(), x.data_ptr(), _DT[x.dtype], m, n, k, dw.data_ptr(),
                                   _stream())
                 elif use_tc:
-                    dw = tc.linear_dw(dz, x)
+                    dw = tc.linear_dw(dz, x, sp)
                 else:
                     dw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _col_sum(dz)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu=False):
-    """y[M,N] = x[M,K] @ weight[N,K]^T (+bias)(ReLU): a 1x1 Conv1d/Conv2d in channel-last form."""
-    if DEFER["on"] and not PROFILE["on"] and x.shape[0] >= 4096 and torch.is_grad_enabled():
-        return _Linear.apply(x, weight.detach(), bias.detach() if bias is not None else None, relu, (weight, bias))
-    return _Linear.apply(x, weight, bias, relu)
+def linear(x, weight, bias=None, relu=False, sparsity=None, want_stats=False):
+    """y[M,N] = x[M,K] @ weight[N,K]^T (+bias)(ReLU): a 1x1 Conv1d/Conv2d in channel-last form.
+    sparsity: optional 64x64 block pattern of `weight` (zero blocks are skipped by the tensor-core kernel).
+    want_stats: also return the per-channel (column % 64) sum / sum of squares of y from the GEMM epilogue, shaped
+    [copies, 2, 64] float64 (an EMPTY tensor when the kernel in use cannot produce them) -> returns (y, sums)."""
+    # (a layer whose input carries no gradient would drop out of the graph with a detached weight: keep it on the plain path)
+    if DEFER["on"] and not PROFILE["on"] and x.shape[0] >= 4096 and torch.is_grad_enabled() and x.requires_grad:
+        return _Linear.apply(x, weight.detach(), bias.detach() if bias is not None else None, relu, (weight, bias),
+                             sparsity, want_stats)
+    return _Linear.apply(x, weight, bias, relu, None, sparsity, want_stats)
 
 
 class _BatchNormAct(Function):
@@ -240,7 +256,7 @@ class _BatchNormAct(Function):
     (stgcn_layers.py:402-414) followed by `+ res` and ReLU (:436-438)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu, sums=None):
         x = x if x.is_contiguous() else x.contiguous()
         m, c = x.shape
         dev = x.device
@@ -248,9 +264,12 @@ class _BatchNormAct(Function):
         stats = torch.empty(4, c, dtype=torch.float32, device=dev)  # mean, rstd, scale, shift
         with torch.cuda.device(dev):
             if training:
-                sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
-                _lib.call("p2r_col_stats", x.data_ptr(), dt, m, c, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
-                _lib.call("p2r_bn_finalize", c, m, sums[0].data_ptr(), sums[1].data_ptr(), _ptr(gamma), _ptr(beta),
+                if sums is None or sums.numel() == 0:     # no statistics from the producing GEMM's epilogue
+                    sums = torch.zeros(1, 2, c, dtype=torch.float64, device=dev)
+                    _lib.call("p2r_col_stats", x.data_ptr(), dt, m, c, sums[0, 0].data_ptr(), sums[0, 1].data_ptr(), _stream())
+                assert sums.dim() == 3 and sums.shape[1] == 2 and sums.shape[2] == c and sums.is_contiguous()
+                _lib.call("p2r_bn_finalize", c, m, sums[0, 0].data_ptr(), sums[0, 1].data_ptr(), sums.shape[0], 2 * c,
+                          _ptr(gamma), _ptr(beta),
                           float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), stats[0].data_ptr(),
                           stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), _stream())
             else:
@@ -290,18 +309,19 @@ class _BatchNormAct(Function):
                       stats[3].data_ptr(), _stream())
         dgamma = sums[1].float() if ctx.needs_input_grad[1] else None
         dbeta = sums[0].float() if ctx.needs_input_grad[2] else None
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
-def batchnorm_act(x, bn, relu=False, residual=None):
+def batchnorm_act(x, bn, relu=False, residual=None, sums=None):
     """Apply nn.BatchNorm{1,2}d module `bn` (its parameters / running stats / momentum / eps / mode) to the
-    channel-last matrix x[M,C], optionally adding `residual` and a ReLU -- one fused elementwise pass."""
+    channel-last matrix x[M,C], optionally adding `residual` and a ReLU -- one fused elementwise pass.
+    sums: per-channel [copies, 2, C] float64 sum / sum of squares of x already produced by the GEMM that wrote x."""
     training = bn.training or not bn.track_running_stats
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     momentum = 0.1 if bn.momentum is None else bn.momentum
     return _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training,
-                               momentum, bn.eps, relu)
+                               momentum, bn.eps, relu, sums)
 
 
 class _TemporalUnfold(Function):
@@ -325,16 +345,17 @@ class _TemporalUnfold(Function):
         return dx, None
 
 
-def temporal_conv(x, weight, bias):
+def temporal_conv(x, weight, bias, want_stats=False):
     """(KT x 1) temporal convolution, zero padding (KT-1)/2, stride 1 (stgcn_layers.py:405-411).
-    x [B,T,V,Ci] channel-last, weight (Co,Ci,KT,1) as stored by nn.Conv2d -> [B*T*V, Co]."""
+    x [B,T,V,Ci] channel-last, weight (Co,Ci,KT,1) as stored by nn.Conv2d -> [B*T*V, Co].
+    want_stats: -> (y, sums) like linear()."""
     co, ci, kt, _ = weight.shape
     tc = _TC_GEMM["fn"]
     if tc is not None and x.dtype == torch.bfloat16 and tc.supports_tconv(x.shape, co):
-        return tc.temporal_conv(x, weight, bias)
+        return tc.temporal_conv(x, weight, bias, want_stats)
     col = _TemporalUnfold.apply(x, kt)
     w2 = weight[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci)  # column = dt*Ci + ci
-    return linear(col, w2, bias)
+    return linear(col, w2, bias, want_stats=want_stats)
 
 
 class _GroupRows(Function):

@@ -60,16 +60,18 @@ class st_gcn_block(nn.Module):
         self.has_residual = residual
         self.relu = nn.ReLU(inplace=True)
 
-    def forward_rows(self, x, A):
-        """x [B,T,V,C] channel-last -> [B,T,V,C]."""
+    def forward_rows(self, x, A, sparsity=None):
+        """x [B,T,V,C] channel-last -> [B,T,V,C].  `sparsity`: 64x64 block pattern of W_eff (zero where two joints
+        are more than max_hop apart); both GEMMs hand the statistics of the BatchNorm that follows them back from
+        their epilogue, so neither BatchNorm re-reads its input to normalise it."""
         b, t, v, c = x.shape
         co = self.gcn.out_channels
         w_eff, b_eff = self.gcn.effective_weight(A)
-        g = ops.linear(x.reshape(b * t, v * c), w_eff, b_eff)                    # graph conv: one GEMM
-        h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True)  # BN + ReLU
-        y = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias)
+        g, s1 = ops.linear(x.reshape(b * t, v * c), w_eff, b_eff, sparsity=sparsity, want_stats=True)   # graph conv
+        h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True, sums=s1)                # BN + ReLU
+        y, s2 = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias, want_stats=True)
         res = x.reshape(b * t * v, c) if self.has_residual else None
-        out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res)         # BN + residual + ReLU
+        out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res, sums=s2)                       # BN + res + ReLU
         return out.reshape(b, t, v, co)
 
 
@@ -102,6 +104,10 @@ class STGCN(nn.Module):
         else:
             self.seed_sampling = cfg.config["data"]["seed_sampling"]
         self._idx_cache = {}
+        # W_eff[(w,co),(v,ci)] = sum_k W_k[co,ci] A_k[v,w]: block (w,v) is structurally zero where no partition links v, w
+        from ..gemm_sm100 import BlockSparsity
+        # (every st_gcn block is 64 -> 64 channels, stgcn.py:53-60: one 64-wide block per joint on both axes)
+        self._w_sparsity = BlockSparsity((A.abs().sum(0) > 0).t().numpy())
 
     # ------------------------------------------------------------------ pieces
     def _seed_inds(self, input_joints):
@@ -147,7 +153,7 @@ class STGCN(nn.Module):
         x = ops.embed_sum(sk.reshape(b * t, j, 64), pos.reshape(b * t, self.knn, 64)).reshape(b, t, j, 64)
 
         for blk, importance in zip(self.st_gcn_networks, self.edge_importance):
-            x = blk.forward_rows(x, self.A * importance)
+            x = blk.forward_rows(x, self.A * importance, self._w_sparsity)
 
         # conv_joint on the seed frames only; reference channel order is c*J + v (stgcn.py:136-139)
         frames = x.reshape(b, t, j * 64)

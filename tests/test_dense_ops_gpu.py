@@ -143,3 +143,93 @@ def test_bf16_storage_variants(cuda):
     bn2 = nn.BatchNorm1d(64).to(cuda)
     z32 = ops.batchnorm_act(y32, bn2, relu=True)
     _close(z16, z32, rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("M", [4096, 5000 * 3 + 17, 70000])
+@pytest.mark.parametrize("relu,res", [(True, False), (False, False), (True, True)])
+def test_streaming_batchnorm_bf16_matches_fp64(cuda, M, relu, res):
+    """[M, 64] bf16 operands take the bulk-TMA streaming kernels (stream_bn.cu); forward, running statistics and all
+    gradients against an fp64 BatchNorm on the same bf16-rounded inputs, including a ragged last tile."""
+    from pose2room_b200 import ops
+    C = 64
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(cuda).bfloat16().requires_grad_(True)
+    r = torch.randn(M, C, generator=g).to(cuda).bfloat16().requires_grad_(True) if res else None
+    bn = nn.BatchNorm1d(C).to(cuda)
+    with torch.no_grad():
+        bn.weight.normal_(1, 0.2)
+        bn.bias.normal_(0, 0.2)
+    bn_ref = nn.BatchNorm1d(C).to(cuda).double()
+    bn_ref.load_state_dict(bn.state_dict())
+    y = ops.batchnorm_act(x, bn, relu=relu, residual=r)
+    assert y.dtype == torch.bfloat16
+    xr = x.detach().double().requires_grad_(True)
+    rr = r.detach().double().requires_grad_(True) if res else None
+    ref = bn_ref(xr)
+    if res:
+        ref = ref + rr
+    if relu:
+        ref = F.relu(ref)
+    _close(y, ref, rtol=1e-2, atol=1e-2)                                  # bf16 storage of y
+    _close(bn.running_mean, bn_ref.running_mean, rtol=1e-5, atol=1e-6)    # statistics are exact sums of the bf16 inputs
+    _close(bn.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-6)
+    go = torch.randn(M, C, generator=g).to(cuda).bfloat16()
+    # the ReLU mask of the kernels comes from the bf16 y (with residual) or the fp32 pre-activation (without): mask the
+    # reference gradient with the kernels' own y so that isolated sign flips at |pre-activation| ~ 0 do not count
+    y.backward(go)
+    if relu:
+        mask = (y.detach().double() > 0).double()
+        pre = bn_ref(xr) + (rr if res else 0)
+        (pre * mask).backward(go.double())
+    else:
+        ref.backward(go.double())
+
+    def close_scaled(a, b, tol):
+        scale = b.abs().max().item() + 1e-12
+        assert (a.double() - b).abs().max().item() <= tol * scale, ((a.double() - b).abs().max().item(), scale)
+    close_scaled(x.grad, xr.grad, 1e-2)
+    close_scaled(bn.weight.grad, bn_ref.weight.grad, 2e-3)
+    close_scaled(bn.bias.grad, bn_ref.bias.grad, 2e-3)
+    if res:
+        close_scaled(r.grad, rr.grad, 1e-2)
+
+
+def test_streaming_kernels_equal_generic_kernels(cuda):
+    """The same C-ABI calls with P2R_STREAM_BN toggled (subprocess: the switch is read once) give identical column sums
+    (up to fp32 partial-sum order) and bit-identical elementwise outputs."""
+    import json, os, subprocess, sys
+    code = r'''
+import json, torch
+from pose2room_b200 import _lib
+dev = torch.device("cuda:0"); M, C = 50000 + 37, 64
+g = torch.Generator().manual_seed(5)
+x = torch.randn(M, C, generator=g).to(dev).bfloat16(); dy = torch.randn(M, C, generator=g).to(dev).bfloat16()
+yy = torch.randn(M, C, generator=g).to(dev).bfloat16()
+st = torch.rand(4, C, generator=g).to(dev) + 0.5
+s = torch.zeros(6, C, dtype=torch.float64, device=dev)
+out = torch.zeros(5, M, C, dtype=torch.bfloat16, device=dev)
+cs = torch.cuda.current_stream().cuda_stream
+_lib.call("p2r_col_stats", x.data_ptr(), 1, M, C, s[0].data_ptr(), s[1].data_ptr(), cs)
+_lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), 2, s[2].data_ptr(), s[3].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), cs)
+_lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), 1, s[4].data_ptr(), s[5].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), cs)
+_lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), None, 1, out[0].data_ptr(), cs)
+_lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), yy.data_ptr(), 1, out[1].data_ptr(), cs)
+_lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), 2, out[2].data_ptr(), None, st[3].data_ptr(), cs)
+_lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[4].data_ptr(), s[5].data_ptr(), 1, out[3].data_ptr(), out[4].data_ptr(), st[3].data_ptr(), cs)
+torch.cuda.synchronize()
+print(json.dumps({"s": s.cpu().tolist(), "o": [float(out[i].float().sum()) for i in range(5)],
+                  "h": [int(out[i].view(torch.int16).long().sum()) for i in range(5)]}))
+'''
+    res = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, P2R_STREAM_BN=flag)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = res
+    sa, sb = torch.tensor(a["s"]), torch.tensor(b["s"])
+    assert torch.allclose(sa, sb, rtol=1e-5, atol=1e-2), (sa - sb).abs().max()
+    assert a["h"][0] == b["h"][0] and a["h"][1] == b["h"][1] and a["h"][4] == b["h"][4]   # bit-identical outputs
+    # dx depends on the sums (tiny differences in the last fp32 bit of the coefficients): compare as values
+    assert abs(a["o"][2] - b["o"][2]) <= 1e-3 * (abs(b["o"][2]) + 1) and abs(a["o"][3] - b["o"][3]) <= 1e-3 * (abs(b["o"][3]) + 1)

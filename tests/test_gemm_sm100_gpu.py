@@ -121,3 +121,138 @@ def test_implicit_temporal_conv_fwd_dx_dw(cuda):
             assert torch.allclose(gw, rw, rtol=1e-5, atol=1e-2) and torch.allclose(gb, rb, rtol=1e-5, atol=1e-2)
     finally:
         gemm_sm100.uninstall()
+
+
+def _random_block_pattern(nb, kb, g, density=0.5):
+    nz = torch.rand(nb, kb, generator=g) < density
+    nz |= torch.eye(nb, kb, dtype=torch.bool)          # every n-block keeps at least one k-block
+    return nz.numpy()
+
+
+@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+def test_gemm_block_sparse_reduction_exact(cuda, bn):
+    """kb_list: only the listed 64-wide k-blocks of each n-tile are loaded / multiplied.  With a weight that IS zero in
+    the skipped blocks the result must equal the dense product -- exactly, on integer-valued operands."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100
+    g = torch.Generator().manual_seed(10 + bn)
+    M, NB, KB = 384, 10, 10                        # N = K = 640 (a multiple of 160 and of 64)
+    nz = _random_block_pattern(NB, KB, g)
+    sp = gemm_sm100.BlockSparsity(nz)
+    w = torch.randint(-3, 4, (NB * 64, KB * 64), generator=g).float()
+    w *= torch.from_numpy(np.kron(nz, np.ones((64, 64), dtype=np.float32)))
+    x = torch.randint(-3, 4, (M, KB * 64), generator=g).float()
+    xb, wb = x.to(cuda).bfloat16(), w.to(cuda).bfloat16()
+    c = gemm_sm100.gemm(xb, wb, out_dtype=torch.float32, block_n=bn, kb_list=sp.kb_list(bn, False, cuda))
+    assert torch.equal(c.cpu(), x @ w.t())
+    # input-gradient orientation: dx = dz . W, reduction over W's rows, pattern transposed
+    dz = torch.randint(-3, 4, (M, NB * 64), generator=g).float()
+    c = gemm_sm100.gemm(dz.to(cuda).bfloat16(), wb.t().contiguous(), out_dtype=torch.float32, block_n=bn,
+                        kb_list=sp.kb_list(bn, True, cuda))
+    assert torch.equal(c.cpu(), dz @ w)
+    # a k-block list shorter than the weight's support really skips work: drop everything -> bias only
+    empty = torch.zeros_like(sp.kb_list(bn, False, cuda))
+    bias = torch.arange(NB * 64, dtype=torch.float32, device=cuda)
+    c = gemm_sm100.gemm(xb, wb, bias=bias, out_dtype=torch.float32, block_n=bn, kb_list=empty)
+    assert torch.equal(c, bias[None].expand(M, -1))
+
+
+def test_gemm_tile_mask_weight_gradient(cuda):
+    """tile_mask: structurally-zero 128x128 tiles of dW = dz^T.x are skipped and stay zero, the others are exact."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100
+    g = torch.Generator().manual_seed(11)
+    M, NB, KB = 1024, 6, 6
+    nz = _random_block_pattern(NB, KB, g, density=0.3)
+    sp = gemm_sm100.BlockSparsity(nz)
+    dz = torch.randint(-2, 3, (M, NB * 64), generator=g).float()
+    x = torch.randint(-2, 3, (M, KB * 64), generator=g).float()
+    mask = sp.tile_mask(128, 128, cuda)
+    c = gemm_sm100.gemm(dz.to(cuda).bfloat16(), x.to(cuda).bfloat16(), True, True, out_dtype=torch.float32, block_n=128,
+                        tile_mask=mask)
+    full = dz.t() @ x
+    keep = torch.from_numpy(np.kron(mask.cpu().numpy(), np.ones((128, 128), dtype=np.float32)))[:NB * 64, :KB * 64]
+    assert torch.equal(c.cpu(), full * keep)
+    # every block the pattern marks non-zero lies inside a kept tile
+    assert (keep.numpy() >= np.kron(nz, np.ones((64, 64), dtype=np.float32))).all()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(384, 640, 256, 160), (1000, 128, 192, 128), (4096, 64, 64, 64), (130, 320, 64, 160),
+                                       (33000, 64, 192, 64)])
+def test_gemm_fused_output_statistics(cuda, M, N, K, bn):
+    """stats: per-channel (column % 64) sum and sum of squares of the STORED bf16 output, from the GEMM epilogue."""
+    from pose2room_b200 import gemm_sm100
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(cuda).bfloat16()
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda)
+    for copies in (1, 16):
+        stats = torch.zeros(copies, 2, 64, dtype=torch.float64, device=cuda)
+        c = gemm_sm100.gemm(a, b, bias=bias, out_dtype=torch.bfloat16, block_n=bn, stats=stats)
+        ref = gemm_sm100.gemm(a, b, bias=bias, out_dtype=torch.bfloat16, block_n=bn)
+        assert torch.equal(c, ref)                                      # the output itself is unchanged
+        cd = c.double().reshape(M, N // 64, 64)
+        s = stats.sum(0)
+        assert torch.allclose(s[0], cd.sum((0, 1)), rtol=1e-5, atol=1e-3 * M ** 0.5), (s[0] - cd.sum((0, 1))).abs().max()
+        assert torch.allclose(s[1], (cd * cd).sum((0, 1)), rtol=1e-5, atol=1e-3), (s[1] - (cd * cd).sum((0, 1))).abs().max()
+
+
+def test_tconv_and_batchnorm_with_fused_statistics(cuda):
+    """temporal_conv(..., want_stats=True) + batchnorm_act(..., sums=...) == the two-pass BatchNorm on the same y."""
+    import torch.nn as nn
+    from pose2room_b200 import gemm_sm100, ops
+    gemm_sm100.install()
+    try:
+        g = torch.Generator().manual_seed(12)
+        B, T, V, C = 2, 256, 25, 64
+        conv = nn.Conv2d(C, C, (3, 1), (1, 1), (1, 0)).to(cuda)
+        x = torch.randn(B, T, V, C, generator=g).to(cuda).bfloat16()
+        y, sums = ops.temporal_conv(x, conv.weight, conv.bias, want_stats=True)
+        assert sums.numel() > 0 and sums.shape[1:] == (2, 64)
+        y2 = ops.temporal_conv(x, conv.weight, conv.bias)
+        assert torch.equal(y, y2)
+        yd = y.double()
+        assert torch.allclose(sums.sum(0)[0], yd.sum(0), rtol=1e-6, atol=1e-2)
+        assert torch.allclose(sums.sum(0)[1], (yd * yd).sum(0), rtol=1e-6, atol=1e-2)
+        bn_a, bn_b = nn.BatchNorm2d(C).to(cuda).train(), nn.BatchNorm2d(C).to(cuda).train()
+        out_a = ops.batchnorm_act(y, bn_a, relu=True, sums=sums)
+        out_b = ops.batchnorm_act(y, bn_b, relu=True)
+        assert torch.allclose(out_a.float(), out_b.float(), atol=2e-2)
+        assert torch.allclose(bn_a.running_mean, bn_b.running_mean, atol=1e-6)
+        assert torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-6, atol=1e-7)
+    finally:
+        gemm_sm100.uninstall()
+
+
+def test_graph_conv_linear_sparse_matches_dense(cuda):
+    """ops.linear on a real W_eff (25 joints, max_hop 5) with the block pattern from the adjacency: forward, dx and dW
+    equal the dense run (the skipped blocks are exact zeros of W_eff; dW is compared on the pattern's support)."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100, ops
+    from pose2room_b200.p2rnet.graph import layout_for_joints, spatial_adjacency
+    gemm_sm100.install()
+    try:
+        g = torch.Generator().manual_seed(13)
+        A = torch.tensor(np.array(spatial_adjacency(layout_for_joints(25), max_hop=5)), dtype=torch.float32)
+        sp = gemm_sm100.BlockSparsity((A.abs().sum(0) > 0).t().numpy())
+        assert 0.4 < sp.density < 0.6
+        wk = torch.randn(11, 64, 64, generator=g) / 8
+        w_eff = torch.einsum("koi,kvw->wovi", wk, A).reshape(1600, 1600).to(cuda)
+        support = torch.from_numpy(np.kron(sp.nz, np.ones((64, 64), dtype=np.float32))).to(cuda)
+        assert torch.equal(w_eff * support, w_eff)
+        bias = torch.randn(1600, generator=g).to(cuda)
+        outs = []
+        for s in (None, sp):
+            x = torch.randn(1024, 1600, generator=torch.Generator().manual_seed(99)).to(cuda).bfloat16().requires_grad_(True)
+            w = w_eff.clone().requires_grad_(True)
+            y, sums = ops.linear(x, w, bias, sparsity=s, want_stats=True)
+            go = torch.randn(1024, 1600, generator=torch.Generator().manual_seed(98)).to(cuda).bfloat16()
+            gx, gw = torch.autograd.grad(y, [x, w], go)
+            outs.append((y, gx, gw, sums))
+        (y0, gx0, gw0, s0), (y1, gx1, gw1, s1) = outs
+        _check(y1, y0.float(), tol=1e-2)
+        _check(gx1, gx0.float(), tol=1e-2)
+        _check(gw1 * support, gw0 * support, tol=1e-4)
+        assert torch.allclose(s0.sum(0), s1.sum(0), rtol=1e-3, atol=1.0)
+    finally:
+        gemm_sm100.uninstall()
