@@ -191,6 +191,18 @@ int p2r_gemm_bf16_ex(int M, int N, int K, const void* A, int lda, int a_mn, cons
 int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows, int Ci,
                    int Co, int KT, int V, const float* bias, int splits, double* stats, int stat_copies, void* stream);
 
+/* Weight plumbing of the fused graph convolution (ref: ConvTemporalGraphical.forward, stgcn_layers.py:58-67; A = adjacency
+ * stack * edge importance, stgcn.py:133-134).  Build  W_eff[(w,co),(v,ci)] = sum_k A[k,v,w] W[k*Co+co, ci]  (bf16), its
+ * transpose (bf16, the operand of the input-gradient GEMM) and  b_eff[(w,co)] = sum_k b[k*Co+co] sum_v A[k,v,w]  (fp32)
+ * from conv_w [K*Co, Ci] fp32, conv_b [K*Co] fp32 (or NULL), A [K,V,V] fp32.  Co = Ci = 64.                          */
+int p2r_gcn_build_weight(const float* conv_w, const float* conv_b, const float* A, int K, int V, int Co, int Ci,
+                         void* w_eff, void* w_eff_t, float* b_eff, void* stream);
+/* ... and its backward: fold dW_eff [V*Co, V*Ci] fp32 and db_eff [V*Co] fp32 onto d_conv_w [K*Co, Ci], d_conv_b [K*Co]
+ * (both accumulated with atomics: zero-filled by the caller) and dA [K,V,V] (written; 0 where A == 0).             */
+int p2r_gcn_reduce_weight_grad(const float* dw_eff, const float* db_eff, const float* conv_w, const float* conv_b,
+                               const float* A, int K, int V, int Co, int Ci, float* d_conv_w, float* d_conv_b,
+                               float* dA, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

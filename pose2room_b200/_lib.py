@@ -44,6 +44,8 @@ SIGNATURES = {
                          _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp],
     "p2r_tconv_bf16": [_c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp,
                        _c_int, _vp],
+    "p2r_gcn_build_weight": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
+    "p2r_gcn_reduce_weight_grad": [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "p2r_embed_sum": [_vp, _vp, _c_int, _c_ll, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_embed_sum_grad": [_vp, _c_int, _c_ll, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_linear": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],

@@ -231,6 +231,14 @@ class _Backend:
         return gemm(dz, w, False, True, out_dtype=torch.bfloat16)
 
     @staticmethod
+    def linear_dx_pretransposed(dz, w_t, sparsity=None):
+        """dx = dz . W with W^T [K, N] already materialised in bf16 (the graph-conv weight builder writes both)."""
+        sp = sparsity if USE_SPARSITY else None
+        bn = GCN_BLOCK_N if (w_t.shape[0] % 160 == 0 or GCN_BLOCK_N != 160) else 128
+        kbl = sp.kb_list(bn, True, dz.device) if sp is not None else None
+        return gemm(dz, w_t, False, False, out_dtype=torch.bfloat16, block_n=bn, kb_list=kbl)
+
+    @staticmethod
     def linear_dw(dz, x, sparsity=None):
         # dW[N,K] = dz^T[N,M] . x[M,K]: both operands MN-major (reduction over the row index m)
         m = dz.shape[0]

@@ -250,6 +250,83 @@ def linear(x, weight, bias=None, relu=False, sparsity=None, want_stats=False):
     return _Linear.apply(x, weight, bias, relu, None, sparsity, want_stats)
 
 
+class _GraphConv(Function):
+    """The graph convolution of st_gcn_block as ONE tensor-core GEMM (bf16 mode): builds W_eff / W_eff^T / b_eff from
+    the conv parameters and A = adjacency * importance with one kernel, runs the block-sparse GEMM (statistics of the
+    following BatchNorm from its epilogue), and in the backward folds dW_eff back onto conv weight, conv bias and A with
+    one kernel.  ref: ConvTemporalGraphical.forward, stgcn_layers.py:58-67."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, a_eff, targets, sparsity, want_stats):
+        tc = _TC_GEMM["fn"]
+        k, v = a_eff.shape[0], a_eff.shape[1]
+        co, ci = conv_w.shape[0] // k, conv_w.shape[1]
+        x = x if x.is_contiguous() else x.contiguous()
+        dev = x.device
+        cw = conv_w.reshape(k * co, ci).float().contiguous()
+        cb = conv_b.float().contiguous() if conv_b is not None else None
+        ae = a_eff.float().contiguous()
+        w_eff = torch.empty(v * co, v * ci, dtype=torch.bfloat16, device=dev)
+        w_eff_t = torch.empty(v * ci, v * co, dtype=torch.bfloat16, device=dev)
+        b_eff = torch.empty(v * co, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("p2r_gcn_build_weight", cw.data_ptr(), _ptr(cb), ae.data_ptr(), k, v, co, ci, w_eff.data_ptr(),
+                      w_eff_t.data_ptr(), b_eff.data_ptr(), _stream())
+        with _Timed("fwd", x.shape[0], v * co, v * ci):
+            y, sums = tc.linear_fwd_ex(x, w_eff, b_eff, False, sparsity, want_stats)
+        ctx.save_for_backward(x, cw, cb, ae, w_eff_t)
+        ctx.targets, ctx.sparsity, ctx.dims = targets, sparsity, (k, v, co, ci)
+        ctx.w_shape = conv_w.shape
+        if sums is None:
+            sums = torch.empty(0, dtype=torch.float64, device=dev)
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, dy, _dsums=None):
+        x, cw, cb, ae, w_eff_t = ctx.saved_tensors
+        k, v, co, ci = ctx.dims
+        sp = ctx.sparsity
+        tc = _TC_GEMM["fn"]
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            with _Timed("dx", dy.shape[0], v * co, v * ci):
+                dx = tc.linear_dx_pretransposed(dy, w_eff_t, sp)
+
+        def weight_grads():
+            dw_eff = tc.linear_dw(dy, x, sp)                     # fp32 [V*Co, V*Ci], structurally-zero tiles stay 0
+            db_eff = _col_sum(dy) if cb is not None else None
+            d_w = torch.zeros(k * co, ci, dtype=torch.float32, device=dy.device)
+            d_b = torch.zeros(k * co, dtype=torch.float32, device=dy.device) if cb is not None else None
+            d_a = torch.empty(k, v, v, dtype=torch.float32, device=dy.device)
+            with torch.cuda.device(dy.device):
+                _lib.call("p2r_gcn_reduce_weight_grad", dw_eff.data_ptr(), _ptr(db_eff), cw.data_ptr(), _ptr(cb),
+                          ae.data_ptr(), k, v, co, ci, d_w.data_ptr(), _ptr(d_b), d_a.data_ptr(), _stream())
+            return [d_w.reshape(ctx.w_shape), d_b, d_a]
+
+        if ctx.targets is not None:
+            _defer(weight_grads, [t if (t is not None and t.requires_grad) else None for t in ctx.targets], (dy, x))
+            return dx, None, None, None, None, None, None
+        gw, gb, ga = weight_grads()
+        return dx, gw, gb, ga, None, None, None
+
+
+def graph_conv(x, conv_weight, conv_bias, a_eff, sparsity=None, want_stats=True):
+    """x [M, V*Ci] frames (channel-last joints) -> (y [M, V*Co], sums): the st_gcn graph convolution with conv weight
+    (K*Co, Ci, 1, 1), conv bias (K*Co,), A_eff (K, V, V).  Tensor-core (bf16) path only -- callers check
+    `graph_conv_available(x)` and use the generic linear() otherwise."""
+    if DEFER["on"] and not PROFILE["on"] and torch.is_grad_enabled() and x.requires_grad:
+        return _GraphConv.apply(x, conv_weight.detach(), conv_bias.detach() if conv_bias is not None else None,
+                                a_eff.detach(), (conv_weight, conv_bias, a_eff), sparsity, want_stats)
+    return _GraphConv.apply(x, conv_weight, conv_bias, a_eff, None, sparsity, want_stats)
+
+
+def graph_conv_available(x, co, ci):
+    tc = _TC_GEMM["fn"]
+    return tc is not None and x.dtype == torch.bfloat16 and co == 64 and ci == 64 and x.shape[0] >= 128
+
+
 class _BatchNormAct(Function):
     """Training- or eval-mode BatchNorm over the rows of x[M,C] (+residual)(+ReLU).
     ref: nn.BatchNorm1d/2d inside SingleConv 'cbr' (sub_modules.py:64-70) and st_gcn_block.tcn

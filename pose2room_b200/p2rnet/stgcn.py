@@ -66,8 +66,12 @@ class st_gcn_block(nn.Module):
         their epilogue, so neither BatchNorm re-reads its input to normalise it."""
         b, t, v, c = x.shape
         co = self.gcn.out_channels
-        w_eff, b_eff = self.gcn.effective_weight(A)
-        g, s1 = ops.linear(x.reshape(b * t, v * c), w_eff, b_eff, sparsity=sparsity, want_stats=True)   # graph conv
+        frames = x.reshape(b * t, v * c)
+        if ops.graph_conv_available(frames, co, c):   # bf16: weight build + block-sparse GEMM + statistics, 2 launches
+            g, s1 = ops.graph_conv(frames, self.gcn.conv.weight, self.gcn.conv.bias, A, sparsity)
+        else:
+            w_eff, b_eff = self.gcn.effective_weight(A)
+            g, s1 = ops.linear(frames, w_eff, b_eff, sparsity=sparsity, want_stats=True)
         h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True, sums=s1)                # BN + ReLU
         y, s2 = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias, want_stats=True)
         res = x.reshape(b * t * v, c) if self.has_residual else None

@@ -256,3 +256,51 @@ def test_graph_conv_linear_sparse_matches_dense(cuda):
         assert torch.allclose(s0.sum(0), s1.sum(0), rtol=1e-3, atol=1.0)
     finally:
         gemm_sm100.uninstall()
+
+
+@pytest.mark.parametrize("defer", [False, True])
+def test_graph_conv_op_matches_einsum_formulation(cuda, defer):
+    """ops.graph_conv (weight-build kernel + block-sparse GEMM + gradient-fold kernel) against the reference's own
+    formulation -- conv 64 -> K*64 followed by einsum 'nkctv,kvw->nctw' (stgcn_layers.py:58-67) -- in fp32 autograd on
+    the same bf16-rounded input: output, input gradient, and the gradients of conv weight, conv bias, edge importance."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100, ops
+    from pose2room_b200.p2rnet.graph import layout_for_joints, spatial_adjacency
+    gemm_sm100.install()
+    try:
+        g = torch.Generator().manual_seed(21)
+        A = torch.tensor(np.array(spatial_adjacency(layout_for_joints(25), max_hop=5)), dtype=torch.float32).to(cuda)
+        K, V, C, N, T = A.shape[0], 25, 64, 2, 256
+        sp = gemm_sm100.BlockSparsity((A.abs().sum(0) > 0).t().cpu().numpy())
+        conv_w = (torch.randn(K * C, C, 1, 1, generator=g) / 8).to(cuda).requires_grad_(True)
+        conv_b = (torch.randn(K * C, generator=g) / 4).to(cuda).requires_grad_(True)
+        imp = (1 + 0.3 * torch.randn(K, V, V, generator=g)).to(cuda).requires_grad_(True)
+        x = torch.randn(N * T, V * C, generator=g).to(cuda).bfloat16().requires_grad_(True)
+        go = torch.randn(N * T, V * C, generator=g).to(cuda).bfloat16()
+
+        def run_ours():
+            y, sums = ops.graph_conv(x, conv_w, conv_b, A * imp, sp)
+            y.backward(go)
+            return y, sums
+        if defer:
+            with ops.overlap_weight_grads():
+                y, sums = run_ours()
+        else:
+            y, sums = run_ours()
+        torch.cuda.synchronize()
+        got = [y.detach().float(), x.grad.float(), conv_w.grad.clone(), conv_b.grad.clone(), imp.grad.clone()]
+        # reference formulation, fp32
+        cw, cb, im = [t.detach().clone().requires_grad_(True) for t in (conv_w, conv_b, imp)]
+        xr = x.detach().float().requires_grad_(True)
+        xin = xr.reshape(N, T, V, C).permute(0, 3, 1, 2)                            # (N, C, T, V)
+        h = torch.nn.functional.conv2d(xin, cw, cb).view(N, K, C, T, V)
+        ref = torch.einsum("nkctv,kvw->nctw", h, A * im).permute(0, 2, 3, 1).reshape(N * T, V * C)
+        ref.backward(go.float())
+        want = [ref.detach(), xr.grad, cw.grad, cb.grad, im.grad]
+        for name, a, b, tol in zip(["y", "dx", "dW", "db", "dImportance"], got, want, [1e-2, 1e-2, 1e-2, 1e-2, 1e-2]):
+            err, scale = (a - b).abs().max().item(), b.abs().max().item()
+            assert err <= tol * scale + 1e-4, (name, err, scale)
+        yd = y.detach().double().reshape(N * T * V, C)
+        assert torch.allclose(sums.sum(0)[0], yd.sum(0), rtol=1e-6, atol=1e-2)
+    finally:
+        gemm_sm100.uninstall()
