@@ -182,6 +182,13 @@ int p2r_gemm_bf16_ex(int M, int N, int K, const void* A, int lda, int a_mn, cons
                      int ldc, int c_dtype, const float* bias, int relu, int splits, int block_n, const int* kb_list,
                      int kb_stride, const unsigned char* tile_mask, double* stats, int stat_copies, void* stream);
 
+/* CTA-pair (tcgen05 cta_group::2, cluster of two CTAs on one TPC) variant for the large K-major GEMMs of the graph
+ * convolution: C[M,N] bf16 = A[M,K] . B[N,K]^T (+bias)(ReLU), one 256 x block_n tile per pair (block_n 128 / 256),
+ * each CTA staging only half of the B tile.  kb_list / stats as in p2r_gemm_bf16_ex, n-tiles of width block_n.       */
+int p2r_gemm_bf16_pair(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                       const float* bias, int relu, int block_n, const int* kb_list, int kb_stride, double* stats,
+                       int stat_copies, void* stream);
+
 /* (KT x 1) temporal convolution (zero padding (KT-1)/2) as an implicit tensor-core GEMM over the 3-D activation tensor
  * [B, rows = T*V, C], a tap shifting by V rows; no unfold buffer (ref: st_gcn_block.tcn conv, stgcn_layers.py:405-411).
  * mode 0: y = conv(x, W2[Co, KT*Ci]) (+bias); mode 1: dx from dy and Wt[KT*Co, Ci]; mode 2: dW2[Co, KT*Ci] (fp32,

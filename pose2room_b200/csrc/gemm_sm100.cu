@@ -401,6 +401,315 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
+// ================================================================================================ CTA-pair kernel
+// gemm2_bf16_kernel: the same GEMM on a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one MMA spans two SMs, M = 256
+// rows (128 per CTA), N = BN columns.  Each CTA stages its own 128 x 64 A tile and only HALF of the B tile
+// (BN/2 x 64), so a CTA reads (128 + BN/2) smem rows per k-block instead of (128 + BN): the single-CTA kernel above is
+// bound by shared-memory bandwidth (TMA writes + MMA operand reads), not by the tensor pipe.
+//   * both CTAs run a TMA producer; all transaction bytes land on the LEADER's full[] barrier (rank 0)
+//   * only the leader issues tcgen05.mma; tcgen05.commit ... multicast::cluster releases the stage in BOTH CTAs and
+//     finally signals tmem_full in both
+//   * each CTA's epilogue warps drain their own TMEM half (128 lanes x BN columns) into their own 128 rows of C
+// K-major A [M,K] and B [N,K], bf16 C, optional bias / ReLU / k-block lists / fused statistics; one tile per pair.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+  // executed by both CTAs of the pair; clearing the peer bit makes the bytes count on CTA 0's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          p2r_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(p2r_smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p2r_smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          p2r_smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {   // arrive on CTA 0's copy of `bar`
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(p2r_smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(p2r_smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BN>
+struct PairSmem {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BOX_ROWS = BN / 2;
+  static constexpr int B_BYTES = B_BOX_ROWS * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_BYTES = 4 * 32 * 128;                          // per epilogue warp: 32 rows x 64 bf16
+  static constexpr int BIAS_BYTES = 2 * BN * 4;                               // bias of the tile, double-buffered
+  static constexpr int MAX_STAGES = (232448 - 1024 - 256 - STAGING_BYTES - BIAS_BYTES) / STAGE_BYTES;   // 1 CTA per SM
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int ACC_COLS = 2 * BN;                                     // double-buffered accumulator
+  static constexpr int TMEM_COLS = ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 + 256;
+};
+
+// Persistent: one pair per TPC (grid = 2 x 74), each pair walks tiles pair_id, pair_id + npairs, ... (n fastest, so
+// the pairs working at the same time share the same rows of A in L2).  The smem ring runs across tile boundaries and
+// the accumulator is double-buffered in TMEM, so the epilogue of tile t overlaps the loads and MMAs of tile t + 1.
+template <int BN, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, const float* __restrict__ bias,
+                  int relu, int tiles_n, int num_tiles, const GemmExtra ex) {
+  using S = PairSmem<BN>;
+  const bool dbg_nostore = (relu & 256) != 0, dbg_nomma = (relu & 512) != 0, dbg_nobias = (relu & 1024) != 0;
+  relu &= 1;
+  if (dbg_nobias) bias = nullptr;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + S::STAGES * S::STAGE_BYTES;                       // 1024-byte aligned (stage sizes are)
+  float* sbias = reinterpret_cast<float*>(staging + S::STAGING_BYTES);        // [2][BN]
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tmem_full = empty + S::STAGES;    // [2]  signalled in both CTAs by the leader's commit
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]  used in the LEADER only: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      p2r_mbar_init(full + s, 1);
+      p2r_mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      p2r_mbar_init(tmem_full + a, 1);
+      p2r_mbar_init(tmem_empty + a, 8);
+    }
+    p2r_fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();           // barriers of both CTAs initialised, both TMEM halves allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // per-tile geometry (shared by the three roles)
+  auto tile_m0 = [&](int tile) { return (tile / tiles_n) * (2 * GEMM_BLOCK_M) + (int)rank * GEMM_BLOCK_M; };
+  auto tile_effn = [&](int n0) {            // MMA width of this tile: the ragged last n-tile issues a narrower MMA
+    const int rem = N - n0;
+    return rem >= BN ? BN : ((rem + 15) & ~15);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair0; tile < num_tiles; tile += npairs) {
+        const int n_tile = tile % tiles_n;
+        const int n0 = n_tile * BN, m0 = tile_m0(tile);
+        const int nb0 = n0 + (int)rank * (tile_effn(n0) / 2);             // this CTA's half of the B rows
+        const int* kbl = ex.kb_list != nullptr ? ex.kb_list + (size_t)n_tile * ex.kb_stride + 1 : nullptr;
+        const int nkb = kbl != nullptr ? __ldg(kbl - 1) : total_kb;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (uint32_t)(it / S::STAGES) & 1u;
+          p2r_mbar_wait(empty + s, ph ^ 1u);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          if (rank == 0) p2r_mbar_expect_tx(full + s, 2 * S::STAGE_BYTES);   // the bytes of both CTAs
+          const int k0 = (kbl != nullptr ? __ldg(kbl + i) : i) * GEMM_BLOCK_K;
+          tma_load_2d_pair(a_dst, &tma_a, full + s, k0, m0);                 // box {64 k, 128 m}
+          tma_load_2d_pair(b_dst, &tma_b, full + s, k0, nb0);                // box {64 k, BN/2 n}
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      int it = 0, t = 0;
+      for (int tile = pair0; tile < num_tiles; tile += npairs, ++t) {
+        const int n_tile = tile % tiles_n;
+        const int nkb = ex.kb_list != nullptr ? __ldg(ex.kb_list + (size_t)n_tile * ex.kb_stride) : total_kb;
+        const uint32_t idesc = make_idesc(2 * GEMM_BLOCK_M, tile_effn(n_tile * BN), 0, 0);
+        const int as = t & 1;
+        if (t >= 2) {   // both CTAs' epilogues must have drained this accumulator buffer
+          p2r_mbar_wait(tmem_empty + as, (uint32_t)((t >> 1) - 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (uint32_t)(it / S::STAGES) & 1u;
+          p2r_mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = p2r_smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + S::A_BYTES;
+          if (!dbg_nomma) {
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+              umma_bf16_pair(tmem_acc, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                             (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(empty + s);      // stage reusable in both CTAs once these MMAs have read it
+        }
+        umma_commit_pair(tmem_full + as);   // accumulator of tile t complete in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    // TMEM -> registers (32 columns at a time) -> bias / ReLU / bf16 -> this warp's 32 x 64 staging tile in shared
+    // memory (128-byte swizzle: conflict-free 16-byte writes) -> ONE bulk-tensor store per 64 columns.  Direct
+    // st.global from this register layout (a lane = a row) writes 16-byte pieces 32 rows apart and was the bound of
+    // the whole kernel; the TMA store writes full 128-byte lines and costs the warp one instruction.
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;            // 0..127 over the epilogue warps
+    uint8_t* stg = staging + q * (32 * 128);
+    float st00 = 0.f, st01 = 0.f, st10 = 0.f, st11 = 0.f;   // sum / sum of squares of channels 2 lane, 2 lane + 1
+    int t = 0;
+    for (int tile = pair0; tile < num_tiles; tile += npairs, ++t) {
+      const int n_tile = tile % tiles_n;
+      const int n0 = n_tile * BN;
+      const int nkb = ex.kb_list != nullptr ? __ldg(ex.kb_list + (size_t)n_tile * ex.kb_stride) : total_kb;
+      const int as = t & 1;
+      const int row0 = tile_m0(tile) + q * 32;
+      const int ncols = min(BN, N - n0);
+      float* sb = sbias + as * BN;
+      for (int c = et; c < BN; c += 128) sb[c] = (bias != nullptr && n0 + c < N) ? __ldg(bias + n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // bias of this tile visible to the four epilogue warps
+      p2r_mbar_wait(tmem_full + as, (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g0 = 0; g0 < ncols; g0 += 64) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = g0 + 32 * h;
+          const int col0 = n0 + c0;
+          float f[32];
+          if (c0 < ncols) {   // (warp-uniform)
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+            if (c0 + 32 >= ncols) {   // last read of this accumulator buffer: hand it back to the leader's MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_on_leader(tmem_empty + as);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = (nkb > 0 ? __uint_as_float(v[j]) : 0.f) + sb[c0 + j];
+              if (relu) x = fmaxf(x, 0.f);
+              f[j] = __bfloat162float(__float2bfloat16_rn(x));   // the value as stored
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          if (h == 0) {   // the previous bulk store must have finished reading the staging tile
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * p + 0], f[8 * p + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * p + 2], f[8 * p + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * p + 4], f[8 * p + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * p + 6], f[8 * p + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            const int piece = (4 * h + p) ^ (lane & 7);          // SWIZZLE_128B: 16-byte chunk index ^ (row & 7)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + piece * 16) = pk;
+          }
+        }
+        p2r_fence_proxy_async();      // generic-proxy writes of the staging tile -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0 && !dbg_nostore) tma_store_2d(&tma_c, stg, n0 + g0, row0);   // rows >= M / columns >= N are clipped
+        if (STATS) {
+          // column sums straight from the staged bf16 tile: lane l owns columns 2l, 2l+1 of this 64-column group
+          // (= channels 2l, 2l+1: n0 + g0 is a multiple of 64); one conflict-free 4-byte read per row
+          const int rows_valid = min(32, M - row0);
+#pragma unroll 8
+          for (int r = 0; r < rows_valid; ++r) {
+            const uint32_t wd = *reinterpret_cast<const uint32_t*>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+            const float lo = __uint_as_float(wd << 16), hi = __uint_as_float(wd & 0xffff0000u);
+            st00 += lo;
+            st01 = fmaf(lo, lo, st01);
+            st10 += hi;
+            st11 = fmaf(hi, hi, st11);
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+    tc_fence_before();
+    if (STATS) {
+      float* red = reinterpret_cast<float*>(smem);   // the ring is idle: every MMA of this pair has completed
+      red[(q * 4 + 0) * 32 + lane] = st00;
+      red[(q * 4 + 1) * 32 + lane] = st01;
+      red[(q * 4 + 2) * 32 + lane] = st10;
+      red[(q * 4 + 3) * 32 + lane] = st11;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int k = q;
+      const float tot = red[(0 * 4 + k) * 32 + lane] + red[(1 * 4 + k) * 32 + lane] + red[(2 * 4 + k) * 32 + lane] +
+                        red[(3 * 4 + k) * 32 + lane];
+      const int copy = (int)(blockIdx.x % (unsigned)ex.stat_copies);
+      // accumulator k: 0 = sum of channel 2l, 1 = its sum of squares, 2 / 3 = the same for channel 2l + 1
+      atomicAdd(ex.stats + ((size_t)copy * 2 + (k & 1)) * 64 + 2 * lane + (k >> 1), (double)tot);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();            // neither CTA leaves (or frees TMEM) while the other may still use the pair's state
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, S::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -598,4 +907,47 @@ extern "C" int p2r_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_
                              void* stream) {
   return p2r_gemm_bf16_ex(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, c_dtype, bias, relu, splits, block_n, nullptr, 0,
                           nullptr, nullptr, 1, stream);
+}
+
+template <int BN>
+static int launch_pair(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                       const float* bias, int relu, const GemmExtra& ex, cudaStream_t st) {
+  using S = PairSmem<BN>;
+  CUtensorMap ma, mb;
+  CUtensorMap mc;
+  if (make_map(&ma, A, K, M, lda, GEMM_BLOCK_M)) return -1;
+  if (make_map(&mb, B, K, N, ldb, BN / 2)) return -1;
+  if (make_map(&mc, C, N, M, ldc, 32)) return -1;                        // store box {64 columns, 32 rows}
+  const int tiles_n = p2r_ceil_div(N, BN), pairs_m = p2r_ceil_div(M, 2 * GEMM_BLOCK_M);
+  const int num_tiles = tiles_n * pairs_m;
+  const unsigned grid = 2u * (unsigned)(num_tiles < P2R_SM_COUNT / 2 ? num_tiles : P2R_SM_COUNT / 2);   // one pair per TPC
+  if (ex.stats != nullptr) {
+    auto kern = gemm2_bf16_kernel<BN, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, mc, M, N, K, bias, relu, tiles_n, num_tiles, ex);
+  } else {
+    auto kern = gemm2_bf16_kernel<BN, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, mc, M, N, K, bias, relu, tiles_n, num_tiles, ex);
+  }
+  P2R_RETURN_LAUNCH("p2r_gemm_bf16_pair");
+}
+
+
+// CTA-pair (cta_group::2) variant for the large K-major GEMMs of the graph convolution: C[M,N] bf16 = A[M,K] . B[N,K]^T
+// (+bias)(ReLU), 256 x block_n tile per pair, block_n in {128, 256}; kb_list / stats as in p2r_gemm_bf16_ex
+// (kb_list indexed by n-tiles of width block_n).
+extern "C" int p2r_gemm_bf16_pair(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                                  const float* bias, int relu, int block_n, const int* kb_list, int kb_stride,
+                                  double* stats, int stat_copies, void* stream) {
+  P2R_CHECK_ARG(M > 0 && N > 0 && K > 0, "p2r_gemm_bf16_pair");
+  P2R_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0,
+                "p2r_gemm_bf16_pair (row pitches must be multiples of 8 bf16 = 16 bytes)");
+  P2R_CHECK_ARG(block_n == 128 || block_n == 256, "p2r_gemm_bf16_pair block_n (a multiple of the 64-column store box)");
+  P2R_CHECK_ARG(kb_list == nullptr || kb_stride >= 1, "p2r_gemm_bf16_pair kb_stride");
+  P2R_CHECK_ARG(stats == nullptr || (stat_copies >= 1 && N % 64 == 0), "p2r_gemm_bf16_pair stats");
+  const GemmExtra ex = {kb_list, kb_stride, nullptr, stats, stat_copies < 1 ? 1 : stat_copies};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_n == 128) return launch_pair<128>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu, ex, st);
+  return launch_pair<256>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu, ex, st);
 }

@@ -10,9 +10,12 @@ import torch
 from . import _lib, ops
 
 # tiling of the block-sparse graph-convolution GEMMs (forward / input gradient) and number of partial-statistics copies
-GCN_BLOCK_N = int(os.environ.get("P2R_GCN_BLOCK_N", "160"))
+GCN_BLOCK_N = int(os.environ.get("P2R_GCN_BLOCK_N", "128"))
 STAT_COPIES = int(os.environ.get("P2R_STAT_COPIES", "16"))
 USE_SPARSITY = os.environ.get("P2R_GCN_SPARSE", "1") != "0"
+# graph-conv forward / input-gradient GEMMs on CTA pairs (persistent cta_group::2 kernel, 256 x PAIR_BLOCK_N tiles)
+USE_PAIR = os.environ.get("P2R_GCN_PAIR", "1") != "0"
+PAIR_BLOCK_N = int(os.environ.get("P2R_GCN_PAIR_BLOCK_N", "256"))
 USE_FUSED_STATS = os.environ.get("P2R_FUSED_STATS", "1") != "0"
 
 
@@ -117,6 +120,29 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bf
     return c
 
 
+def gemm_pair(a, b, bias=None, relu=False, block_n=256, kb_list=None, stats=None, _debug_flags=0):
+    """C[M,N] bf16 = a[M,K] @ b[N,K]^T on CTA pairs (p2r_gemm_bf16_pair): K-major bf16 operands, 256 x block_n tiles."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+    assert a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]
+    m, k = a.shape
+    n = b.shape[0]
+    c = torch.empty(m, n, dtype=torch.bfloat16, device=a.device)
+    if bias is not None:
+        bias = bias.float().contiguous()
+    if kb_list is not None:
+        assert kb_list.dtype == torch.int32 and kb_list.is_contiguous() and kb_list.shape[0] == -(-n // block_n)
+    if stats is not None:
+        assert stats.dtype == torch.float64 and stats.is_contiguous() and tuple(stats.shape[1:]) == (2, 64)
+    with torch.cuda.device(a.device):
+        _lib.call("p2r_gemm_bf16_pair", m, n, k, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), c.data_ptr(),
+                  c.stride(0), bias.data_ptr() if bias is not None else None, int(relu) | int(_debug_flags), int(block_n),
+                  kb_list.data_ptr() if kb_list is not None else None,
+                  int(kb_list.shape[1]) if kb_list is not None else 0,
+                  stats.data_ptr() if stats is not None else None, int(stats.shape[0]) if stats is not None else 1,
+                  _stream())
+    return c
+
+
 class _TemporalConvTC(torch.autograd.Function):
     """(KT x 1) temporal conv of st_gcn_block.tcn as implicit tensor-core GEMMs (forward, d input, d weight):
     three row-shifted TMA views of the SAME activation tensor instead of an unfold buffer."""
@@ -211,6 +237,10 @@ class _Backend:
         sp = sparsity if USE_SPARSITY else None
         if sp is None and sums is None:
             return _Backend.linear_fwd(x, weight, bias, relu), None
+        if USE_PAIR and x.shape[0] >= 4096 and n >= 512 and n % 64 == 0:
+            kbl = sp.kb_list(PAIR_BLOCK_N, False, x.device) if sp is not None else None
+            y = gemm_pair(x, weight.to(torch.bfloat16), bias, relu, block_n=PAIR_BLOCK_N, kb_list=kbl, stats=sums)
+            return y, sums
         bn = GCN_BLOCK_N if (n % 160 == 0 or GCN_BLOCK_N != 160) else (64 if n <= 64 else 128)
         kbl = sp.kb_list(bn, False, x.device) if sp is not None else None
         y = gemm(x, weight.to(torch.bfloat16), False, False, bias, relu, out_dtype=torch.bfloat16, block_n=bn,
@@ -234,6 +264,9 @@ class _Backend:
     def linear_dx_pretransposed(dz, w_t, sparsity=None):
         """dx = dz . W with W^T [K, N] already materialised in bf16 (the graph-conv weight builder writes both)."""
         sp = sparsity if USE_SPARSITY else None
+        if USE_PAIR and dz.shape[0] >= 4096 and w_t.shape[0] >= 512:
+            kbl = sp.kb_list(PAIR_BLOCK_N, True, dz.device) if sp is not None else None
+            return gemm_pair(dz, w_t, block_n=PAIR_BLOCK_N, kb_list=kbl)
         bn = GCN_BLOCK_N if (w_t.shape[0] % 160 == 0 or GCN_BLOCK_N != 160) else 128
         kbl = sp.kb_list(bn, True, dz.device) if sp is not None else None
         return gemm(dz, w_t, False, False, out_dtype=torch.bfloat16, block_n=bn, kb_list=kbl)

@@ -304,3 +304,35 @@ def test_graph_conv_op_matches_einsum_formulation(cuda, defer):
         assert torch.allclose(sums.sum(0)[0], yd.sum(0), rtol=1e-6, atol=1e-2)
     finally:
         gemm_sm100.uninstall()
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_cta_pair_kernel(cuda, bn):
+    """The cta_group::2 kernel (one MMA across two SMs): exact on integer operands, ragged M / N, bias + ReLU, block-
+    sparse k-lists and fused statistics."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100
+    g = torch.Generator().manual_seed(30 + bn)
+    # the last two shapes give every pair several tiles: the ring and the double-buffered accumulator wrap around
+    for (M, N, K) in [(256, bn, 64), (512, 640, 256), (300, 320, 192), (1024, 1600, 1600), (8192, 640, 128),
+                      (16384 + 100, 1600, 192)]:
+        a = torch.randint(-3, 4, (M, K), generator=g).float()
+        b = torch.randint(-3, 4, (N, K), generator=g).float()
+        bias = torch.randint(-5, 6, (N,), generator=g).float()
+        c = gemm_sm100.gemm_pair(a.to(cuda).bfloat16(), b.to(cuda).bfloat16(), bias=bias.to(cuda), relu=True, block_n=bn)
+        ref = torch.relu(a @ b.t() + bias)
+        assert torch.equal(c.float().cpu(), ref.bfloat16().float()), (M, N, K)
+    # block-sparse reduction + statistics on random data
+    M, NB, KB = 768, 10, 10
+    nz = _random_block_pattern(NB, KB, g)
+    sp = gemm_sm100.BlockSparsity(nz)
+    w = torch.randn(NB * 64, KB * 64, generator=g) / 20
+    w *= torch.from_numpy(np.kron(nz, np.ones((64, 64), dtype=np.float32)))
+    x = torch.randn(M, KB * 64, generator=g)
+    xb, wb = x.to(cuda).bfloat16(), w.to(cuda).bfloat16()
+    stats = torch.zeros(4, 2, 64, dtype=torch.float64, device=cuda)
+    c = gemm_sm100.gemm_pair(xb, wb, block_n=bn, kb_list=sp.kb_list(bn, False, cuda), stats=stats)
+    _check(c, xb.float() @ wb.float().t(), tol=1e-2)
+    cd = c.double().reshape(M, NB, 64)
+    assert torch.allclose(stats.sum(0)[0], cd.sum((0, 1)), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(stats.sum(0)[1], (cd * cd).sum((0, 1)), rtol=1e-5, atol=1e-2)

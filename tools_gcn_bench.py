@@ -28,6 +28,12 @@ def main():
         st = torch.zeros(16, 2, 64, dtype=torch.float64, device=dev)
         rec["sparse_stats_bn%d_ms" % bn] = timeit(lambda: gemm_sm100.gemm(x, w, bias=bias, block_n=bn, kb_list=kbl, stats=st))
         rec["dense_stats_bn%d_ms" % bn] = timeit(lambda: gemm_sm100.gemm(x, w, bias=bias, block_n=bn, stats=st))
+    for bn in (128, 256):
+        kbl = sp.kb_list(bn, False, dev)
+        st = torch.zeros(16, 2, 64, dtype=torch.float64, device=dev)
+        rec["pair_dense_bn%d_ms" % bn] = timeit(lambda: gemm_sm100.gemm_pair(x, w, bias=bias, block_n=bn))
+        rec["pair_sparse_bn%d_ms" % bn] = timeit(lambda: gemm_sm100.gemm_pair(x, w, bias=bias, block_n=bn, kb_list=kbl))
+        rec["pair_sparse_stats_bn%d_ms" % bn] = timeit(lambda: gemm_sm100.gemm_pair(x, w, bias=bias, block_n=bn, kb_list=kbl, stats=st))
     rec["dw_dense_ms"] = timeit(lambda: gemm_sm100.gemm(dy, x, True, True, out_dtype=torch.float32, block_n=128))
     mask = sp.tile_mask(128, 128, dev)
     rec["dw_masked_ms"] = timeit(lambda: gemm_sm100.gemm(dy, x, True, True, out_dtype=torch.float32, block_n=128, tile_mask=mask))
