@@ -21,6 +21,7 @@
 // the other's main loop.
 #include "p2r_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 #define GEMM_BLOCK_M 128
 #define GEMM_BLOCK_K 64
@@ -149,7 +150,17 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   return v[0];
 }
 
-template <int BLOCK_N, int STAGES_OVERRIDE = 0>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(p2r_smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BLOCK_N, int STAGES_OVERRIDE = 0, bool TS = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
@@ -158,20 +169,29 @@ struct GemmSmem {
   static constexpr int ACC_STAGES = BLOCK_N <= 128 ? 2 : 1;   // double-buffered accumulator when 2 x 2 CTAs fit in TMEM
   static constexpr int ACC_COLS = ACC_STAGES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // TS (TMA-store epilogue): a 32 x 64 bf16 staging tile per epilogue warp + the tile's bias, double-buffered
+  static constexpr int STAGING_BYTES = TS ? 4 * 32 * 128 : 0;
+  static constexpr int BIAS_BYTES = TS ? 2 * BLOCK_N * 4 : 0;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP = 0, int NSTAGE = 0, bool STATS = false>
+// TS = true: the epilogue stages bf16 tiles in shared memory and writes them with bulk-tensor (TMA) stores through
+// tma_c (box {64 columns, 32 rows}); see the CTA-pair kernel below for why.  Needs bf16 C, BLOCK_N % 64 == 0.
+template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP = 0, int NSTAGE = 0, bool STATS = false,
+          bool TS = false>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_c,
                  OutT* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ bias, int relu,
                  int kblocks_per_split, const TapArgs tap, int tiles_per_cta, const GemmExtra ex) {
-  using S = GemmSmem<BLOCK_N, NSTAGE>;
+  using S = GemmSmem<BLOCK_N, NSTAGE, TS>;
   if (ex.tile_mask != nullptr && ex.tile_mask[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // whole CTA, uniform
   constexpr int ACC = S::ACC_STAGES;   // accumulator buffers in TMEM (2: the epilogue of tile t overlaps the MMAs of t+1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint8_t* staging = smem + S::STAGES * S::STAGE_BYTES;                      // (TS) 1024-byte aligned
+  float* sbias = reinterpret_cast<float*>(staging + S::STAGING_BYTES);       // (TS) [2][BLOCK_N]
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
   uint64_t* empty = full + S::STAGES;
   uint64_t* tmem_full = empty + S::STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
@@ -202,6 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (TS) tma_prefetch_desc(&tma_c);
   }
   if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
   tc_fence_before();
@@ -291,6 +312,97 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const bool vec_ok = ((size_t)ldc * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
     constexpr bool do_stats = STATS && !ATOMIC;   // (a template flag: the extra registers stay out of the plain kernels)
+    if (TS) {
+      // ---- TMA-store epilogue: TMEM -> registers -> bias / ReLU / bf16 -> swizzled 32 x 64 staging tile -> bulk store
+      const int et = threadIdx.x - 64;
+      uint8_t* stg = staging + q * (32 * 128);
+      float ts00 = 0.f, ts01 = 0.f, ts10 = 0.f, ts11 = 0.f;   // sum / sum of squares of channels 2 lane, 2 lane + 1
+      for (int t = 0; t < ntiles; ++t) {
+        const int as = t % ACC;
+        const int row0 = (tile0 + t) * GEMM_BLOCK_M + q * 32;
+        const int ncols = min(BLOCK_N, N - n0);
+        float* sb = sbias + as * BLOCK_N;
+        for (int c = et; c < BLOCK_N; c += 128) sb[c] = (bias != nullptr && n0 + c < N) ? __ldg(bias + n0 + c) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        p2r_mbar_wait(tmem_full + as, (uint32_t)(t / ACC) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int g0 = 0; g0 < ncols; g0 += 64) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = g0 + 32 * h;
+            float f[32];
+            if (c0 < ncols) {   // (warp-uniform)
+              uint32_t v[32];
+              tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
+              if (c0 + 32 >= ncols) {   // last read of this accumulator buffer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) p2r_mbar_arrive(tmem_empty + as);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = (nkb > 0 ? __uint_as_float(v[j]) : 0.f) + sb[c0 + j];
+                if (relu) x = fmaxf(x, 0.f);
+                f[j] = x;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
+            if (h == 0) {   // the previous bulk store must have finished reading the staging tile
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * p + 0], f[8 * p + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * p + 2], f[8 * p + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * p + 4], f[8 * p + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * p + 6], f[8 * p + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0);
+              pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2);
+              pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              const int piece = (4 * h + p) ^ (lane & 7);          // SWIZZLE_128B
+              *reinterpret_cast<uint4*>(stg + lane * 128 + piece * 16) = pk;
+            }
+          }
+          p2r_fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tma_c, stg, n0 + g0, row0);   // rows >= M / columns >= N are clipped
+          if (do_stats) {
+            const int rows_valid = min(32, M - row0);
+#pragma unroll 8
+            for (int r = 0; r < rows_valid; ++r) {
+              const uint32_t wd = *reinterpret_cast<const uint32_t*>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+              const float lo = __uint_as_float(wd << 16), hi = __uint_as_float(wd & 0xffff0000u);
+              ts00 += lo;
+              ts01 = fmaf(lo, lo, ts01);
+              ts10 += hi;
+              ts11 = fmaf(hi, hi, ts11);
+            }
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+      tc_fence_before();
+      if (do_stats) {
+        float* red = reinterpret_cast<float*>(smem);   // the ring is idle: every MMA of this CTA has completed
+        red[(q * 4 + 0) * 32 + lane] = ts00;
+        red[(q * 4 + 1) * 32 + lane] = ts01;
+        red[(q * 4 + 2) * 32 + lane] = ts10;
+        red[(q * 4 + 3) * 32 + lane] = ts11;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int k = q;
+        const float tot = red[(0 * 4 + k) * 32 + lane] + red[(1 * 4 + k) * 32 + lane] + red[(2 * 4 + k) * 32 + lane] +
+                          red[(3 * 4 + k) * 32 + lane];
+        const int copy = (int)((blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)ex.stat_copies);
+        atomicAdd(ex.stats + ((size_t)copy * 2 + (k & 1)) * 64 + 2 * lane + (k >> 1), (double)tot);
+      }
+    } else {
     // statistics accumulators: st[h][r] belongs to channel 32 h + 16 r + (lane & 15); lanes < 16 hold the sum, lanes
     // >= 16 the sum of squares
     float st00 = 0.f, st01 = 0.f, st10 = 0.f, st11 = 0.f;
@@ -393,6 +505,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       atomicAdd(ex.stats + ((size_t)copy * 2 + (lane >> 4)) * 64 + k * 16 + (lane & 15), (double)tot);
     }
     tc_fence_before();
+    }   // !TS
   }
   __syncthreads();
   if (warp == 1) {
@@ -461,16 +574,6 @@ __device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {   // arri
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(p2r_smem_u32(bar)), "r"(0));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(p2r_smem_u32(src)), "r"(c0), "r"(c1)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int BN>
 struct PairSmem {
@@ -626,7 +729,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = g0 + 32 * h;
-          const int col0 = n0 + c0;
           float f[32];
           if (c0 < ncols) {   // (warp-uniform)
             uint32_t v[32];
@@ -762,43 +864,64 @@ static int make_map3(CUtensorMap* map, const void* ptr, long long C, long long r
   return 0;
 }
 
+static bool ts_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("P2R_TMA_STORE");
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int TAP, int NSTAGE>
 static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* C, int ldc, int c_dtype, int M, int N,
                             int K, const float* bias, int relu, int splits, const TapArgs& tap, cudaStream_t st,
                             const GemmExtra& ex = GemmExtra{nullptr, 0, nullptr, nullptr, 1}) {
-  using S = GemmSmem<BLOCK_N, NSTAGE>;
   const int total_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   int kps = total_kb;
   if (splits > 1) {
     kps = (total_kb + splits - 1) / splits;
     splits = (total_kb + kps - 1) / kps;
   } else splits = 1;
+  // TMA-store epilogue for bf16 outputs of the 64- and 256-wide tilings (the memory-bound point-MLP / temporal-conv
+  // GEMMs; with 128 / 160 columns the extra staging memory would cost the second co-resident CTA)
+  constexpr bool TS_OK = (BLOCK_N == 64 || BLOCK_N == 256) && TAP != 2;
+  const bool ts = TS_OK && c_dtype == 1 && splits == 1 && ex.tile_mask == nullptr && ldc % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(C) % 16) == 0 && ts_enabled();
+  CUtensorMap mc = ma;
+  if (ts && make_map(&mc, C, N, M, ldc, 32)) return -1;
   // several m-tiles per CTA when there are many more tiles than CTA slots: barrier / TMEM set-up is amortised and the
   // next tile's TMA loads and MMAs run under the current tile's epilogue (double-buffered accumulator)
   const long long tiles_m = p2r_ceil_div(M, GEMM_BLOCK_M), tiles_n = p2r_ceil_div(N, BLOCK_N);
   int tpc = 1;
-  if (splits == 1 && S::ACC_STAGES == 2 && ex.tile_mask == nullptr) {
+  if (splits == 1 && GemmSmem<BLOCK_N, NSTAGE>::ACC_STAGES == 2 && ex.tile_mask == nullptr) {
     const long long slots = (long long)P2R_SM_COUNT * 8;
     tpc = (int)((tiles_m * tiles_n) / slots);
     if (tpc < 1) tpc = 1;
     if (tpc > 8) tpc = 8;
   }
   dim3 grid((unsigned)tiles_n, (unsigned)p2r_ceil_div(tiles_m, tpc), splits);
-#define GEMM_GO(OutT, ATOMIC, STATS)                                                                            \
+#define GEMM_GO(OutT, ATOMIC, STATS, TS)                                                                        \
   do {                                                                                                          \
-    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE, STATS>;                        \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);                          \
-    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc, ex);  \
+    using SS = GemmSmem<BLOCK_N, NSTAGE, TS>;                                                                   \
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE, STATS, TS>;                    \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::TOTAL);                         \
+    kern<<<grid, GEMM_THREADS, SS::TOTAL, st>>>(ma, mb, mc, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc, ex); \
   } while (0)
   if (ex.stats != nullptr) {
     if (A_MN || B_MN || TAP == 2 || splits > 1 || c_dtype != 1) {
       p2r_set_last_error("p2r_gemm_bf16_ex: fused statistics need K-major operands, bf16 output, no split-K", -1);
       return -1;
     }
-    if (!A_MN && !B_MN && TAP != 2) GEMM_GO(__nv_bfloat16, false, true);
-  } else if (splits > 1) GEMM_GO(float, true, false);
-  else if (c_dtype == 1) GEMM_GO(__nv_bfloat16, false, false);
-  else GEMM_GO(float, false, false);
+    if (!A_MN && !B_MN && TAP != 2) {
+      if (TS_OK && ts) GEMM_GO(__nv_bfloat16, false, true, TS_OK);
+      else GEMM_GO(__nv_bfloat16, false, true, false);
+    }
+  } else if (splits > 1) GEMM_GO(float, true, false, false);
+  else if (c_dtype == 1) {
+    if (TS_OK && ts) GEMM_GO(__nv_bfloat16, false, false, TS_OK);
+    else GEMM_GO(__nv_bfloat16, false, false, false);
+  } else GEMM_GO(float, false, false, false);
 #undef GEMM_GO
   P2R_RETURN_LAUNCH("p2r_gemm_bf16");
 }
