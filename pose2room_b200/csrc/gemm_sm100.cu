@@ -979,6 +979,9 @@ extern "C" int p2r_tconv_bf16(int mode, const void* act, const void* w, const vo
   if (make_map(&ma, other, Co, M, Co, GEMM_BLOCK_K)) return -1;          // dy as MN-major A: inner = Co, rows = m
   if (make_map3(&mb, act, Ci, rows, B, GEMM_BLOCK_K)) return -1;         // x as MN-major B, 3-D
   const TapArgs tap = {1, rows, Ci, -pad * V, V};
+  // KT = 3: ONE 192-column tile holds all three taps, so dy is streamed once (not once per tap) and a split is a single
+  // CTA: 32 KB instead of 48 KB through L2 -> SM per 64 reduction rows
+  if (KT == 3) return launch_with_maps<192, true, true, 2, 4>(ma, mb, out, KT * Ci, 0, Co, KT * Ci, M, nullptr, 0, splits, tap, st);
   return launch_with_maps<64, true, true, 2, 0>(ma, mb, out, KT * Ci, 0, Co, KT * Ci, M, nullptr, 0, splits, tap, st);
 }
 

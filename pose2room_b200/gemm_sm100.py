@@ -196,7 +196,7 @@ class _TemporalConvTC(torch.autograd.Function):
                         m = b * t * v
                         dw2 = torch.zeros(co, kt * ci, dtype=torch.float32, device=x.device)
                         _lib.call("p2r_tconv_bf16", 2, x.data_ptr(), None, dy.data_ptr(), dw2.data_ptr(), b, t * v, ci, co,
-                                  kt, v, None, max(1, min(128, m // 8192)), None, 1, _stream())
+                                  kt, v, None, max(1, min(148, m // 4096)), None, 1, _stream())
                         gw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
                     if need_b:
                         gb = ops._col_sum(dy)
@@ -205,7 +205,7 @@ class _TemporalConvTC(torch.autograd.Function):
                 return dx, None, None, None, None
             if ctx.needs_input_grad[1]:
                 m = b * t * v
-                splits = max(1, min(128, m // 8192))
+                splits = max(1, min(148, m // 4096))
                 dw2 = torch.zeros(co, kt * ci, dtype=torch.float32, device=x.device)
                 _lib.call("p2r_tconv_bf16", 2, x.data_ptr(), None, dy.data_ptr(), dw2.data_ptr(), b, t * v, ci, co, kt, v,
                           None, splits, None, 1, _stream())
@@ -215,16 +215,40 @@ class _TemporalConvTC(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _pad_rows(t, rows):
+    """[n, k] -> [rows, k] with zero rows appended (odd output widths: 259-channel vote head, 100 mixture weights)."""
+    out = torch.zeros(rows, t.shape[1], dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
+
+
+def _pad_cols(t, cols):
+    out = torch.zeros(t.shape[0], cols, dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out
+
+
 class _Backend:
     """Interface expected by ops._Linear (see ops._TC_GEMM)."""
 
     @staticmethod
     def supports(m, n, k):
-        # TMA needs 16-byte row pitches for every operand in every role (x:[M,K], w:[N,K], dy:[M,N])
-        return k % 8 == 0 and n % 8 == 0 and k >= 32 and m >= 128
+        # TMA needs 16-byte row pitches for every operand in every role (x:[M,K], w:[N,K], dy:[M,N]); an output width
+        # that is not a multiple of 8 is zero-padded to the next one (the extra columns are sliced off again)
+        return k % 8 == 0 and k >= 32 and m >= 128 and n >= 8
 
     @staticmethod
     def linear_fwd(x, weight, bias, relu):
+        n = weight.shape[0]
+        if n % 8:
+            n8 = _pad8(n)
+            w8 = _pad_rows(weight.to(torch.bfloat16), n8)
+            b8 = torch.cat([bias.float(), bias.new_zeros(n8 - n, dtype=torch.float32)]) if bias is not None else None
+            return gemm(x, w8, False, False, b8, relu, out_dtype=torch.bfloat16)[:, :n].contiguous()
         return gemm(x, weight.to(torch.bfloat16), False, False, bias, relu, out_dtype=torch.bfloat16)
 
     @staticmethod
@@ -251,6 +275,9 @@ class _Backend:
     def linear_dx(dz, weight, sparsity=None):
         # dx[M,K] = dz[M,N] . W[N,K]:  A = dz (K-major over n), B = W viewed as [K_red = N, N_out = K] -> MN-major
         w = weight.to(torch.bfloat16)
+        if w.shape[0] % 8:      # odd layer width: zero-pad the reduction dimension of both operands
+            n8 = _pad8(w.shape[0])
+            dz, w = _pad_cols(dz, n8), _pad_rows(w, n8)
         n_out = w.shape[1]
         sp = sparsity if USE_SPARSITY else None
         if (n_out % 160 == 0 and n_out >= 640) or sp is not None:
@@ -274,6 +301,9 @@ class _Backend:
     @staticmethod
     def linear_dw(dz, x, sparsity=None):
         # dW[N,K] = dz^T[N,M] . x[M,K]: both operands MN-major (reduction over the row index m)
+        if dz.shape[1] % 8:     # odd layer width: pad the columns of dz, drop the extra rows of dW
+            n_true = dz.shape[1]
+            return _Backend.linear_dw(_pad_cols(dz, _pad8(n_true)), x, sparsity)[:n_true]
         m = dz.shape[0]
         n, k = dz.shape[1], x.shape[1]
         tiles = ((n + 127) // 128) * ((k + 127) // 128)

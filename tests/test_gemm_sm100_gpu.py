@@ -71,7 +71,8 @@ def test_linear_autograd_bf16_backend(cuda):
     gemm_sm100.install()
     try:
         g = torch.Generator().manual_seed(2)
-        for (M, K, N) in [(2048, 1600, 1600), (8192, 64, 64), (4096, 192, 64), (1024, 256, 256)]:
+        for (M, K, N) in [(2048, 1600, 1600), (8192, 64, 64), (4096, 192, 64), (1024, 256, 256), (4096, 256, 259),
+                          (4096, 128, 100)]:   # the last two: odd widths, zero-padded to a multiple of 8
             x = torch.randn(M, K, generator=g).to(cuda).bfloat16().requires_grad_(True)
             w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda).requires_grad_(True)
             b = torch.randn(N, generator=g).to(cuda).requires_grad_(True)
