@@ -24,6 +24,11 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 B_PER_GPU, T_FRAMES, JOINTS = 32, 1024, 25
+# DRAM bytes of ONE launch of the dominant kernel (graph-conv forward GEMM, block-sparse, fused statistics) from the
+# ncu --set full capture of this round: dram__bytes_read.sum 109.0 MB + dram__bytes_write.sum 67.5 MB
+# (profiles/r01_ncu_kernels_summary.txt; algorithmic bytes: X 104.9 MB + W_eff 5.1 MB + Y 104.9 MB -- part of Y is still
+# in the 126 MB L2 when the kernel ends)
+GCN_FWD_DRAM_BYTES_NCU = 109.048e6 + 67.502e6
 # algorithmic (conv 64->704 + einsum, the reference's formulation) forward FLOPs of ONE graph convolution for ONE
 # sequence at T=1024, J=25: (13.84 + 5.41) GFLOP / 6 blocks  (SURVEY.md section 8d / BASELINE.md section 3)
 GCN_ALGO_GFLOP_PER_SEQ = (13.84 + 5.41) / 6.0
@@ -321,20 +326,42 @@ def main():
         achieved = algo_flops / (t_ms * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "graph-conv GEMM fwd (M=%d,N=K=%d) %s" % (gcn[0][1], vj, precision),
+                    "traffic": GCN_FWD_DRAM_BYTES_NCU if (precision == "bf16" and B == B_PER_GPU) else None,
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_kernels_summary.txt)",
+                    "kernel": "graph-conv GEMM fwd (M=%d,N=K=%d) %s, CTA-pair tcgen05, block-sparse K, fused BN statistics" % (gcn[0][1], vj, precision),
                     "avg_launch_ms": t_ms, "launches_timed": len(gcn), "executed_tflops": exec_flops / (t_ms * 1e-3) / 1e12,
                     "peak_source": peaks["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
                     "share_of_step": t_ms * 6 / (ms / args.steps)}
     ops.PROFILE["log"] = []
 
     # ---- end to end: pinned host batch -> H2D -> step -> loss read back --------------------------------
-    for _ in range(2):
-        step(tensors).item()          # pinned host tensors -> H2D into the step's input buffers -> step -> loss D2H
+    # Every step's batch is copied from pinned host memory inside the timed region and every step's loss is read back
+    # (.item()).  Like a prefetching input pipeline (the reference's DataLoader uses pin_memory + workers,
+    # dataloader.py:190-194), the H2D copy of batch i+1 runs on a copy stream while step i computes; the step itself
+    # starts with a device-to-device copy from the landed staging buffers into the captured graph's input buffers.
+    copy_stream = torch.cuda.Stream()
+    staging = [{k: torch.empty_like(v) for k, v in resident.items()} for _ in range(2)]
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            for k in staging[i % 2]:
+                staging[i % 2][k].copy_(tensors[k], non_blocking=True)
+            landed[i % 2].record(copy_stream)
+
+    def e2e_loop(n):
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(landed[i % 2])
+            step(staging[i % 2]).item()      # D2D into the step's inputs -> step -> loss D2H (host sync)
+
+    e2e_loop(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        step(tensors).item()
+    e2e_loop(args.steps)
     f1.record()
     barrier()
     ms_e2e = max_over_ranks(f0.elapsed_time(f1))

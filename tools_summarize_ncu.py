@@ -1,0 +1,75 @@
+"""Summarise ncu outputs into the small text/csv files kept under profiles/ (run here, on the CPU box).
+
+  python tools_summarize_ncu.py launches gpurun_out/launches.csv profiles/r01_launch_list_summary.csv "<command>"
+  python tools_summarize_ncu.py full gpurun_out/round_prof.ncu-rep profiles/r01_ncu_kernels_summary.txt
+"""
+import csv
+import io
+import re
+import subprocess
+import sys
+
+
+def short(name):
+    name = re.sub(r"\(anonymous namespace\)::", "", name)
+    name = re.sub(r"\(CUtensorMap_st.*", "", name)
+    name = re.sub(r"\((int|bool|long|float|const|__nv|unsigned|double|StreamArgs|at::).*", "", name)
+    name = name.replace("(int)", "").replace("(bool)", "")
+    return name.strip()[:110]
+
+
+def launches(src, dst, command):
+    rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("=="))]
+    hdr = rows[0]
+    ki, mi, vi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    ui = hdr.index("Metric Unit")
+    agg = {}
+    for r in rows[1:]:
+        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
+            continue
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] in ("ns", "nsecond") else (v * 1e3 if r[ui] in ("ms", "msecond") else v)
+        k = short(r[ki])
+        t, c = agg.get(k, (0.0, 0))
+        agg[k] = (t + v, c + 1)
+    tot = sum(t for t, _ in agg.values())
+    n = sum(c for _, c in agg.values())
+    with open(dst, "w") as f:
+        f.write("# ncu launch list of a bf16 train-step window (%d launches, eager mode, gpu__time_duration.sum, --clock-control none)\n" % n)
+        f.write("# command: %s\n# per-launch times are cold-cache and serialised: compare SHARES\n" % command)
+        f.write("kernel,launches,total_us,share\n")
+        for k, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+            f.write('"%s",%d,%.1f,%.4f\n' % (k, c, t, t / tot))
+    print(open(dst).read()[:3000])
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "dram__bytes_read.sum",
+            "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
+            "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_elapsed.avg.per_second"]
+    idx = [(w, hdr.index(w)) for w in want if w in hdr]
+    ki = hdr.index("Kernel Name")
+    seen = {}
+    with open(dst, "w") as f:
+        f.write("# ncu --set full --clock-control none, one launch per kernel (cold cache, profiler replay): %s\n" % src)
+        for r in rows[2:]:
+            k = short(r[ki])
+            seen[k] = seen.get(k, 0) + 1
+            if seen[k] > 1:
+                continue
+            f.write("\n%s\n" % k)
+            for w, i in idx:
+                f.write("    %-70s %s %s\n" % (w, r[i], units[i]))
+    print(open(dst).read()[:6000])
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    else:
+        full(sys.argv[2], sys.argv[3])
