@@ -48,7 +48,7 @@ PROFILE = {"on": False, "log": []}
 # frees -- the graph behind the weight, e.g. the einsum that builds W_eff) and remember the real one as the target of
 # the deferred gradient.  Off by default: a plain forward + `loss.backward()` (what the reference's trainer does,
 # models/training.py:25-43) behaves exactly as before.
-DEFER = {"on": False, "stream": None, "items": []}
+DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": []}
 
 
 class overlap_weight_grads:
@@ -61,6 +61,7 @@ class overlap_weight_grads:
 
     def __exit__(self, exc_type, exc, tb):
         DEFER["on"] = False
+        DEFER["keep"] = []
         items, DEFER["items"] = DEFER["items"], []
         torch.cuda.current_stream().wait_stream(DEFER["stream"])      # join: every deferred dW / db is complete
         if exc_type is None and items:
@@ -68,6 +69,30 @@ class overlap_weight_grads:
             grads = [g for t, g, _ in items]
             torch.autograd.backward(tensors, grads)                    # views / einsum backward -> leaf .grad
         return False
+
+
+def parallel_branches(fns):
+    """Run independent chains of small kernels (the four box heads: ~90 launches each, forward and again in the
+    backward) side by side.  Inside `overlap_weight_grads()` every chain but the first gets its own stream, forked from
+    and joined back to the current one (autograd replays each chain's backward on the stream of its forward); outside
+    it the chains simply run one after the other.  Outputs are kept alive until the context exits, so memory handed
+    out on a branch stream is never recycled while the main stream still reads it."""
+    if not DEFER["on"] or PROFILE["on"] or len(fns) < 2:
+        return [fn() for fn in fns]
+    main = torch.cuda.current_stream()
+    while len(DEFER["branch_streams"]) < len(fns) - 1:
+        DEFER["branch_streams"].append(torch.cuda.Stream())
+    outs = [None] * len(fns)
+    for i in range(len(fns) - 1):
+        DEFER["branch_streams"][i].wait_stream(main)          # fork point: before anything of this group is enqueued
+    outs[0] = fns[0]()                                        # host issue order = list order (RNG consumption order)
+    for i, fn in enumerate(fns[1:]):
+        with torch.cuda.stream(DEFER["branch_streams"][i]):
+            outs[i + 1] = fn()
+    for i in range(len(fns) - 1):
+        main.wait_stream(DEFER["branch_streams"][i])
+    DEFER["keep"].append(outs)
+    return outs
 
 
 def _defer(fn, targets, keep):

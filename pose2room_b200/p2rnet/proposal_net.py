@@ -165,18 +165,20 @@ class ProposalNet(nn.Module):
         p = feats.shape[1]
         act = torch.bfloat16 if self.precision == "bf16" else torch.float32
         rows = feats.reshape(b * p, -1).to(act)
-        center_f = run_rows(self.conv_center, rows)
-        size_f = run_rows(self.conv_size, rows)
-        heading_f = run_rows(self.conv_heading, rows)
-        sem_obj = run_rows(self.conv_sem_obj, rows).float().reshape(b, p, -1)
-        if generate:
-            c, pi_c = self.gmm_center.generate_rows(center_f, self.multi_mode, self.n_samples)
-            s, pi_s = self.gmm_size.generate_rows(size_f, self.multi_mode, self.n_samples)
-            h, pi_h = self.gmm_heading.generate_rows(heading_f, self.multi_mode, self.n_samples)
-        else:
-            c = self.gmm_center.predict_rows(center_f)
-            s = self.gmm_size.predict_rows(size_f)
-            h = self.gmm_heading.predict_rows(heading_f)
+        # four independent chains (each ~30 small launches, again in the backward): side by side when the step runs
+        # multi-stream (ops.overlap_weight_grads), one after the other otherwise.  The train-mode noise is drawn in
+        # the reference's order (center, size, heading: mdn.py:44) because the host issues the chains in that order.
+        def gmm(head, conv):
+            def run():
+                f = run_rows(conv, rows)
+                if generate:
+                    return head.generate_rows(f, self.multi_mode, self.n_samples)
+                return head.predict_rows(f), None
+            return run
+        (c, pi_c), (s, pi_s), (h, pi_h), sem_obj = ops.parallel_branches([
+            gmm(self.gmm_center, self.conv_center), gmm(self.gmm_size, self.conv_size),
+            gmm(self.gmm_heading, self.conv_heading),
+            lambda: run_rows(self.conv_sem_obj, rows).float().reshape(b, p, -1)])
         end_points = decode_scores(c.reshape(b, p, 3), s.reshape(b, p, 3), h.reshape(b, p, 2), sem_obj, end_points)
         if generate:
             # reference layout of pi: (B, G, P)  (proposal_net.py:239-247)
