@@ -11,6 +11,7 @@ away, which yields the same distances and indices because valid boxes always for
 import torch
 from torch import nn
 
+from .. import ops
 from ..geometry import huber_loss, nn_distance
 from .registers import LOSSES
 
@@ -99,11 +100,15 @@ class BoxNetDetectionLoss(BaseLoss):
         return center_loss, size_loss, heading_loss, sem_cls_loss
 
     def __call__(self, est, gt, dataset_config):
-        vote_loss = self.compute_vote_loss(est, gt)
-        assignment, objectness_loss, objectness_label, objectness_mask = self.compute_correspondence(est, gt)
-        meta = {"object_assignment": assignment, "objectness_label": objectness_label}
-        center_loss, size_loss, heading_loss, sem_cls_loss = self.compute_box_and_sem_cls_loss(est, gt, meta,
-                                                                                               dataset_config)
+        def box_chain():
+            assignment, objectness_loss, objectness_label, objectness_mask = self.compute_correspondence(est, gt)
+            meta = {"object_assignment": assignment, "objectness_label": objectness_label}
+            return (objectness_loss, objectness_label, objectness_mask) + \
+                self.compute_box_and_sem_cls_loss(est, gt, meta, dataset_config)
+        # the vote loss and the proposal losses share nothing: two chains of ~100 tiny launches, side by side when the
+        # step runs multi-stream (ops.parallel_branches), sequential otherwise
+        (objectness_loss, objectness_label, objectness_mask, center_loss, size_loss, heading_loss, sem_cls_loss), \
+            vote_loss = ops.parallel_branches([box_chain, lambda: self.compute_vote_loss(est, gt)])
         total = 10 * vote_loss + 5 * objectness_loss + 10 * center_loss + 10 * size_loss + 10 * heading_loss + sem_cls_loss
         n_prop = float(objectness_label.shape[0] * objectness_label.shape[1])
         pos_ratio = torch.sum(objectness_label.float()) / n_prop
