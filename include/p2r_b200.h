@@ -189,6 +189,13 @@ int p2r_gemm_bf16_pair(int M, int N, int K, const void* A, int lda, const void* 
                        const float* bias, int relu, int block_n, const int* kb_list, int kb_stride, double* stats,
                        int stat_copies, void* stream);
 
+/* Weight gradient of the graph convolution on CTA pairs: dW[N1,N2] fp32 (zero-filled by the caller) += dz^T . x with
+ * dz [R,N1], x [R,N2] bf16 row-major (reduction over the rows).  tile_list = (row tile, column tile) int pairs of the
+ * 256 x 256 output tiles to compute (the structurally non-zero ones); the reduction is split `splits` ways and the
+ * partial tiles are combined by bulk-tensor reduce-add stores.                                                      */
+int p2r_gemm_bf16_pair_dw(int R, int N1, int N2, const void* dz, int ldz, const void* x, int ldx, float* dW, int ldw,
+                          const int* tile_list, int num_tiles, int splits, void* stream);
+
 /* (KT x 1) temporal convolution (zero padding (KT-1)/2) as an implicit tensor-core GEMM over the 3-D activation tensor
  * [B, rows = T*V, C], a tap shifting by V rows; no unfold buffer (ref: st_gcn_block.tcn conv, stgcn_layers.py:405-411).
  * mode 0: y = conv(x, W2[Co, KT*Ci]) (+bias); mode 1: dx from dy and Wt[KT*Co, Ci]; mode 2: dW2[Co, KT*Ci] (fp32,

@@ -44,6 +44,7 @@ SIGNATURES = {
                          _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp],
     "p2r_gemm_bf16_pair": [_c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _vp, _c_int,
                            _vp, _c_int, _vp],
+    "p2r_gemm_bf16_pair_dw": [_c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _vp],
     "p2r_tconv_bf16": [_c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp,
                        _c_int, _vp],
     "p2r_gcn_build_weight": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],

@@ -157,6 +157,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  // element-wise += of a shared-memory tile into global memory, done by the copy engine / L2 (fp32 tensor map)
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(p2r_smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -812,6 +820,172 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
+// gemm2_dw_kernel: weight gradient of the graph convolution on CTA pairs.
+//   dW[N1, N2] (fp32, zero-filled by the caller) += dz^T . x,   dz [R, N1], x [R, N2] bf16 row-major (both operands are
+//   "MN-major": the reduction runs over the ROWS R = B*T frames), 256 x 256 output tiles, structurally-zero tiles are
+//   not in `tile_list`, the reduction is split `splits` ways; a work unit u = (split u / num_tiles, tile u % num_tiles)
+//   so the pairs working at the same time stream the same rows of dz and x (shared through L2).  The epilogue stages
+//   32 x 32 fp32 tiles in shared memory and adds them into dW with bulk-tensor REDUCE stores (cp.reduce.async.bulk
+//   .add): split-K without per-element atomics.
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_dw_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                const __grid_constant__ CUtensorMap tma_c, int N1, int N2, int R, const int* __restrict__ tile_list,
+                int num_tiles, int splits, int kps) {
+  using S = PairSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + S::STAGES * S::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tmem_full = empty + S::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_kb = (R + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int num_units = num_tiles * splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      p2r_mbar_init(full + s, 1);
+      p2r_mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      p2r_mbar_init(tmem_full + a, 1);
+      p2r_mbar_init(tmem_empty + a, 8);
+    }
+    p2r_fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto unit_effn = [&](int n0) {            // MMA width: whole 64-column blocks per CTA (a multiple of 128 in total)
+    const int rem = N2 - n0;
+    return rem >= BN ? BN : ((rem + 127) & ~127);
+  };
+  auto unit_kb0 = [&](int u) { return (u / num_tiles) * kps; };
+  auto unit_nkb = [&](int u) { return min(total_kb, unit_kb0(u) + kps) - unit_kb0(u); };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int u = pair0; u < num_units; u += npairs) {
+        const int tile = u % num_tiles;
+        const int m0 = __ldg(tile_list + 2 * tile) * (2 * GEMM_BLOCK_M) + (int)rank * GEMM_BLOCK_M;
+        const int n0 = __ldg(tile_list + 2 * tile + 1) * BN;
+        const int nb0 = n0 + (int)rank * (unit_effn(n0) / 2);
+        const int kb0 = unit_kb0(u), nkb = unit_nkb(u);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (uint32_t)(it / S::STAGES) & 1u;
+          p2r_mbar_wait(empty + s, ph ^ 1u);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          if (rank == 0) p2r_mbar_expect_tx(full + s, 2 * S::STAGE_BYTES);
+          const int k0 = (kb0 + i) * GEMM_BLOCK_K;
+#pragma unroll
+          for (int h = 0; h < GEMM_BLOCK_M / 64; ++h)                      // boxes {64 m, 64 k}
+            tma_load_2d_pair(a_dst + h * (GEMM_BLOCK_K * 128), &tma_a, full + s, m0 + h * 64, k0);
+#pragma unroll
+          for (int h = 0; h < BN / 128; ++h)                               // boxes {64 n, 64 k}
+            tma_load_2d_pair(b_dst + h * (GEMM_BLOCK_K * 128), &tma_b, full + s, nb0 + h * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      int it = 0, t = 0;
+      for (int u = pair0; u < num_units; u += npairs, ++t) {
+        const int tile = u % num_tiles;
+        const int n0 = __ldg(tile_list + 2 * tile + 1) * BN;
+        const uint32_t idesc = make_idesc(2 * GEMM_BLOCK_M, unit_effn(n0), 1, 1);
+        const int nkb = unit_nkb(u);
+        const int as = t & 1;
+        if (t >= 2) {
+          p2r_mbar_wait(tmem_empty + as, (uint32_t)((t >> 1) - 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (uint32_t)(it / S::STAGES) & 1u;
+          p2r_mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = p2r_smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+            umma_bf16_pair(tmem_acc, make_desc(a_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024),
+                           make_desc(b_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024), idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit_pair(empty + s);
+        }
+        umma_commit_pair(tmem_full + as);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs): fp32 tiles, bulk-tensor reduce-add =====================
+    const int q = warp & 3;
+    uint8_t* stg = staging + q * (32 * 128);
+    int t = 0;
+    for (int u = pair0; u < num_units; u += npairs, ++t) {
+      const int tile = u % num_tiles;
+      const int row0 = __ldg(tile_list + 2 * tile) * (2 * GEMM_BLOCK_M) + (int)rank * GEMM_BLOCK_M + q * 32;
+      const int n0 = __ldg(tile_list + 2 * tile + 1) * BN;
+      const int ncols = min(BN, N2 - n0);
+      const int nkb = unit_nkb(u);
+      const int as = t & 1;
+      p2r_mbar_wait(tmem_full + as, (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        if (c0 + 32 >= ncols) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_leader(tmem_empty + as);
+        }
+        if (lane == 0) tma_store_wait_read();     // the previous reduce-store has finished reading the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          uint4 pk;
+          pk.x = nkb > 0 ? v[4 * p + 0] : 0u;
+          pk.y = nkb > 0 ? v[4 * p + 1] : 0u;
+          pk.z = nkb > 0 ? v[4 * p + 2] : 0u;
+          pk.w = nkb > 0 ? v[4 * p + 3] : 0u;
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((p ^ (lane & 7)) << 4)) = pk;   // SWIZZLE_128B
+        }
+        p2r_fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < N1) tma_reduce_add_2d(&tma_c, stg, n0 + c0, row0);   // rows / columns outside dW are clipped
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+    tc_fence_before();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, S::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1076,4 +1250,51 @@ extern "C" int p2r_gemm_bf16_pair(int M, int N, int K, const void* A, int lda, c
   cudaStream_t st = (cudaStream_t)stream;
   if (block_n == 128) return launch_pair<128>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu, ex, st);
   return launch_pair<256>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu, ex, st);
+}
+
+// 2-D fp32 tensor map over C [rows, cols] (ld floats between rows): box {32 columns = 128 bytes, 32 rows}, 128B swizzle.
+static int make_map_f32(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { p2r_set_last_error("p2r_gemm_bf16_pair_dw: cuTensorMapEncodeTiled entry point unavailable", -1); return -1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { p2r_set_last_error("p2r_gemm_bf16_pair_dw: cuTensorMapEncodeTiled (fp32) failed", -1); return -1; }
+  return 0;
+}
+
+// Weight gradient on CTA pairs: dW[N1, N2] fp32 (zero-filled by the caller) += dz^T . x with dz [R, N1], x [R, N2] bf16
+// row-major.  tile_list: int pairs (row tile, column tile) of the 256 x 256 output tiles to compute (the structurally
+// non-zero ones), num_tiles of them; splits: how many ways the reduction over R is split (reduce-add stores combine them).
+extern "C" int p2r_gemm_bf16_pair_dw(int R, int N1, int N2, const void* dz, int ldz, const void* x, int ldx, float* dW,
+                                     int ldw, const int* tile_list, int num_tiles, int splits, void* stream) {
+  P2R_CHECK_ARG(R > 0 && N1 > 0 && N2 > 0 && num_tiles > 0 && tile_list != nullptr && splits >= 1, "p2r_gemm_bf16_pair_dw");
+  P2R_CHECK_ARG(ldz % 8 == 0 && ldx % 8 == 0 && ldw % 4 == 0, "p2r_gemm_bf16_pair_dw (row pitches must be multiples of 16 bytes)");
+  constexpr int BN = 256;
+  using S = PairSmem<BN>;
+  CUtensorMap ma, mb, mc;
+  if (make_map(&ma, dz, N1, R, ldz, GEMM_BLOCK_K)) return -1;     // MN-major operands: inner = output index, rows = reduction
+  if (make_map(&mb, x, N2, R, ldx, GEMM_BLOCK_K)) return -1;
+  if (make_map_f32(&mc, dW, N2, N1, ldw)) return -1;
+  const int total_kb = (R + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  int kps = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kps - 1) / kps;
+  const long long units = (long long)num_tiles * splits;
+  // The weight gradient runs on a second stream beside the HBM-bound BatchNorm chain; a persistent kernel that took every
+  // SM (226 KB of shared memory, all of TMEM) would shut that chain out, so it is given a SHARE of the CTA pairs.
+  static int dw_pairs = 0;
+  if (dw_pairs == 0) {
+    const char* e = getenv("P2R_DW_PAIRS");
+    dw_pairs = e ? atoi(e) : P2R_SM_COUNT / 2;
+    if (dw_pairs < 1 || dw_pairs > P2R_SM_COUNT / 2) dw_pairs = P2R_SM_COUNT / 2;
+  }
+  const unsigned grid = 2u * (unsigned)(units < dw_pairs ? units : dw_pairs);
+  auto kern = gemm2_dw_kernel<BN>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, (cudaStream_t)stream>>>(ma, mb, mc, N1, N2, R, tile_list, num_tiles, splits, kps);
+  P2R_RETURN_LAUNCH("p2r_gemm_bf16_pair_dw");
 }

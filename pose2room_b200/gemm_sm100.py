@@ -16,6 +16,11 @@ USE_SPARSITY = os.environ.get("P2R_GCN_SPARSE", "1") != "0"
 # graph-conv forward / input-gradient GEMMs on CTA pairs (persistent cta_group::2 kernel, 256 x PAIR_BLOCK_N tiles)
 USE_PAIR = os.environ.get("P2R_GCN_PAIR", "1") != "0"
 PAIR_BLOCK_N = int(os.environ.get("P2R_GCN_PAIR_BLOCK_N", "256"))
+# Weight gradient on CTA pairs (gemm2_dw_kernel: 128 us alone vs 212 us for the 128x128-tile kernel).  OFF by default: in
+# the step the weight gradients run on a second stream under the BatchNorm chain, and a persistent kernel that owns all
+# shared memory / TMEM of its SMs cannot co-reside with that chain -- measured 9.44-9.55 ms/step vs 9.32 with the small
+# co-resident tiles.
+USE_PAIR_DW = os.environ.get("P2R_GCN_PAIR_DW", "0") != "0"
 USE_FUSED_STATS = os.environ.get("P2R_FUSED_STATS", "1") != "0"
 
 
@@ -49,6 +54,14 @@ class BlockSparsity:
                 tab[i, 0] = len(ks)
                 tab[i, 1:1 + len(ks)] = ks
             self._cache[key] = torch.from_numpy(tab).to(device)
+        return self._cache[key]
+
+    def tile_list(self, block_m, block_n, device):
+        """int32 [T, 2]: (row tile, column tile) of the structurally non-zero block_m x block_n tiles of dW[N,K]."""
+        key = ("tiles", block_m, block_n, str(device))
+        if key not in self._cache:
+            mask = self.tile_mask(block_m, block_n, "cpu").numpy()
+            self._cache[key] = torch.from_numpy(np.argwhere(mask > 0).astype(np.int32)).contiguous().to(device)
         return self._cache[key]
 
     def tile_mask(self, block_m, block_n, device):
@@ -141,6 +154,27 @@ def gemm_pair(a, b, bias=None, relu=False, block_n=256, kb_list=None, stats=None
                   stats.data_ptr() if stats is not None else None, int(stats.shape[0]) if stats is not None else 1,
                   _stream())
     return c
+
+
+def gemm_pair_dw(dz, x, tile_list=None, splits=0):
+    """dW[N1,N2] fp32 = dz[R,N1]^T @ x[R,N2] on CTA pairs (p2r_gemm_bf16_pair_dw): 256 x 256 tiles from `tile_list`
+    (default: all), split-K combined by bulk-tensor reduce-add stores."""
+    assert dz.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dz.shape[0] == x.shape[0]
+    assert dz.stride(1) == 1 and x.stride(1) == 1
+    r, n1 = dz.shape
+    n2 = x.shape[1]
+    if tile_list is None:
+        tm, tn = -(-n1 // 256), -(-n2 // 256)
+        tile_list = torch.tensor([[i, j] for i in range(tm) for j in range(tn)], dtype=torch.int32, device=dz.device)
+    assert tile_list.dtype == torch.int32 and tile_list.is_contiguous() and tile_list.shape[1] == 2
+    t = tile_list.shape[0]
+    if splits <= 0:      # ~5 waves of work units over the 74 CTA pairs
+        splits = max(1, min(round(370 / t), r // 1024))
+    dw = torch.zeros(n1, n2, dtype=torch.float32, device=dz.device)
+    with torch.cuda.device(dz.device):
+        _lib.call("p2r_gemm_bf16_pair_dw", r, n1, n2, dz.data_ptr(), dz.stride(0), x.data_ptr(), x.stride(0),
+                  dw.data_ptr(), dw.stride(0), tile_list.data_ptr(), t, int(splits), _stream())
+    return dw
 
 
 class _TemporalConvTC(torch.autograd.Function):
@@ -307,6 +341,9 @@ class _Backend:
         m = dz.shape[0]
         n, k = dz.shape[1], x.shape[1]
         tiles = ((n + 127) // 128) * ((k + 127) // 128)
+        if USE_PAIR_DW and n >= 1024 and k >= 1024 and m >= 8192:   # graph conv: CTA pairs, 256 x 256 tiles, reduce-add split-K
+            tl = sparsity.tile_list(256, 256, dz.device) if (sparsity is not None and USE_SPARSITY) else None
+            return gemm_pair_dw(dz, x, tl)
         if tiles >= 148:  # graph-conv: 13 x 13 = 169 tiles of 128x128 fill the chip without split-K / atomics
             mask = sparsity.tile_mask(128, 128, dz.device) if (sparsity is not None and USE_SPARSITY) else None
             return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128, tile_mask=mask)

@@ -337,3 +337,26 @@ def test_gemm_cta_pair_kernel(cuda, bn):
     cd = c.double().reshape(M, NB, 64)
     assert torch.allclose(stats.sum(0)[0], cd.sum((0, 1)), rtol=1e-5, atol=1e-2)
     assert torch.allclose(stats.sum(0)[1], (cd * cd).sum((0, 1)), rtol=1e-5, atol=1e-2)
+
+
+def test_gemm_cta_pair_weight_gradient(cuda):
+    """dW = dz^T . x on CTA pairs (MN-major operands, 256 x 256 tiles, split-K by bulk-tensor reduce-add): exact on
+    integer operands for the full tile set, and equal to the masked product for a tile list."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100
+    g = torch.Generator().manual_seed(40)
+    for (R, N1, N2, splits) in [(512, 256, 256, 1), (2048, 640, 320, 3), (4096, 1600, 1600, 0), (1000, 384, 200, 2)]:
+        dz = torch.randint(-2, 3, (R, N1), generator=g).float()
+        x = torch.randint(-2, 3, (R, N2), generator=g).float()
+        dw = gemm_sm100.gemm_pair_dw(dz.to(cuda).bfloat16(), x.to(cuda).bfloat16(), splits=splits)
+        assert torch.equal(dw.cpu(), dz.t() @ x), (R, N1, N2, splits)
+    nz = _random_block_pattern(25, 25, g, density=0.3)
+    sp = gemm_sm100.BlockSparsity(nz)
+    R = 8192
+    dz = torch.randint(-2, 3, (R, 1600), generator=g).float()
+    x = torch.randint(-2, 3, (R, 1600), generator=g).float()
+    tl = sp.tile_list(256, 256, cuda)
+    dw = gemm_sm100.gemm_pair_dw(dz.to(cuda).bfloat16(), x.to(cuda).bfloat16(), tl)
+    keep = torch.from_numpy(np.kron(sp.tile_mask(256, 256, "cpu").numpy(), np.ones((256, 256), dtype=np.float32)))[:1600, :1600]
+    assert torch.equal(dw.cpu(), (dz.t() @ x) * keep)
+    assert (keep.numpy() >= np.kron(nz, np.ones((64, 64), dtype=np.float32))).all()

@@ -37,6 +37,11 @@ def main():
     rec["dw_dense_ms"] = timeit(lambda: gemm_sm100.gemm(dy, x, True, True, out_dtype=torch.float32, block_n=128))
     mask = sp.tile_mask(128, 128, dev)
     rec["dw_masked_ms"] = timeit(lambda: gemm_sm100.gemm(dy, x, True, True, out_dtype=torch.float32, block_n=128, tile_mask=mask))
+    tl = sp.tile_list(256, 256, dev)
+    rec["dw_pair_tiles"] = [int(tl.shape[0]), 49]
+    for sk in (0, 5, 9, 14):
+        rec["dw_pair_s%d_ms" % sk] = timeit(lambda: gemm_sm100.gemm_pair_dw(dy, x, tl, splits=sk))
+    rec["dw_pair_dense_ms"] = timeit(lambda: gemm_sm100.gemm_pair_dw(dy, x))
     rec["dw_active_tiles"] = [int(mask.sum()), int(mask.numel())]
     # temporal conv forward with / without statistics
     B, T, V, C = 32, 1024, 25, 64
