@@ -192,7 +192,7 @@ class _TemporalConvTC(torch.autograd.Function):
         bias_f = bias.float().contiguous() if bias is not None else None
         sums = None
         if want_stats and USE_FUSED_STATS and co == 64:
-            sums = torch.zeros(STAT_COPIES, 2, 64, dtype=torch.float64, device=x.device)
+            sums = ops.zeros_ws((STAT_COPIES, 2, 64), torch.float64, x.device)
         with torch.cuda.device(x.device):
             _lib.call("p2r_tconv_bf16", 0, x.data_ptr(), w2.data_ptr(), None, y.data_ptr(), b, t * v, ci, co, kt, v,
                       bias_f.data_ptr() if bias_f is not None else None, 1,
@@ -291,7 +291,7 @@ class _Backend:
         n = weight.shape[0]
         sums = None
         if want_stats and USE_FUSED_STATS and n % 64 == 0:
-            sums = torch.zeros(STAT_COPIES, 2, 64, dtype=torch.float64, device=x.device)
+            sums = ops.zeros_ws((STAT_COPIES, 2, 64), torch.float64, x.device)
         sp = sparsity if USE_SPARSITY else None
         if sp is None and sums is None:
             return _Backend.linear_fwd(x, weight, bias, relu), None

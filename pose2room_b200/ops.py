@@ -48,7 +48,26 @@ PROFILE = {"on": False, "log": []}
 # frees -- the graph behind the weight, e.g. the einsum that builds W_eff) and remember the real one as the target of
 # the deferred gradient.  Off by default: a plain forward + `loss.backward()` (what the reference's trainer does,
 # models/training.py:25-43) behaves exactly as before.
-DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": []}
+DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": [], "ws": {}, "ws_off": {}}
+_WS_BYTES = 8 << 20
+
+
+def zeros_ws(shape, dtype, device):
+    """Zero-filled scratch for column sums (BatchNorm statistics, bias gradients).  Inside the multi-stream step
+    context the ~100 small buffers of a step are carved from one workspace that is cleared by a single memset when the
+    context is entered, instead of one fill kernel each; the result must not outlive the step.  Outside: torch.zeros."""
+    if not DEFER["on"]:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    n = 1
+    for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+        n *= int(d)
+    nbytes = (n * torch.empty(0, dtype=dtype).element_size() + 255) // 256 * 256
+    key = str(device)
+    off = DEFER["ws_off"].get(key, 0)
+    if key not in DEFER["ws"] or off + nbytes > _WS_BYTES:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    DEFER["ws_off"][key] = off + nbytes
+    return DEFER["ws"][key][off:off + nbytes].view(dtype)[:n].view(shape)
 
 
 class overlap_weight_grads:
@@ -57,6 +76,12 @@ class overlap_weight_grads:
             DEFER["stream"] = torch.cuda.Stream()
         DEFER["items"] = []
         DEFER["on"] = True
+        if torch.cuda.is_available():          # one memset for every small zero-initialised buffer of the step
+            key = str(torch.device("cuda", torch.cuda.current_device()))
+            if key not in DEFER["ws"]:
+                DEFER["ws"][key] = torch.empty(_WS_BYTES, dtype=torch.uint8, device=key)
+            DEFER["ws"][key].zero_()
+            DEFER["ws_off"][key] = 0
         return self
 
     def __exit__(self, exc_type, exc, tb):
@@ -155,13 +180,13 @@ def _col_sum(dy, y=None, relu=False):
     m, c = dy.shape
     vec = 8 if dy.dtype == torch.bfloat16 else 4
     if not relu and c > 256 and c % vec == 0:     # wide matrices (the 1600-column graph-conv output)
-        s1 = torch.zeros(c, dtype=torch.float64, device=dy.device)
+        s1 = zeros_ws(c, torch.float64, dy.device)
         with torch.cuda.device(dy.device):
             _lib.call("p2r_col_sum_wide", dy.data_ptr(), _DT[dy.dtype], m, c, s1.data_ptr(), _stream())
         return s1.float()
     if c > 256 and c % 256 or c <= 256 and 256 % c:
         return (dy.float() if not relu else dy.float() * (y > 0)).sum(0)  # odd channel counts (259, 100, 24): tiny tensors
-    s1 = torch.zeros(c, dtype=torch.float64, device=dy.device)
+    s1 = zeros_ws(c, torch.float64, dy.device)
     with torch.cuda.device(dy.device):
         _lib.call("p2r_col_bwd_stats", dy.data_ptr(), None, _ptr(y), _DT[dy.dtype], m, c, None, None, int(relu),
                   s1.data_ptr(), None, None, None, _stream())
@@ -181,6 +206,7 @@ class _Linear(Function):
         x = x if x.is_contiguous() else x.contiguous()
         tc = _TC_GEMM["fn"]
         sums = None
+        w_lp = None
         with _Timed("fwd", x.shape[0], weight.shape[0], x.shape[1]):
             if _smallk_ok(x, weight.shape[0], x.shape[1], relu):
                 y = torch.empty(x.shape[0], weight.shape[0], dtype=x.dtype, device=x.device)
@@ -190,13 +216,15 @@ class _Linear(Function):
                     _lib.call("p2r_smallk_linear", x.data_ptr(), wf.data_ptr(), _ptr(bf), _DT[x.dtype], x.shape[0],
                               weight.shape[0], x.shape[1], y.data_ptr(), _stream())
             elif tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
+                w_lp = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)   # once per step: reused by dx
                 if sparsity is not None or want_stats:
-                    y, sums = tc.linear_fwd_ex(x, weight, bias, relu, sparsity, want_stats)
+                    y, sums = tc.linear_fwd_ex(x, w_lp, bias, relu, sparsity, want_stats)
                 else:
-                    y = tc.linear_fwd(x, weight, bias, relu)
+                    y = tc.linear_fwd(x, w_lp, bias, relu)
             else:
                 y = sgemm(x, weight, False, True, bias, relu, out_dtype=x.dtype)
         ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.w_lp = w_lp
         ctx.relu = relu
         ctx.has_bias = bias is not None
         if want_stats:
@@ -224,7 +252,8 @@ class _Linear(Function):
         use_tc = tc is not None and x.dtype == torch.bfloat16 and tc.supports(m, n, k)
         if ctx.needs_input_grad[0]:
             with _Timed("dx", m, n, k):
-                dx = tc.linear_dx(dz, weight, sp) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
+                w_dx = ctx.w_lp if (use_tc and ctx.w_lp is not None) else weight
+                dx = tc.linear_dx(dz, w_dx, sp) if use_tc else sgemm(dz, weight, False, False, out_dtype=x.dtype)
         if ctx.targets is not None:
             tw, tb = ctx.targets
             need_w = tw is not None and tw.requires_grad
@@ -367,7 +396,7 @@ class _BatchNormAct(Function):
         with torch.cuda.device(dev):
             if training:
                 if sums is None or sums.numel() == 0:     # no statistics from the producing GEMM's epilogue
-                    sums = torch.zeros(1, 2, c, dtype=torch.float64, device=dev)
+                    sums = zeros_ws((1, 2, c), torch.float64, dev)
                     _lib.call("p2r_col_stats", x.data_ptr(), dt, m, c, sums[0, 0].data_ptr(), sums[0, 1].data_ptr(), _stream())
                 assert sums.dim() == 3 and sums.shape[1] == 2 and sums.shape[2] == c and sums.is_contiguous()
                 _lib.call("p2r_bn_finalize", c, m, sums[0, 0].data_ptr(), sums[0, 1].data_ptr(), sums.shape[0], 2 * c,
@@ -400,7 +429,7 @@ class _BatchNormAct(Function):
         dt = _DT[x.dtype]
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
-        sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
+        sums = zeros_ws((2, c), torch.float64, dev)
         with torch.cuda.device(dev):
             _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
                       stats[1].data_ptr(), ctx.relu_mode, sums[0].data_ptr(), sums[1].data_ptr(), stats[2].data_ptr(),
@@ -409,8 +438,9 @@ class _BatchNormAct(Function):
                       stats[1].data_ptr(), stats[2].data_ptr(), sums[0].data_ptr() if ctx.training else None,
                       sums[1].data_ptr() if ctx.training else None, ctx.relu_mode, dx.data_ptr(), _ptr(dres),
                       stats[3].data_ptr(), _stream())
-        dgamma = sums[1].float() if ctx.needs_input_grad[1] else None
-        dbeta = sums[0].float() if ctx.needs_input_grad[2] else None
+        sums_f = sums.float() if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None   # one conversion
+        dgamma = sums_f[1] if ctx.needs_input_grad[1] else None
+        dbeta = sums_f[0] if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
