@@ -119,6 +119,8 @@ int p2r_sgemm(int M, int N, int K, const void* A, int lda, int trans_a, int a_dt
 int p2r_col_stats(const void* x, int dtype, long long M, int C, double* s1, double* s2, void* stream);
 /* backward column sums: dz = dy masked by the ReLU (relu = 0 none, 1: y > 0, 2: x*scale+shift > 0, recomputed);
  * s1 = sum dz, s2 = sum dz*(x-mean)*rstd (s2/x may be NULL)                                                       */
+/* relu: 0 none, 1 mask from y > 0, 2 mask recomputed from x*scale+shift > 0, 3 `y` points to the bit mask written by
+ * p2r_affine_act (streaming kernels only) -- same meaning in p2r_bn_bwd_apply                                      */
 int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
                       const float* rstd, int relu, double* s1, double* s2, const float* scale, const float* shift,
                       void* stream);
@@ -130,9 +132,13 @@ int p2r_col_sum_wide(const void* dy, int dtype, long long M, int C, double* s1, 
 int p2r_bn_finalize(int C, long long M, const double* s1, const double* s2, int copies, long long copy_stride,
                     const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                     float* running_var, float* mean, float* rstd, float* scale, float* shift, void* stream);
-/* y = x*scale[c] + shift[c] (+residual) (ReLU)                                                     */
+/* y = x*scale[c] + shift[c] (+residual) (ReLU).  relu_mask (optional, only where p2r_stream_bn_supported(...) == 1):
+ * [M, C/8] bytes, bit i of byte j = (y[row, 8 j + i] > 0) -- the backward passes read it (relu mode 3 below) instead of
+ * the whole output tensor.                                                                          */
 int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift,
-                   const void* residual, int relu, void* y, void* stream);
+                   const void* residual, int relu, void* y, unsigned char* relu_mask, void* stream);
+/* 1 when [M, C] operands of this dtype take the bulk-TMA streaming kernels (bf16, C = 64, M >= 4096)              */
+int p2r_stream_bn_supported(int dtype, long long M, int C);
 /* BN(+ReLU)(+residual) backward, elementwise part (s1 == NULL: eval-mode BN)                       */
 int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
                      const float* rstd, const float* scale, const double* s1, const double* s2, int relu, void* dx,

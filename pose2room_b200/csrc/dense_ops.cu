@@ -372,8 +372,9 @@ extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, i
   P2R_CHECK_ARG(!(relu == 1 && y == nullptr), "p2r_col_bwd_stats (relu = 1 needs y)");
   P2R_CHECK_ARG(!(relu == 2 && (x == nullptr || scale == nullptr || shift == nullptr)), "p2r_col_bwd_stats (relu = 2 needs x, scale, shift)");
   if (M == 0) return 0;
-  if ((x != nullptr || relu == 0) && (s2 == nullptr || x != nullptr) && p2r_stream_bn_ok(dtype, M, C, dy, x, y))
-    return p2r_stream_col_bwd_stats(dy, x, relu == 1 ? y : nullptr, M, mean, rstd, relu, s1, s2, scale, shift, (cudaStream_t)stream);
+  if ((x != nullptr || relu == 0) && (s2 == nullptr || x != nullptr) && p2r_stream_bn_ok(dtype, M, C, dy, x, relu == 3 ? nullptr : y))
+    return p2r_stream_col_bwd_stats(dy, x, (relu == 1 || relu == 3) ? y : nullptr, M, mean, rstd, relu, s1, s2, scale, shift, (cudaStream_t)stream);
+  P2R_CHECK_ARG(relu != 3, "p2r_col_bwd_stats (relu = 3, the bit mask, needs p2r_stream_bn_supported(dtype, M, C))");
   int rpc;
   const int grid = colreduce_grid(M, &rpc);
   if (dtype == 0) {
@@ -472,12 +473,13 @@ affine_act_vec_kernel(long long nvec, int C, const T* __restrict__ x, const floa
 }
 
 extern "C" int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift,
-                              const void* residual, int relu, void* y, void* stream) {
+                              const void* residual, int relu, void* y, unsigned char* relu_mask, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_affine_act");
   const long long total = M * C;
   if (total == 0) return 0;
   if (p2r_stream_bn_ok(dtype, M, C, x, residual, y))
-    return p2r_stream_affine_act(x, M, scale, shift, residual, relu, y, (cudaStream_t)stream);
+    return p2r_stream_affine_act(x, M, scale, shift, residual, relu, y, relu_mask, (cudaStream_t)stream);
+  P2R_CHECK_ARG(relu_mask == nullptr, "p2r_affine_act (the ReLU bit mask needs p2r_stream_bn_supported(dtype, M, C))");
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, x, residual, y))
     affine_act_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
@@ -575,10 +577,11 @@ extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, in
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_bn_bwd_apply");
   const long long total = M * C;
   if (total == 0) return 0;
-  if (x != nullptr && (relu != 1 || y != nullptr) && (relu != 2 || shift != nullptr) &&
-      p2r_stream_bn_ok(dtype, M, C, dy, x, y, dx, dres))
-    return p2r_stream_bn_bwd_apply(dy, x, relu == 1 ? y : nullptr, M, mean, rstd, scale, s1, s2, relu, dx, dres, shift,
-                                   (cudaStream_t)stream);
+  if (x != nullptr && ((relu != 1 && relu != 3) || y != nullptr) && (relu != 2 || shift != nullptr) &&
+      p2r_stream_bn_ok(dtype, M, C, dy, x, relu == 3 ? nullptr : y, dx, dres))
+    return p2r_stream_bn_bwd_apply(dy, x, (relu == 1 || relu == 3) ? y : nullptr, M, mean, rstd, scale, s1, s2, relu, dx, dres,
+                                   shift, (cudaStream_t)stream);
+  P2R_CHECK_ARG(relu != 3, "p2r_bn_bwd_apply (relu = 3, the bit mask, needs p2r_stream_bn_supported(dtype, M, C))");
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, dy, x, y, dx, dres))
     bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);

@@ -45,6 +45,8 @@ struct StreamArgs {
   int relu;             // 0 none; 1 mask from in[2] (y > 0); 2 mask recomputed from x*scale+shift > 0; AFFINE: 0/1
   double* o1;           // STATS_*: outputs (atomically accumulated, zero-filled by the caller)
   double* o2;
+  unsigned char* mask_out;        // AFFINE: optional ReLU bit mask of the output, [M, 8] bytes (bit i of byte cv = channel 8 cv + i)
+  const unsigned char* mask_in;   // STATS_BWD / BWD_APPLY with relu == 3: that mask instead of re-reading y
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -147,33 +149,46 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
 #pragma unroll
           for (int i = 0; i < 8; ++i) { acc1[i] += p[i]; acc2[i] = fmaf(p[i], p[i], acc2[i]); }
         } else if (MODE == STATS_BWD) {
-          // p = dy, q = x (NIN >= 2), w = y (NIN == 3, relu == 1)
+          // p = dy, q = x (NIN >= 2), w = y (NIN == 3, relu == 1); relu == 3: one mask byte per thread instead of y
+          const unsigned mb = (NIN == 2 && a.relu == 3) ? (unsigned)__ldg(a.mask_in + (size_t)(r0 + r) * 8 + cv) : 0xffu;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float dz = p[i];
             if (NIN >= 3 && !(w[i] > 0.f)) dz = 0.f;
             if (NIN == 2 && a.relu == 2 && !(fmaf(q[i], sc[i], sh[i]) > 0.f)) dz = 0.f;
+            if (NIN == 2 && !((mb >> i) & 1u)) dz = 0.f;
             acc1[i] += dz;
             if (NIN >= 2) acc2[i] = fmaf(dz, q[i], acc2[i]);
           }
         } else if (MODE == AFFINE) {
           // p = x, q = residual (NIN == 2)
           float y[8];
+          unsigned bits = 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float t = fmaf(p[i], sc[i], sh[i]);
             if (NIN >= 2) t += q[i];
             y[i] = a.relu ? fmaxf(t, 0.f) : t;
           }
-          *reinterpret_cast<uint4*>(a.out[0] + go) = pack8(y);
+          const uint4 packed = pack8(y);
+          *reinterpret_cast<uint4*>(a.out[0] + go) = packed;
+          if (a.mask_out != nullptr) {      // the mask of the STORED (bf16-rounded) output, as the backward would see it
+            float yr[8];
+            unpack8(packed, yr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bits |= (yr[i] > 0.f ? 1u : 0u) << i;
+            a.mask_out[(size_t)(r0 + r) * 8 + cv] = (unsigned char)bits;
+          }
         } else {
-          // BWD_APPLY: p = dy, q = x, w = y (NIN == 3, relu == 1)
+          // BWD_APPLY: p = dy, q = x, w = y (NIN == 3, relu == 1); relu == 3: mask byte
+          const unsigned mb = (NIN == 2 && a.relu == 3) ? (unsigned)__ldg(a.mask_in + (size_t)(r0 + r) * 8 + cv) : 0xffu;
           float g[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float dz = p[i];
             if (NIN >= 3 && !(w[i] > 0.f)) dz = 0.f;
             if (NIN == 2 && a.relu == 2 && !(fmaf(q[i], sc[i], sh[i]) > 0.f)) dz = 0.f;
+            if (NIN == 2 && !((mb >> i) & 1u)) dz = 0.f;
             p[i] = dz;
             g[i] = fmaf(dz, A[i], fmaf(q[i], Bc[i], D[i]));
           }
@@ -262,6 +277,10 @@ bool p2r_stream_bn_enabled() {
   return v == 1;
 }
 
+extern "C" int p2r_stream_bn_supported(int dtype, long long M, int C) {
+  return (p2r_stream_bn_enabled() && dtype == 1 && C == SB_C && M >= 4096) ? 1 : 0;
+}
+
 bool p2r_stream_bn_ok(int dtype, long long M, int C, const void* p0, const void* p1, const void* p2, const void* p3,
                       const void* p4) {
   return p2r_stream_bn_enabled() && dtype == 1 && C == SB_C && M >= 4096 && aligned16(p0) && aligned16(p1) &&
@@ -283,7 +302,8 @@ int p2r_stream_col_bwd_stats(const void* dy, const void* x, const void* y, long 
   StreamArgs a = {};
   a.in[0] = (const __nv_bfloat16*)dy;
   a.in[1] = (const __nv_bfloat16*)x;
-  a.in[2] = (const __nv_bfloat16*)y;
+  a.in[2] = relu == 3 ? nullptr : (const __nv_bfloat16*)y;
+  a.mask_in = relu == 3 ? (const unsigned char*)y : nullptr;
   a.M = M;
   a.mean = mean;
   a.rstd = rstd;
@@ -298,8 +318,9 @@ int p2r_stream_col_bwd_stats(const void* dy, const void* x, const void* y, long 
 }
 
 int p2r_stream_affine_act(const void* x, long long M, const float* scale, const float* shift, const void* residual,
-                          int relu, void* y, cudaStream_t st) {
+                          int relu, void* y, unsigned char* relu_mask, cudaStream_t st) {
   StreamArgs a = {};
+  a.mask_out = relu_mask;
   a.in[0] = (const __nv_bfloat16*)x;
   a.in[1] = (const __nv_bfloat16*)residual;
   a.out[0] = (__nv_bfloat16*)y;
@@ -317,7 +338,8 @@ int p2r_stream_bn_bwd_apply(const void* dy, const void* x, const void* y, long l
   StreamArgs a = {};
   a.in[0] = (const __nv_bfloat16*)dy;
   a.in[1] = (const __nv_bfloat16*)x;
-  a.in[2] = (const __nv_bfloat16*)y;
+  a.in[2] = relu == 3 ? nullptr : (const __nv_bfloat16*)y;
+  a.mask_in = relu == 3 ? (const unsigned char*)y : nullptr;
   a.out[0] = (__nv_bfloat16*)dx;
   a.out[1] = (__nv_bfloat16*)dres;
   a.M = M;

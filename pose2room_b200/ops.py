@@ -412,11 +412,17 @@ class _BatchNormAct(Function):
             y = torch.empty_like(x)
             if residual is not None:
                 residual = residual if residual.is_contiguous() else residual.contiguous()
+            # ReLU mask for the backward: recomputed from x (mode 2) unless a residual was added; then either the output
+            # itself (mode 1) or -- with the streaming kernels -- a 1-bit-per-element mask written by this pass (mode 3):
+            # the two backward passes then read M*8 bytes instead of the whole M*128-byte output
+            mask = None
+            if relu and residual is not None and torch.is_grad_enabled() and c % 8 == 0 and \
+                    _lib.query("p2r_stream_bn_supported", dt, m, c) == 1:
+                mask = torch.empty(m, c // 8, dtype=torch.uint8, device=dev)
             _lib.call("p2r_affine_act", x.data_ptr(), dt, m, c, stats[2].data_ptr(), stats[3].data_ptr(),
-                      _ptr(residual), int(relu), y.data_ptr(), _stream())
-        # ReLU mask in the backward: recomputed from x (relu mode 2) unless a residual was added (mode 1 reads y)
-        ctx.relu_mode = 0 if not relu else (1 if residual is not None else 2)
-        ctx.save_for_backward(x, y if ctx.relu_mode == 1 else None, stats)
+                      _ptr(residual), int(relu), y.data_ptr(), _ptr(mask), _stream())
+        ctx.relu_mode = 0 if not relu else ((3 if mask is not None else 1) if residual is not None else 2)
+        ctx.save_for_backward(x, mask if ctx.relu_mode == 3 else (y if ctx.relu_mode == 1 else None), stats)
         ctx.training, ctx.has_res = training, residual is not None
         return y
 

@@ -212,8 +212,8 @@ cs = torch.cuda.current_stream().cuda_stream
 _lib.call("p2r_col_stats", x.data_ptr(), 1, M, C, s[0].data_ptr(), s[1].data_ptr(), cs)
 _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), 2, s[2].data_ptr(), s[3].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), cs)
 _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), 1, s[4].data_ptr(), s[5].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), cs)
-_lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), None, 1, out[0].data_ptr(), cs)
-_lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), yy.data_ptr(), 1, out[1].data_ptr(), cs)
+_lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), None, 1, out[0].data_ptr(), None, cs)
+_lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), yy.data_ptr(), 1, out[1].data_ptr(), None, cs)
 _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), 2, out[2].data_ptr(), None, st[3].data_ptr(), cs)
 _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[4].data_ptr(), s[5].data_ptr(), 1, out[3].data_ptr(), out[4].data_ptr(), st[3].data_ptr(), cs)
 torch.cuda.synchronize()
