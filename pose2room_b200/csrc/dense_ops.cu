@@ -838,11 +838,62 @@ embed_sum_kernel(long long frames, int J, int K, int C, const T* __restrict__ a,
   }
 }
 
+// C = 64 bf16: 16-byte vectors.  A warp owns one frame; lane = (row lane 0..3, 8-channel group 0..7): every load / store
+// instruction of the warp moves four whole 128-byte rows.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+embed_sum_vec64_kernel(long long frames, int J, int K, const __nv_bfloat16* __restrict__ a,
+                       const __nv_bfloat16* __restrict__ b_in, __nv_bfloat16* __restrict__ out) {
+  const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  const int rl = lane >> 3, c0 = (lane & 7) * 8;
+  const int nsrc = BWD ? J : K, ndst = BWD ? K : J;
+  const __nv_bfloat16* src = (BWD ? a : b_in) + (size_t)f * nsrc * 64 + c0;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = 0.f;
+  for (int r = rl; r < nsrc; r += 4) {
+    float v[8];
+    vload(src + (size_t)r * 64, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] += __shfl_xor_sync(0xffffffffu, m[i], 8);
+    m[i] += __shfl_xor_sync(0xffffffffu, m[i], 16);
+    m[i] *= 1.f / (float)K;
+  }
+  __nv_bfloat16* dst = out + (size_t)f * ndst * 64 + c0;
+  if (BWD) {
+    for (int r = rl; r < ndst; r += 4) vstore(dst + (size_t)r * 64, m);
+  } else {
+    const __nv_bfloat16* skp = a + (size_t)f * J * 64 + c0;
+    for (int r = rl; r < ndst; r += 4) {
+      float v[8];
+      vload(skp + (size_t)r * 64, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += m[i];
+      vstore(dst + (size_t)r * 64, v);
+    }
+  }
+}
+
+static bool embed_vec_ok(int dtype, int C, const void* p0, const void* p1, const void* p2) {
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return dtype == 1 && C == 64 && al(p0) && al(p1) && al(p2);
+}
+
 extern "C" int p2r_embed_sum(const void* sk, const void* pos, int dtype, long long frames, int J, int K, int C, void* x,
                              void* stream) {
   P2R_CHECK_ARG(frames >= 0 && J > 0 && K > 0 && C > 0, "p2r_embed_sum");
   if (frames == 0) return 0;
   const int grid = p2r_ceil_div(frames * 32, 256);
+  if (embed_vec_ok(dtype, C, sk, pos, x)) {
+    embed_sum_vec64_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, (const __nv_bfloat16*)sk, (const __nv_bfloat16*)pos, (__nv_bfloat16*)x);
+    P2R_RETURN_LAUNCH("p2r_embed_sum");
+  }
   if (dtype == 0)
     embed_sum_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const float*)sk, (const float*)pos, (float*)x);
   else
@@ -855,6 +906,10 @@ extern "C" int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, i
   P2R_CHECK_ARG(frames >= 0 && J > 0 && K > 0 && C > 0, "p2r_embed_sum_grad");
   if (frames == 0) return 0;
   const int grid = p2r_ceil_div(frames * 32, 256);
+  if (embed_vec_ok(dtype, C, dx, dpos, nullptr)) {
+    embed_sum_vec64_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, (const __nv_bfloat16*)dx, nullptr, (__nv_bfloat16*)dpos);
+    P2R_RETURN_LAUNCH("p2r_embed_sum_grad");
+  }
   if (dtype == 0)
     embed_sum_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, J, K, C, (const float*)dx, nullptr, (float*)dpos);
   else

@@ -268,6 +268,8 @@ def _pad_cols(t, cols):
 
 class _Backend:
     """Interface expected by ops._Linear (see ops._TC_GEMM)."""
+    # the CTA-pair weight-gradient kernel owns whole SMs: run it in line with the backward chain, not beside it
+    DW_INLINE = USE_PAIR_DW and os.environ.get("P2R_GCN_DW_INLINE", "1") != "0"
 
     @staticmethod
     def supports(m, n, k):

@@ -120,14 +120,18 @@ def parallel_branches(fns):
     return outs
 
 
-def _defer(fn, targets, keep):
+def _defer(fn, targets, keep, inline=False):
     """Run fn() -> list of gradients on the side stream; `targets` are the autograd-connected tensors they belong to;
     `keep` are the operands the side-stream kernels read (kept alive until the join so the caching allocator cannot
-    hand their memory to main-stream tensors in the meantime)."""
-    side = DEFER["stream"]
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
+    hand their memory to main-stream tensors in the meantime).  inline=True: run on the current stream (kernels that
+    own whole SMs gain nothing from a second stream) but still hand the gradients over at the join."""
+    if inline:
         grads = fn()
+    else:
+        side = DEFER["stream"]
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            grads = fn()
     for t, g in zip(targets, grads):
         if t is not None and g is not None:
             DEFER["items"].append((t, g.to(t.dtype) if g.dtype != t.dtype else g, keep))
@@ -360,7 +364,8 @@ class _GraphConv(Function):
             return [d_w.reshape(ctx.w_shape), d_b, d_a]
 
         if ctx.targets is not None:
-            _defer(weight_grads, [t if (t is not None and t.requires_grad) else None for t in ctx.targets], (dy, x))
+            _defer(weight_grads, [t if (t is not None and t.requires_grad) else None for t in ctx.targets], (dy, x),
+                   inline=getattr(tc, "DW_INLINE", False))
             return dx, None, None, None, None, None, None
         gw, gb, ga = weight_grads()
         return dx, gw, gb, ga, None, None, None

@@ -233,3 +233,22 @@ print(json.dumps({"s": s.cpu().tolist(), "o": [float(out[i].float().sum()) for i
     assert a["h"][0] == b["h"][0] and a["h"][1] == b["h"][1] and a["h"][4] == b["h"][4]   # bit-identical outputs
     # dx depends on the sums (tiny differences in the last fp32 bit of the coefficients): compare as values
     assert abs(a["o"][2] - b["o"][2]) <= 1e-3 * (abs(b["o"][2]) + 1) and abs(a["o"][3] - b["o"][3]) <= 1e-3 * (abs(b["o"][3]) + 1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_embed_sum_fwd_bwd(cuda, dtype):
+    """x = sk + mean_k(pos) broadcast over the joints of a frame (stgcn.py:121,129); bf16 with C = 64 takes the
+    vectorised kernel.  Integer-valued data keeps bf16 exact."""
+    from pose2room_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    F_, J, K, C = 777, 25, 20, 64
+    sk = torch.randint(-3, 4, (F_, J, C), generator=g).float().to(cuda).to(dtype).requires_grad_(True)
+    pos = (torch.randint(-2, 3, (F_, K, C), generator=g).float() * K).to(cuda).to(dtype).requires_grad_(True)   # mean stays integral
+    x = ops.embed_sum(sk, pos)
+    ref = sk.detach().float() + pos.detach().float().mean(1, keepdim=True)
+    assert torch.equal(x.float(), ref)
+    go = (torch.randint(-2, 3, (F_, J, C), generator=g).float() * 4).to(cuda).to(dtype)
+    gsk, gpos = torch.autograd.grad(x, [sk, pos], go)
+    assert torch.equal(gsk.float(), go.float())
+    want = (go.float().sum(1, keepdim=True) / K).expand(F_, K, C)
+    assert torch.allclose(gpos.float(), want, rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-6)
