@@ -55,34 +55,76 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md).  NVML is polled every 10 ms from a
+    thread (a 10-step timed region lasts ~0.1 s: spawning nvidia-smi per sample would catch one sample at best);
+    `timed(True/False)` brackets the regions whose samples are summarised.  Falls back to nvidia-smi without pynvml."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.in_region = index, [], False, False
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:     # CUDA ordinal -> the same physical GPU in NVML (CUDA_VISIBLE_DEVICES may renumber)
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid).replace("GPU-", "")
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def timed(self, on):
+        self.in_region = on
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        return mhz, mask
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        if self.max_mhz is None and f[1].isdigit():
+            self.max_mhz = int(f[1])
+        mask = 0
+        for bit, col in ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5)):
+            if f[col].lower().startswith("active"):
+                mask |= bit
+        return int(f[0]), mask
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                mhz, mask = self._sample_nvml() if self.nvml is not None else self._sample_smi()
+                self.rows.append((self.in_region, mhz, mask))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.01 if self.nvml is not None else 0.2)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        rows = [r for r in self.rows if r[0]] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sm = sorted(r[1] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [name for bit, name in self.REASONS.items() if mask & bit],
+                "samples": len(rows), "samples_in_timed_regions": sum(1 for r in self.rows if r[0]),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm (CPU)
@@ -295,11 +337,13 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.timed(True)
     e0.record()
     for _ in range(args.steps):
         step(static)
     e1.record()
     barrier()
+    sampler.timed(False)
     launches = launches_per_step * args.steps
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * args.steps / (ms * 1e-3)
@@ -312,7 +356,6 @@ def main():
         eager_step(static)
     torch.cuda.synchronize()
     ops.PROFILE["on"] = False
-    sampler.stop_flag = True
 
     # ---- roofline of the dominant kernel: the fused graph-convolution GEMM (forward) -------------------
     vj = JOINTS * 64
@@ -360,10 +403,13 @@ def main():
     e2e_loop(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.timed(True)
     f0.record()
     e2e_loop(args.steps)
     f1.record()
     barrier()
+    sampler.timed(False)
+    sampler.stop_flag = True
     ms_e2e = max_over_ranks(f0.elapsed_time(f1))
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
 
