@@ -301,7 +301,10 @@ class _Backend:
             kbl = sp.kb_list(PAIR_BLOCK_N, False, x.device) if sp is not None else None
             y = gemm_pair(x, weight.to(torch.bfloat16), bias, relu, block_n=PAIR_BLOCK_N, kb_list=kbl, stats=sums)
             return y, sums
-        bn = GCN_BLOCK_N if (n % 160 == 0 or GCN_BLOCK_N != 160) else (64 if n <= 64 else 128)
+        if n <= 64:
+            bn = 64
+        else:
+            bn = GCN_BLOCK_N if (n % 160 == 0 or GCN_BLOCK_N != 160) else 128
         kbl = sp.kb_list(bn, False, x.device) if sp is not None else None
         y = gemm(x, weight.to(torch.bfloat16), False, False, bias, relu, out_dtype=torch.bfloat16, block_n=bn,
                  kb_list=kbl, stats=sums)

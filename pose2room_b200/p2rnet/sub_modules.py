@@ -24,6 +24,11 @@ class SingleConv(nn.Sequential):
     def forward_rows(self, x):
         """x [M, Cin] channel-last rows -> [M, Cout]."""
         w = self.conv.weight.reshape(self.conv.out_channels, self.conv.in_channels)
+        if "b" in self.order and self.conv.out_channels == 64 and self.batchnorm.training:
+            # 64-channel layers (pos_embed / sk_feat over all T*J points): the BatchNorm statistics come out of the GEMM
+            # epilogue (an empty tensor when the kernel in use has no fused statistics: batchnorm_act then runs its pass)
+            y, sums = ops.linear(x, w, self.conv.bias, want_stats=True)
+            return ops.batchnorm_act(y, self.batchnorm, relu="r" in self.order, sums=sums)
         y = ops.linear(x, w, self.conv.bias)
         if "b" in self.order:
             y = ops.batchnorm_act(y, self.batchnorm, relu="r" in self.order)
