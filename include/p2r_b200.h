@@ -139,10 +139,13 @@ int p2r_affine_act(const void* x, int dtype, long long M, int C, const float* sc
                    const void* residual, int relu, void* y, unsigned char* relu_mask, void* stream);
 /* 1 when [M, C] operands of this dtype take the bulk-TMA streaming kernels (bf16, C = 64, M >= 4096)              */
 int p2r_stream_bn_supported(int dtype, long long M, int C);
-/* BN(+ReLU)(+residual) backward, elementwise part (s1 == NULL: eval-mode BN)                       */
+/* BN(+ReLU)(+residual) backward, elementwise part (s1 == NULL: eval-mode BN).  colsum / period (optional, only where
+ * p2r_stream_bn_supported(...) == 1, period <= 32): also accumulate colsum[row % period][c] += dx[row][c] (double,
+ * zero-filled by the caller) -- the bias gradient of the graph convolution whose output rows cycle through the joints
+ * (stgcn_layers.py:50-56 bias), without another pass over dx.                                       */
 int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
                      const float* rstd, const float* scale, const double* s1, const double* s2, int relu, void* dx,
-                     void* dres, const float* shift, void* stream);
+                     void* dres, const float* shift, double* colsum, int period, void* stream);
 /* dz = dy * (y > 0)                                                                                */
 int p2r_relu_bwd(const void* dy, const void* y, int dtype, long long total, void* dz, void* stream);
 /* (KT x 1) temporal conv as GEMM: x[B,T,V,C] -> col[B*T*V, KT*C] (zero padded), and its adjoint    */
@@ -218,7 +221,7 @@ int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, 
 int p2r_gcn_build_weight(const float* conv_w, const float* conv_b, const float* A, int K, int V, int Co, int Ci,
                          void* w_eff, void* w_eff_t, float* b_eff, void* stream);
 /* ... and its backward: fold dW_eff [V*Co, V*Ci] fp32 and db_eff [V*Co] fp32 onto d_conv_w [K*Co, Ci], d_conv_b [K*Co]
- * (both accumulated with atomics: zero-filled by the caller) and dA [K,V,V] (written; 0 where A == 0).             */
+ * and dA [K,V,V] (all three written in full, no atomics: deterministic; dA is 0 where A == 0).                    */
 int p2r_gcn_reduce_weight_grad(const float* dw_eff, const float* db_eff, const float* conv_w, const float* conv_b,
                                const float* A, int K, int V, int Co, int Ci, float* d_conv_w, float* d_conv_b,
                                float* dA, void* stream);

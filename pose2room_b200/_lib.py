@@ -59,7 +59,8 @@ SIGNATURES = {
     "p2r_bn_finalize": [_c_int, _c_ll, _vp, _vp, _c_int, _c_ll, _vp, _vp, _c_float, _c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "p2r_affine_act": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp],
     "p2r_stream_bn_supported": [_c_int, _c_ll, _c_int],
-    "p2r_bn_bwd_apply": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp],
+    "p2r_bn_bwd_apply": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp,
+                         _c_int, _vp],
     "p2r_relu_bwd": [_vp, _vp, _c_int, _c_ll, _vp, _vp],
     "p2r_temporal_unfold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_temporal_fold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],

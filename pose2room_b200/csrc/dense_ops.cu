@@ -571,17 +571,22 @@ bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict
   }
 }
 
+// colsum / period (optional, streaming kernels with period <= 32 only): also accumulate sum over rows of dx per
+// (row % period, channel) into colsum[period][C] (double, zero-filled by the caller) -- the bias gradient of a layer whose
+// output rows cycle through `period` joints, without another pass over dx.
 extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
                                 const float* mean, const float* rstd, const float* scale, const double* s1,
-                                const double* s2, int relu, void* dx, void* dres, const float* shift, void* stream) {
+                                const double* s2, int relu, void* dx, void* dres, const float* shift, double* colsum,
+                                int period, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_bn_bwd_apply");
   const long long total = M * C;
   if (total == 0) return 0;
   if (x != nullptr && ((relu != 1 && relu != 3) || y != nullptr) && (relu != 2 || shift != nullptr) &&
       p2r_stream_bn_ok(dtype, M, C, dy, x, relu == 3 ? nullptr : y, dx, dres))
     return p2r_stream_bn_bwd_apply(dy, x, (relu == 1 || relu == 3) ? y : nullptr, M, mean, rstd, scale, s1, s2, relu, dx, dres,
-                                   shift, (cudaStream_t)stream);
+                                   shift, colsum, period, (cudaStream_t)stream);
   P2R_CHECK_ARG(relu != 3, "p2r_bn_bwd_apply (relu = 3, the bit mask, needs p2r_stream_bn_supported(dtype, M, C))");
+  P2R_CHECK_ARG(colsum == nullptr, "p2r_bn_bwd_apply (fused column sums need p2r_stream_bn_supported(dtype, M, C))");
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, dy, x, y, dx, dres))
     bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);

@@ -84,17 +84,17 @@ extern "C" int p2r_gcn_build_weight(const float* conv_w, const float* conv_b, co
   P2R_RETURN_LAUNCH("p2r_gcn_build_weight");
 }
 
-// Backward of the construction above.  grid (V, V), block (w, v):
-//   d_conv_w[k*64+co, ci] += A[k,v,w] * dW_eff[(w,co),(v,ci)]                       (atomics; zero-filled by the caller)
-//   dA[k,v,w]              = <W_k, dW_eff block> + sum_co conv_b[k,co] * db_eff[w,co] where A[k,v,w] != 0, else 0
-//   d_conv_b[k*64+co]     += db_eff[w,co] * sum_v A[k,v,w]                          (blocks v == 0; zero-filled by caller)
+// Backward of the construction above, two launches, no atomics (deterministic):
+//   gcn_dA_kernel, grid (V, V), block (w, v):
+//     dA[k,v,w] = <W_k, dW_eff block (w,v)> + sum_co conv_b[k,co] * db_eff[w,co]   where A[k,v,w] != 0, else 0
+//   gcn_dw_kernel, grid (K, 8), block (k, 8 output rows co):
+//     d_conv_w[k*64+co, ci] = sum over (v,w) with A[k,v,w] != 0 of A[k,v,w] * dW_eff[(w,co),(v,ci)]
+//     d_conv_b[k*64+co]     = sum_w db_eff[w,co] * sum_v A[k,v,w]                          (the slice that owns co)
 // Entries of dA where A == 0 are written as 0: A = adjacency * importance, so the chain rule multiplies them by the
 // adjacency's zero anyway, and the structurally-zero blocks of dW_eff are never computed (tile mask of the dW GEMM).
 __global__ void __launch_bounds__(256)
-gcn_reduce_weight_grad_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff,
-                              const float* __restrict__ conv_w, const float* __restrict__ conv_b,
-                              const float* __restrict__ A, int K, int V, float* __restrict__ d_conv_w,
-                              float* __restrict__ d_conv_b, float* __restrict__ dA) {
+gcn_dA_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff, const float* __restrict__ conv_w,
+              const float* __restrict__ conv_b, const float* __restrict__ A, int K, int V, float* __restrict__ dA) {
   __shared__ float red[8];
   const int w = blockIdx.x, v = blockIdx.y, t = threadIdx.x;
   const int r = t >> 2, c0 = (t & 3) * 16;
@@ -118,13 +118,9 @@ gcn_reduce_weight_grad_kernel(const float* __restrict__ dw_eff, const float* __r
       loaded = true;
     }
     const float* wk = conv_w + ((size_t)k * GC_C + r) * GC_C + c0;
-    float* dwk = d_conv_w + ((size_t)k * GC_C + r) * GC_C + c0;
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      dot = fmaf(__ldg(wk + i), blk[i], dot);
-      atomicAdd(dwk + i, a * blk[i]);
-    }
+    for (int i = 0; i < 16; ++i) dot = fmaf(__ldg(wk + i), blk[i], dot);
     if (t < GC_C && conv_b != nullptr && db_eff != nullptr)
       dot = fmaf(__ldg(conv_b + k * GC_C + t), __ldg(db_eff + w * GC_C + t), dot);
 #pragma unroll
@@ -139,13 +135,37 @@ gcn_reduce_weight_grad_kernel(const float* __restrict__ dw_eff, const float* __r
       dA[((size_t)k * V + v) * V + w] = s;
     }
   }
-  if (v == 0 && t < GC_C && d_conv_b != nullptr && db_eff != nullptr) {
-    const float g = __ldg(db_eff + w * GC_C + t);
-    for (int k = 0; k < K; ++k) {
-      float cs = 0.f;
-      for (int u = 0; u < V; ++u) cs += __ldg(A + ((size_t)k * V + u) * V + w);
-      if (cs != 0.f) atomicAdd(d_conv_b + k * GC_C + t, g * cs);
+}
+
+__global__ void __launch_bounds__(256)
+gcn_dw_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff, const float* __restrict__ A, int K,
+              int V, float* __restrict__ d_conv_w, float* __restrict__ d_conv_b) {
+  extern __shared__ float sA[];                              // A[k] : V x V
+  const int k = blockIdx.x, slice = blockIdx.y, t = threadIdx.x;
+  for (int i = t; i < V * V; i += 256) sA[i] = __ldg(A + (size_t)k * V * V + i);
+  __syncthreads();
+  const int co = slice * 8 + (t >> 5);                       // 8 output rows per CTA, one warp each
+  const int ci = (t & 31) * 2;                               // two adjacent columns per lane: 256-byte rows per warp
+  const size_t ld = (size_t)V * GC_C;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int v = 0; v < V; ++v)
+    for (int w = 0; w < V; ++w) {
+      const float a = sA[v * V + w];
+      if (a != 0.f) {                                        // (block-uniform)
+        const float2 q = __ldg(reinterpret_cast<const float2*>(dw_eff + ((size_t)w * GC_C + co) * ld + (size_t)v * GC_C + ci));
+        acc0 = fmaf(a, q.x, acc0);
+        acc1 = fmaf(a, q.y, acc1);
+      }
     }
+  *reinterpret_cast<float2*>(d_conv_w + ((size_t)k * GC_C + co) * GC_C + ci) = make_float2(acc0, acc1);
+  if (d_conv_b != nullptr && db_eff != nullptr && (t & 31) == 0) {
+    float s = 0.f;
+    for (int w = 0; w < V; ++w) {
+      float cs = 0.f;
+      for (int v = 0; v < V; ++v) cs += sA[v * V + w];
+      s = fmaf(__ldg(db_eff + w * GC_C + co), cs, s);
+    }
+    d_conv_b[k * GC_C + co] = s;
   }
 }
 
@@ -153,7 +173,9 @@ extern "C" int p2r_gcn_reduce_weight_grad(const float* dw_eff, const float* db_e
                                           const float* conv_b, const float* A, int K, int V, int Co, int Ci,
                                           float* d_conv_w, float* d_conv_b, float* dA, void* stream) {
   P2R_CHECK_ARG(K > 0 && V > 0 && Co == GC_C && Ci == GC_C, "p2r_gcn_reduce_weight_grad (64 -> 64 channel blocks)");
-  gcn_reduce_weight_grad_kernel<<<dim3(V, V), 256, 0, (cudaStream_t)stream>>>(dw_eff, db_eff, conv_w, conv_b, A, K, V,
-                                                                               d_conv_w, d_conv_b, dA);
+  P2R_CHECK_ARG((size_t)V * V * sizeof(float) <= 48 * 1024, "p2r_gcn_reduce_weight_grad (adjacency too large for shared memory)");
+  gcn_dA_kernel<<<dim3(V, V), 256, 0, (cudaStream_t)stream>>>(dw_eff, db_eff, conv_w, conv_b, A, K, V, dA);
+  gcn_dw_kernel<<<dim3(K, GC_C / 8), 256, (size_t)V * V * sizeof(float), (cudaStream_t)stream>>>(dw_eff, db_eff, A, K, V,
+                                                                                               d_conv_w, d_conv_b);
   P2R_RETURN_LAUNCH("p2r_gcn_reduce_weight_grad");
 }

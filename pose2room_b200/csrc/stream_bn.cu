@@ -45,6 +45,8 @@ struct StreamArgs {
   int relu;             // 0 none; 1 mask from in[2] (y > 0); 2 mask recomputed from x*scale+shift > 0; AFFINE: 0/1
   double* o1;           // STATS_*: outputs (atomically accumulated, zero-filled by the caller)
   double* o2;
+  double* colsum;       // BWD_APPLY: optional sums of dx over the rows with the same (row % period): [period][64] doubles,
+  int period;           //            atomically accumulated (the bias gradient of the layer that produced x: rows = joints)
   unsigned char* mask_out;        // AFFINE: optional ReLU bit mask of the output, [M, 8] bytes (bit i of byte cv = channel 8 cv + i)
   const unsigned char* mask_in;   // STATS_BWD / BWD_APPLY with relu == 3: that mask instead of re-reading y
 };
@@ -77,6 +79,13 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (a.M + SB_ROWS - 1) / SB_ROWS;
 
+  // BWD_APPLY with a.colsum: per-(row % period, channel) sums of dx, accumulated with shared-memory float atomics
+  // (row stride 72 floats + a per-lane rotation of the channel order make the 32 lanes of a warp hit 32 banks)
+  constexpr int CS_LD = 72, CS_MAXP = 32;
+  __shared__ float cs_tab[MODE == BWD_APPLY ? CS_MAXP * CS_LD : 1];
+  const bool do_cs = MODE == BWD_APPLY && a.colsum != nullptr;
+  if (do_cs)
+    for (int i = tid; i < CS_MAXP * CS_LD; i += SB_THREADS) cs_tab[i] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       p2r_mbar_init(full + s, 1);
@@ -193,7 +202,18 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
             g[i] = fmaf(dz, A[i], fmaf(q[i], Bc[i], D[i]));
           }
           if (a.out[1]) *reinterpret_cast<uint4*>(a.out[1] + go) = pack8(p);
-          *reinterpret_cast<uint4*>(a.out[0] + go) = pack8(g);
+          const uint4 gp = pack8(g);
+          *reinterpret_cast<uint4*>(a.out[0] + go) = gp;
+          if (do_cs) {      // sums of the STORED (bf16) dx, like a separate pass over dx would see them
+            float gr[8];
+            unpack8(gp, gr);
+            float* row = cs_tab + (int)((r0 + r) % a.period) * CS_LD + c0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ii = (i + lane) & 7;
+              atomicAdd(row + ii, gr[ii]);
+            }
+          }
         }
       }
     }
@@ -201,6 +221,15 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
     if (lane == 0) p2r_mbar_arrive(empty + s);   // this warp no longer reads stage s
   }
 
+  if (MODE == BWD_APPLY) {
+    if (do_cs) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // every consumer has added its last row
+      for (int i = tid; i < a.period * SB_C; i += SB_CONSUMERS) {
+        const float v = cs_tab[(i / SB_C) * CS_LD + (i % SB_C)];
+        if (v != 0.f) atomicAdd(a.colsum + i, (double)v);
+      }
+    }
+  }
   if (MODE == STATS_FWD || MODE == STATS_BWD) {
     // lanes l, l^8, l^16, l^24 own the same channels: fold them, then combine the 8 warps through shared memory
 #pragma unroll
@@ -334,8 +363,10 @@ int p2r_stream_affine_act(const void* x, long long M, const float* scale, const 
 
 int p2r_stream_bn_bwd_apply(const void* dy, const void* x, const void* y, long long M, const float* mean,
                             const float* rstd, const float* scale, const double* s1, const double* s2, int relu,
-                            void* dx, void* dres, const float* shift, cudaStream_t st) {
+                            void* dx, void* dres, const float* shift, double* colsum, int period, cudaStream_t st) {
   StreamArgs a = {};
+  a.colsum = (colsum != nullptr && period >= 1 && period <= 32) ? colsum : nullptr;
+  a.period = period;
   a.in[0] = (const __nv_bfloat16*)dy;
   a.in[1] = (const __nv_bfloat16*)x;
   a.in[2] = relu == 3 ? nullptr : (const __nv_bfloat16*)y;

@@ -72,7 +72,8 @@ class st_gcn_block(nn.Module):
         else:
             w_eff, b_eff = self.gcn.effective_weight(A)
             g, s1 = ops.linear(frames, w_eff, b_eff, sparsity=sparsity, want_stats=True)
-        h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True, sums=s1)                # BN + ReLU
+        # BN + ReLU; its backward also leaves the per-(joint, channel) sums of dg = the graph conv's bias gradient
+        h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True, sums=s1, colsum_period=v)
         y, s2 = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias, want_stats=True)
         res = x.reshape(b * t * v, c) if self.has_residual else None
         out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res, sums=s2)                       # BN + res + ReLU

@@ -214,8 +214,8 @@ _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0]
 _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), 1, s[4].data_ptr(), s[5].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), cs)
 _lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), None, 1, out[0].data_ptr(), None, cs)
 _lib.call("p2r_affine_act", x.data_ptr(), 1, M, C, st[2].data_ptr(), st[3].data_ptr(), yy.data_ptr(), 1, out[1].data_ptr(), None, cs)
-_lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), 2, out[2].data_ptr(), None, st[3].data_ptr(), cs)
-_lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[4].data_ptr(), s[5].data_ptr(), 1, out[3].data_ptr(), out[4].data_ptr(), st[3].data_ptr(), cs)
+_lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), 2, out[2].data_ptr(), None, st[3].data_ptr(), None, 0, cs)
+_lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), yy.data_ptr(), 1, M, C, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), s[4].data_ptr(), s[5].data_ptr(), 1, out[3].data_ptr(), out[4].data_ptr(), st[3].data_ptr(), None, 0, cs)
 torch.cuda.synchronize()
 print(json.dumps({"s": s.cpu().tolist(), "o": [float(out[i].float().sum()) for i in range(5)],
                   "h": [int(out[i].view(torch.int16).long().sum()) for i in range(5)]}))
@@ -252,3 +252,27 @@ def test_embed_sum_fwd_bwd(cuda, dtype):
     assert torch.equal(gsk.float(), go.float())
     want = (go.float().sum(1, keepdim=True) / K).expand(F_, K, C)
     assert torch.allclose(gpos.float(), want, rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-6)
+
+
+def test_bn_backward_fused_periodic_column_sums(cuda):
+    """p2r_bn_bwd_apply with colsum / period: the per-(row % period, channel) sums of the dx it writes equal a separate
+    column sum over the stored bf16 dx (the graph convolution's bias gradient, 25 joints)."""
+    from pose2room_b200 import _lib
+    if _lib.query("p2r_stream_bn_supported", 1, 25 * 2048, 64) != 1:
+        pytest.skip("streaming kernels disabled")
+    M, C, P = 25 * 2048 + 25 * 3, 64, 25
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(M, C, generator=g).to(cuda).bfloat16()
+    dy = torch.randn(M, C, generator=g).to(cuda).bfloat16()
+    st = (torch.rand(4, C, generator=g) + 0.5).to(cuda)
+    s = torch.zeros(2, C, dtype=torch.float64, device=cuda)
+    cs_stream = torch.cuda.current_stream().cuda_stream
+    _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(), 2,
+              s[0].data_ptr(), s[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), cs_stream)
+    dx = torch.empty_like(x)
+    colsum = torch.zeros(P, C, dtype=torch.float64, device=cuda)
+    _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, 1, M, C, st[0].data_ptr(), st[1].data_ptr(),
+              st[2].data_ptr(), s[0].data_ptr(), s[1].data_ptr(), 2, dx.data_ptr(), None, st[3].data_ptr(),
+              colsum.data_ptr(), P, cs_stream)
+    want = dx.double().reshape(M // P, P, C).sum(0)
+    assert torch.allclose(colsum, want, rtol=1e-4, atol=1e-2), (colsum - want).abs().max()

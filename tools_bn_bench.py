@@ -32,7 +32,7 @@ out["col_bwd_stats_relu2_us"] = t(lambda: _lib.call("p2r_col_bwd_stats", dy.data
 out["col_bwd_stats_relu1_us"] = t(lambda: _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), res.data_ptr(), DT, M, C, stats[0].data_ptr(), stats[1].data_ptr(), 1, s[0].data_ptr(), s[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), st))
 out["affine_us"] = t(lambda: _lib.call("p2r_affine_act", x.data_ptr(), DT, M, C, stats[2].data_ptr(), stats[3].data_ptr(), None, 1, y.data_ptr(), None, st))
 out["affine_res_us"] = t(lambda: _lib.call("p2r_affine_act", x.data_ptr(), DT, M, C, stats[2].data_ptr(), stats[3].data_ptr(), res.data_ptr(), 1, y.data_ptr(), None, st))
-out["bwd_apply_relu2_us"] = t(lambda: _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, DT, M, C, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), s[0].data_ptr(), s[1].data_ptr(), 2, dx.data_ptr(), None, stats[3].data_ptr(), st))
-out["bwd_apply_relu1_res_us"] = t(lambda: _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), res.data_ptr(), DT, M, C, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), s[0].data_ptr(), s[1].data_ptr(), 1, dx.data_ptr(), dres.data_ptr(), stats[3].data_ptr(), st))
+out["bwd_apply_relu2_us"] = t(lambda: _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, DT, M, C, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), s[0].data_ptr(), s[1].data_ptr(), 2, dx.data_ptr(), None, stats[3].data_ptr(), None, 0, st))
+out["bwd_apply_relu1_res_us"] = t(lambda: _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), res.data_ptr(), DT, M, C, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), s[0].data_ptr(), s[1].data_ptr(), 1, dx.data_ptr(), dres.data_ptr(), stats[3].data_ptr(), None, 0, st))
 out["ideal_us_per_105MB_pass"] = 104.9e6 / 6548e9 * 1e6
 print(json.dumps(out))
