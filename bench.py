@@ -187,11 +187,72 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ supervision
+# Twice in ~60 runs of this round an experimental multi-stream configuration of the step stopped making progress during
+# the warm-up steps (cause not established; never seen with the shipped defaults).  A bench that
+# hangs helps nobody, so: (1) every measuring process carries a watchdog that exits with an error when no phase
+# boundary has been crossed for P2R_BENCH_STALL_S seconds; (2) the single-GPU run is a child process of a small
+# supervisor that, if the child stalls, kills it and measures once more with the single-stream step
+# (P2R_OVERLAP_DW=0) and says so in `config.fallback`.  Multi-rank runs (torchrun) only have the watchdog.
+_HEARTBEAT = {"t": time.time(), "phase": "start"}
+
+
+def beat(phase):
+    _HEARTBEAT["t"], _HEARTBEAT["phase"] = time.time(), phase
+
+
+def start_watchdog():
+    limit = float(os.environ.get("P2R_BENCH_STALL_S", "150"))
+
+    def run():
+        while True:
+            time.sleep(2.0)
+            if time.time() - _HEARTBEAT["t"] > limit:
+                sys.stderr.write("bench.py: no progress for %.0f s in phase '%s' -- aborting\n" % (limit, _HEARTBEAT["phase"]))
+                sys.stderr.flush()
+                os._exit(17)
+    threading.Thread(target=run, daemon=True).start()
+
+
+def supervise():
+    import signal
+    attempts = [({}, None), ({"P2R_OVERLAP_DW": "0"}, "single-stream step: the multi-stream attempt stalled and was killed")]
+    for extra, label in attempts:
+        env = dict(os.environ, P2R_BENCH_CHILD="1", **extra)
+        p = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE,
+                             start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=float(os.environ.get("P2R_BENCH_TIMEOUT_S", "420")))
+        except subprocess.TimeoutExpired:
+            os.killpg(p.pid, signal.SIGKILL)
+            p.wait()
+            sys.stderr.write("bench.py: attempt timed out\n")
+            continue
+        lines = [l for l in out.decode().splitlines() if l.startswith("{")]
+        if p.returncode == 0 and lines:
+            if label is None:
+                print(lines[-1], flush=True)
+            else:
+                d = json.loads(lines[-1])
+                d["config"]["fallback"] = label
+                print(json.dumps(d), flush=True)
+            return 0
+        if p.returncode != 17:          # a real failure, not a stall: do not hide it behind a retry
+            sys.stdout.write(out.decode())
+            return p.returncode or 1
+        sys.stderr.write("bench.py: attempt stalled (watchdog)\n")
+    return 1
+
+
 # ------------------------------------------------------------------------------------------ our arm (GPU)
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and os.environ.get("P2R_BENCH_CHILD") != "1" and \
+            os.environ.get("P2R_BENCH_SUPERVISE", "1") != "0":
+        sys.exit(supervise())
+    start_watchdog()
 
     import torch.distributed as dist
     from pose2room_b200 import _lib, ops, synthetic
@@ -209,6 +270,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     _lib.load()
+    beat("library loaded")
 
     precision = args.precision
     if precision == "auto":
@@ -232,6 +294,7 @@ def main():
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-3, fused=True, capturable=True)
 
+    beat("model built")
     B = args.batch
     host = synthetic.make_batch(B, T_FRAMES, JOINTS, seed=1234 + rank, pin=True)
     tensors = {k: v for k, v in host.items() if isinstance(v, torch.Tensor)}
@@ -282,12 +345,14 @@ def main():
                     step(static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            beat("eager warm-up done")
             dbg("eager warm-up done, capturing")
             graph = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
                 static_loss = captured(static)
             torch.cuda.synchronize()
+            beat("graph captured")
             dbg("captured")
         except Exception as e:  # report, do not hide: the bench line says whether the graph was used
             print("bench.py: CUDA graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
@@ -333,6 +398,7 @@ def main():
     barrier()
 
     # ---- device-resident throughput -------------------------------------------------------------------
+    beat("warm-up replays done")
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -344,6 +410,7 @@ def main():
     e1.record()
     barrier()
     sampler.timed(False)
+    beat("timed region done")
     launches = launches_per_step * args.steps
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * args.steps / (ms * 1e-3)
@@ -356,6 +423,7 @@ def main():
         eager_step(static)
     torch.cuda.synchronize()
     ops.PROFILE["on"] = False
+    beat("per-kernel timing done")
 
     # ---- roofline of the dominant kernel: the fused graph-convolution GEMM (forward) -------------------
     vj = JOINTS * 64
@@ -412,6 +480,7 @@ def main():
     sampler.stop_flag = True
     ms_e2e = max_over_ranks(f0.elapsed_time(f1))
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    beat("end-to-end leg done")
 
     if rank == 0:
         cpu = None
