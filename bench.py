@@ -427,7 +427,9 @@ def main():
 
     # ---- roofline of the dominant kernel: the fused graph-convolution GEMM (forward) -------------------
     vj = JOINTS * 64
-    gcn = [r for r in ops.PROFILE["log"] if r[0] == "fwd" and r[2] == vj and r[3] == vj]
+    # the CTA-pair launch itself ("pair_fwd": events around the one C-ABI call); older paths log the whole operator ("fwd")
+    gcn = [r for r in ops.PROFILE["log"] if r[0] == "pair_fwd" and r[2] == vj and r[3] == vj] or \
+          [r for r in ops.PROFILE["log"] if r[0] == "fwd" and r[2] == vj and r[3] == vj]
     peaks = measured_peaks()
     roofline = None
     if gcn:

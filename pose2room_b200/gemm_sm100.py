@@ -146,7 +146,8 @@ def gemm_pair(a, b, bias=None, relu=False, block_n=256, kb_list=None, stats=None
         assert kb_list.dtype == torch.int32 and kb_list.is_contiguous() and kb_list.shape[0] == -(-n // block_n)
     if stats is not None:
         assert stats.dtype == torch.float64 and stats.is_contiguous() and tuple(stats.shape[1:]) == (2, 64)
-    with torch.cuda.device(a.device):
+    # (per-kernel timing for bench.py's roofline leg: the events bracket this launch alone)
+    with torch.cuda.device(a.device), ops._Timed("pair_fwd" if stats is not None else "pair", m, n, k):
         _lib.call("p2r_gemm_bf16_pair", m, n, k, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), c.data_ptr(),
                   c.stride(0), bias.data_ptr() if bias is not None else None, int(relu) | int(_debug_flags), int(block_n),
                   kb_list.data_ptr() if kb_list is not None else None,
