@@ -214,12 +214,13 @@ def start_watchdog():
     threading.Thread(target=run, daemon=True).start()
 
 
-def supervise():
+def supervise(script=None):
     import signal
+    script = script or os.path.abspath(__file__)
     attempts = [({}, None), ({"P2R_OVERLAP_DW": "0"}, "single-stream step: the multi-stream attempt stalled and was killed")]
     for extra, label in attempts:
         env = dict(os.environ, P2R_BENCH_CHILD="1", **extra)
-        p = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE,
+        p = subprocess.Popen([sys.executable, script] + sys.argv[1:], env=env, stdout=subprocess.PIPE,
                              start_new_session=True)
         try:
             out, _ = p.communicate(timeout=float(os.environ.get("P2R_BENCH_TIMEOUT_S", "420")))

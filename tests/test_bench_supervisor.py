@@ -1,0 +1,58 @@
+"""CPU: bench.py's supervisor -- a measuring child that stalls is killed and the measurement is repeated once with the
+single-stream step, flagged in config.fallback; a child that fails for another reason is not retried."""
+import json
+import os
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _run(tmp_path, body, monkeypatch, capsys, timeout="3"):
+    import bench
+    script = tmp_path / "fake_child.py"
+    script.write_text(textwrap.dedent(body))
+    monkeypatch.setenv("P2R_BENCH_TIMEOUT_S", timeout)
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    rc = bench.supervise(str(script))
+    return rc, capsys.readouterr()
+
+
+def test_stalled_child_falls_back_to_single_stream(tmp_path, monkeypatch, capsys):
+    rc, io = _run(tmp_path, '''
+        import json, os, time
+        assert os.environ["P2R_BENCH_CHILD"] == "1"
+        if os.environ.get("P2R_OVERLAP_DW") != "0":
+            time.sleep(60)                       # the multi-stream attempt never finishes
+        print(json.dumps({"value": 1.0, "config": {"workload": "w"}}))
+    ''', monkeypatch, capsys)
+    assert rc == 0
+    lines = [l for l in io.out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                         # exactly ONE json line
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0 and "single-stream" in d["config"]["fallback"]
+    assert "timed out" in io.err
+
+
+def test_watchdog_exit_is_retried_and_real_failures_are_not(tmp_path, monkeypatch, capsys):
+    rc, io = _run(tmp_path, '''
+        import json, os, sys
+        if os.environ.get("P2R_OVERLAP_DW") != "0":
+            sys.exit(17)                         # what the in-process watchdog does on a stall
+        print(json.dumps({"value": 2.0, "config": {}}))
+    ''', monkeypatch, capsys, timeout="30")
+    assert rc == 0 and json.loads(io.out.strip().splitlines()[-1])["config"]["fallback"]
+    rc, io = _run(tmp_path, '''
+        import sys
+        print("bench.py: no CUDA device")
+        sys.exit(1)
+    ''', monkeypatch, capsys, timeout="30")
+    assert rc == 1 and "no CUDA device" in io.out and not any(l.startswith("{") for l in io.out.splitlines())
+
+
+def test_healthy_child_line_is_passed_through_unchanged(tmp_path, monkeypatch, capsys):
+    rc, io = _run(tmp_path, '''
+        print('{"value": 3.5, "config": {"workload": "w"}}')
+    ''', monkeypatch, capsys, timeout="30")
+    assert rc == 0 and io.out.strip() == '{"value": 3.5, "config": {"workload": "w"}}'
