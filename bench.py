@@ -337,6 +337,7 @@ def main():
     for k in static:
         static[k].copy_(resident[k])
     graph, static_loss, use_graph = None, None, os.environ.get("P2R_CUDA_GRAPH", "1") != "0"
+    opt_graph = None
     if use_graph:
         try:
             side = torch.cuda.Stream()
@@ -355,6 +356,20 @@ def main():
             torch.cuda.synchronize()
             beat("graph captured")
             dbg("captured")
+            if world > 1 and os.environ.get("P2R_OPT_GRAPH", "1") != "0":
+                # several ranks: the NCCL all-reduce stays outside the captures, but the fused AdamW (whose host-side
+                # launch path costs more than its kernels) becomes a second small graph replayed right after it
+                try:
+                    graph.replay()                      # gradients exist at their captured addresses
+                    parallel.allreduce_gradients(params)
+                    opt_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(opt_graph):
+                        opt.step()
+                    torch.cuda.synchronize()
+                    beat("optimizer graph captured")
+                except Exception as e:
+                    print("bench.py: optimizer graph capture failed, stepping eagerly: %r" % (e,), file=sys.stderr)
+                    opt_graph = None
         except Exception as e:  # report, do not hide: the bench line says whether the graph was used
             print("bench.py: CUDA graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
             graph, use_graph = None, False
@@ -370,7 +385,11 @@ def main():
                 static[k].copy_(data[k], non_blocking=True)
         graph.replay()
         if world > 1:
-            finish()
+            if opt_graph is not None:
+                parallel.allreduce_gradients(params)
+                opt_graph.replay()
+            else:
+                finish()
         return static_loss
     launches_per_step = None
 
