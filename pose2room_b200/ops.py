@@ -9,6 +9,8 @@ statistic ("data layout").
 Precision: activations may be float32 (parity mode: fp32-exact SIMT GEMM, fixed summation order) or
 bfloat16 (throughput mode: tensor-core GEMM from gemm_sm100.cu, fp32 accumulate).  Parameters stay fp32.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -314,7 +316,7 @@ def linear(x, weight, bias=None, relu=False, sparsity=None, want_stats=False):
 _COLSUM = {}
 # OFF by default: the kernel is correct in isolation and in an eager step (tests, tools_dbg_hang.py), but bench.py's
 # back-to-back warm-up steps did not finish with it enabled (two runs, cause not established) -- see DESIGN.md section 3.
-_FUSED_COLSUM = __import__("os").environ.get("P2R_FUSED_COLSUM", "0") != "0"
+_FUSED_COLSUM = os.environ.get("P2R_FUSED_COLSUM", "0") != "0"
 
 
 class _GraphConv(Function):
