@@ -79,3 +79,17 @@ def test_host_helpers_without_the_multi_stream_context():
     assert out == [1, 2, 3] and order == ["a", "b", "c"]          # list order = issue order (RNG consumption order)
     z = ops.zeros_ws((3, 5), torch.float64, torch.device("cpu"))
     assert z.shape == (3, 5) and z.dtype == torch.float64 and float(z.abs().sum()) == 0.0
+
+
+def test_internal_joint_order_is_a_permutation_that_tightens_the_tables():
+    """stgcn._JOINT_ORDER_25 (throughput mode works in this joint order internally): a permutation of the 25 joints with
+    fewer k-blocks per 256-wide n-tile and fewer non-zero 128x128 weight-gradient tiles than the reference order."""
+    from pose2room_b200.p2rnet.stgcn import _JOINT_ORDER_25 as perm
+    assert sorted(perm) == list(range(25))
+    _, nz = _pattern(25)
+    ident, mine = BlockSparsity(nz), BlockSparsity(nz[perm][:, perm])
+    kb = lambda sp: int(sp.kb_list(256, False, "cpu")[:, 0].sum())
+    tiles = lambda sp: int(sp.tile_mask(128, 128, "cpu").sum())
+    assert (kb(ident), tiles(ident)) == (123, 109)
+    assert (kb(mine), tiles(mine)) == (106, 99)
+    assert mine.density == ident.density                           # the same blocks, moved
