@@ -226,6 +226,21 @@ int p2r_gcn_reduce_weight_grad(const float* dw_eff, const float* db_eff, const f
                                const float* A, int K, int V, int Co, int Ci, float* d_conv_w, float* d_conv_b,
                                float* dA, void* stream);
 
+/* ---- sample -> batch (ref: models/p2rnet/dataloader.py) ------------------------------------------------------------
+ * One launch builds the three large tensors of the `data` dict for a whole batch from raw samples RESIDENT in device
+ * memory: frame picking (dataloader.py:128-131), flip / rotate / translate of joints and votes (augment_data,
+ * dataloader.py:31-84, bit-exact incl. the reference's float32 / float64 rounding points -- csrc/augment_math.h), dtype
+ * casts (:137-145) and batching (collate_fn, :148-160).
+ *   joints f32 [F_total, J, 3], votes f32 [F_total, J, 10] (column 0 = vote mask): all raw frames of all samples, packed;
+ *   frame_start i64 [n_samples + 1]: first packed frame of each sample; sample_ids i32 [B]: the batch;
+ *   params f64 [B, 16]: per batch item (enabled, flip, rot[9] row-major, shift[3], floor height, 0) -- the host draws
+ *   them with the reference's RNG calls (dataloader.py:33-37); enabled = 0 copies the raw values (val / test);
+ *   out_channels 3, or 4 to append joint height above the floor (use_height, dataloader.py:112-115).
+ * Outputs: input_joints f32 [B,T,J,out_channels], vote_label f32 [B,T,J,9], vote_label_mask i64 [B,T,J]; T = num_frames. */
+int p2r_make_batch(const float* joints, const float* votes, const long long* frame_start, const int* sample_ids,
+                   const double* params, int b, int num_frames, int j, int out_channels, float* input_joints,
+                   float* vote_label, long long* vote_label_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ def _rot(theta):
     return np.array([[c, 0.0, -s], [0.0, 1.0, 0.0], [s, 0.0, c]])
 
 
-def make_scene(rng, T, J):
+def make_scene(rng, T, J, raw=False):
     steps = rng.normal(0.0, 0.05, size=(T, 3))
     hip = np.cumsum(steps, axis=0)
     hip[:, 1] = np.clip(0.9 + hip[:, 1], 0.8, 1.0)
@@ -55,6 +55,9 @@ def make_scene(rng, T, J):
         mask[inside] = 1
         slot[inside] = np.minimum(2, slot[inside] + 1)
 
+    if raw:
+        return dict(joints=joints, votes=votes, mask=mask, centers=centers, sizes=sizes, theta=theta,
+                    classes=classes)
     out = dict(
         input_joints=joints.astype(np.float32),
         box_label_mask=np.zeros(MAX_GT, np.float32),
@@ -72,6 +75,20 @@ def make_scene(rng, T, J):
     out["heading"][:n_gt, 0] = np.sin(theta)
     out["heading"][:n_gt, 1] = np.cos(theta)
     return out
+
+
+def make_raw_sample(rng, F, J, name="synthetic"):
+    """One sample in the reference's ON-DISK schema (what utils/virtualhome/3_generate_samples.py:188-193
+    writes and dataloader.py:90-101 reads back): skeleton_joints f32 (F,J,3), skeleton_joint_votes f32
+    (F,J,10) with column 0 = vote mask, object_nodes = list of dict(class_id, centroid f32 (3,), R_mat f32
+    (3,3) with rows (heading, up, right), size f32 (3,))."""
+    sc = make_scene(rng, F, J, raw=True)
+    votes10 = np.concatenate([sc["mask"][..., None].astype(np.float64), sc["votes"]], -1)
+    nodes = [dict(class_id=np.int32(sc["classes"][g]), centroid=sc["centers"][g].astype(np.float32),
+                  R_mat=_rot(sc["theta"][g]).astype(np.float32), size=sc["sizes"][g].astype(np.float32))
+             for g in range(len(sc["theta"]))]
+    return dict(skeleton_joints=sc["joints"].astype(np.float32),
+                skeleton_joint_votes=votes10.astype(np.float32), object_nodes=nodes, name=name)
 
 
 def make_batch(B, T, J, seed=1234, as_torch=True, pin=False):
