@@ -245,6 +245,72 @@ def supervise(script=None):
     return 1
 
 
+# ------------------------------------------------------------------------------------------ sample -> batch leg
+def data_path_leg(dev, B, reps=30):
+    """Informational: the sample -> batch path (pose2room_b200/dataloader.py) at the BASELINE shape.
+    96 raw samples of 1100-1500 frames resident in HBM; every launch builds a batch of B augmented sequences from a
+    different third of them into a different set of output buffers (264 MB rotating footprint > the 126 MB L2).
+    `kernel_*` = the p2r_make_batch launch alone (CUDA events), `loader_*` = the public make_batch call including the
+    host-side draws, box labels and parameter upload (wall clock around a synchronised loop)."""
+    from pose2room_b200 import _lib, dataloader as DL
+    rng = np.random.default_rng(99)
+    n = 3 * B
+    frames = rng.integers(1100, 1500, size=n)
+    frame_start = np.zeros(n + 1, np.int64)
+    frame_start[1:] = np.cumsum(frames)
+    F = int(frame_start[-1])
+    joints = rng.standard_normal((F, JOINTS, 3), dtype=np.float32)
+    votes = rng.standard_normal((F, JOINTS, 10), dtype=np.float32)
+    votes[..., 0] = rng.integers(0, 2, size=(F, JOINTS))
+    R = np.tile(np.eye(3, dtype=np.float32), (n, 10, 1, 1))
+    store = DL.PackedSamples(joints, votes, frame_start, np.full(n, 10, np.int32), np.zeros((n, 10), np.int32),
+                             rng.standard_normal((n, 10, 3)).astype(np.float32), R,
+                             rng.uniform(0.2, 1.7, (n, 10, 3)).astype(np.float32), ["s%d" % i for i in range(n)])
+
+    class _Cfg:
+        config = {"data": {"num_frames": T_FRAMES, "no_height": True, "max_gt_boxes": 10}}
+        dataset_config = None
+    ds = DL.P2RNet_VirtualHome(_Cfg(), "train", packed=store, device=dev)
+    sets = [list(range(k * B, (k + 1) * B)) for k in range(3)]
+    for k in range(3):
+        ds.make_batch(sets[k])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        ds.make_batch(sets[i % 3])
+    torch.cuda.synchronize()
+    loader_ms = (time.perf_counter() - t0) / reps * 1e3
+    # the launch alone, inputs already on the device
+    jd, vd, fsd = store.device_arrays(dev)
+    draws = [[DL.draw_augmentation() for _ in range(B)] for _ in range(3)]
+    params = [torch.from_numpy(ds.host_side(sets[k], draws[k])[0]).to(dev) for k in range(3)]
+    ids = [torch.tensor(sets[k], dtype=torch.int32, device=dev) for k in range(3)]
+    outs = [(torch.empty(B, T_FRAMES, JOINTS, 3, device=dev), torch.empty(B, T_FRAMES, JOINTS, 9, device=dev),
+             torch.empty(B, T_FRAMES, JOINTS, dtype=torch.int64, device=dev)) for _ in range(3)]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(k):
+        _lib.call("p2r_make_batch", jd.data_ptr(), vd.data_ptr(), fsd.data_ptr(), ids[k].data_ptr(), params[k].data_ptr(),
+                  B, T_FRAMES, JOINTS, 3, outs[k][0].data_ptr(), outs[k][1].data_ptr(), outs[k][2].data_ptr(), stream)
+    for k in range(3):
+        launch(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        launch(i % 3)
+    e1.record()
+    torch.cuda.synchronize()
+    kernel_ms = e0.elapsed_time(e1) / reps
+    algo_bytes = B * T_FRAMES * JOINTS * (13 * 4 + 12 * 4 + 8)      # 52 B read + 56 B written per (frame, joint)
+    peaks = measured_peaks()
+    return {"what": "sample -> batch (frame picking + flip/rotate/translate + casts + collate) from HBM-resident raw samples",
+            "kernel_ms": kernel_ms, "kernel_GBps": algo_bytes / (kernel_ms * 1e-3) / 1e9,
+            "kernel_frac_of_hbm_peak": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": algo_bytes,
+            "loader_ms_per_batch": loader_ms, "loader_sequences_per_s": B / (loader_ms * 1e-3),
+            "h2d_bytes_per_batch": B * (16 * 8 + 4 + 10 * 9 * 4 + 10 * 8)}
+
+
 # ------------------------------------------------------------------------------------------ our arm (GPU)
 def main():
     args = parse()
@@ -504,6 +570,14 @@ def main():
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     beat("end-to-end leg done")
 
+    data_path = None
+    if rank == 0 and world == 1 and os.environ.get("P2R_BENCH_DATA_PATH", "1") != "0":
+        try:
+            data_path = data_path_leg(dev, B)
+        except Exception as e:      # informational leg: report, never lose the headline line over it
+            data_path = {"error": repr(e)}
+        beat("data-path leg done")
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -524,7 +598,7 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "data_path": data_path,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
