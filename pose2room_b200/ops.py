@@ -314,7 +314,7 @@ def linear(x, weight, bias=None, relu=False, sparsity=None, want_stats=False):
 # column sums of a gradient tensor produced as a by-product by the BatchNorm backward that wrote it (keyed by data_ptr,
 # consumed by the layer before it in the same backward pass: the bias gradient of the graph convolution)
 _COLSUM = {}
-# OFF by default: the kernel is correct in isolation and in an eager step (tests, tools_dbg_hang.py), but bench.py's
+# OFF by default: the kernel is correct in isolation and in an eager step (tests), but bench.py's
 # back-to-back warm-up steps did not finish with it enabled (two runs, cause not established) -- see DESIGN.md section 3.
 _FUSED_COLSUM = os.environ.get("P2R_FUSED_COLSUM", "0") != "0"
 

@@ -1,4 +1,9 @@
 """BN kernel microbench on the block-activation shape [819200, 64] bf16 (diagnostic)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import os, sys, json
 import torch
 import torch.nn as nn

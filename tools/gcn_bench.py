@@ -1,5 +1,10 @@
 """Graph-convolution GEMM microbench (diagnostic, not the bench.py contract): dense vs block-sparse k-lists vs fused
 statistics, forward / dx / dW, per tile width, next to cuBLAS dense on the same shape."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import json
 
 import numpy as np
@@ -7,7 +12,7 @@ import torch
 
 from pose2room_b200 import gemm_sm100
 from pose2room_b200.p2rnet.graph import layout_for_joints, spatial_adjacency
-from tools_gemm_bench import timeit
+from gemm_bench import timeit
 
 
 def main():

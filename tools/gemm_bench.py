@@ -1,4 +1,9 @@
 """GEMM microbench (not the bench.py contract): our tcgen05 kernel vs cuBLAS (torch.matmul) on the hot-path shapes."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import json
 import sys
 

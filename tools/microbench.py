@@ -1,6 +1,11 @@
 """Operator microbench (not the bench.py contract): times each native op with CUDA events on the live and the
 large-cloud shapes, next to the unmodified reference kernels from oracle/_ref when present.
-Usage (GPU box): python tools_microbench.py > gpurun_out/microbench.json"""
+Usage (GPU box): python microbench.py > gpurun_out/microbench.json"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import json
 import sys
 

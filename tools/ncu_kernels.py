@@ -1,4 +1,9 @@
 """Launches the hot kernels at their BASELINE shapes a few times each (for `ncu --set full -k regex:...` captures)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import torch
 import torch.nn as nn
 

@@ -1,4 +1,9 @@
 """Launches the graph-conv GEMM variants a few times each for an `ncu --set full` capture (diagnostic)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import numpy as np
 import torch
 

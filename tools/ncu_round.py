@@ -1,4 +1,9 @@
 """Launches each hot kernel of the train step once or twice at its BASELINE shape (for one `ncu --set full` capture)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import numpy as np
 import torch
 import torch.nn as nn

@@ -1,8 +1,13 @@
 """Isolate what bounds the CTA-pair GEMM: full kernel vs no stores / no MMAs / no bias (diagnostic)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import json
 import torch
 from pose2room_b200 import gemm_sm100
-from tools_gemm_bench import timeit
+from gemm_bench import timeit
 dev = torch.device("cuda:0")
 M, N = 32768, 1600
 x = torch.randn(M, N, device=dev).bfloat16()

@@ -1,5 +1,10 @@
 """Kernel timeline of ONE replay of the captured train-step graph (torch.profiler / CUPTI): busy vs idle time,
 per-stream time, largest gaps.  Diagnostic only -- not a bench number."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import json
 import sys
 

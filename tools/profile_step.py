@@ -1,4 +1,9 @@
 """Per-kernel time table of one train step (torch.profiler / CUPTI). Diagnostic only -- not a bench number."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import sys
 
 import numpy as np

@@ -1,3 +1,8 @@
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root (run as `python tools/<name>.py`)
+
 import sys, traceback; sys.path.insert(0, '.')
 import numpy as np, torch
 from pose2room_b200 import gemm_sm100, ops, synthetic

@@ -1,8 +1,13 @@
 """Summarise ncu outputs into the small text/csv files kept under profiles/ (run here, on the CPU box).
 
-  python tools_summarize_ncu.py launches gpurun_out/launches.csv profiles/r01_launch_list_summary.csv "<command>"
-  python tools_summarize_ncu.py full gpurun_out/round_prof.ncu-rep profiles/r01_ncu_kernels_summary.txt
+  python summarize_ncu.py launches gpurun_out/launches.csv profiles/r01_launch_list_summary.csv "<command>"
+  python summarize_ncu.py full gpurun_out/round_prof.ncu-rep profiles/r01_ncu_kernels_summary.txt
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (run as `python tools/<name>.py`)
+
 import csv
 import io
 import re
