@@ -38,7 +38,15 @@ def _worker(rank, world, port, out):
     calc.gt_map_cls = {0: [(rank, np.full((8, 3), float(rank)))]}
     calc.scan_cnt = 1
     parallel.gather_ap_state(calc)
-    torch.save(dict(w0=w0, local=local, reduced=reduced, scans=calc.scan_cnt,
+    # sample -> batch path: the loader shards the split with the reference's DistributedSampler (dataloader.py:179-180)
+    from pose2room_b200 import dataloader as DL, synthetic
+    from tests.dataloader_helpers import Cfg
+    rng = np.random.default_rng(0)                                        # the same split on every rank
+    store = DL.PackedSamples.from_samples([synthetic.make_raw_sample(rng, 6, 25, name="n%d" % i) for i in range(9)])
+    loader = DL.P2RNet_dataloader(Cfg(num_frames=4, batch_size=2, distributed=True), "train", packed=store)
+    loader.sampler.set_epoch(3)                                           # train_epoch.py:24-25
+    shard = [i for b in loader.dataloader.batch_sampler for i in b]
+    torch.save(dict(w0=w0, local=local, reduced=reduced, scans=calc.scan_cnt, shard=shard, batches=len(loader.dataloader),
                     classes=sorted(v[0][0] for v in calc.gt_map_cls.values())), os.path.join(out, "r%d.pt" % rank))
     dist.destroy_process_group()
 
@@ -55,6 +63,10 @@ def test_broadcast_allreduce_and_ap_gather_world2(tmp_path):
         assert torch.allclose(a, want, rtol=1e-12, atol=1e-12), i               # ... and it is the mean
     assert r[0]["reduced"][-1].dtype == torch.float32 and torch.allclose(r[0]["reduced"][-1], torch.full((4,), 1.5))
     assert r[0]["scans"] == 2 and r[0]["classes"] == [0, 1] and r[1]["classes"] == [0, 1]
+    # 9 samples over 2 ranks: 5 each (one padded duplicate, like the reference), disjoint otherwise, 3 batches of <= 2
+    assert len(r[0]["shard"]) == len(r[1]["shard"]) == 5 and r[0]["batches"] == r[1]["batches"] == 3
+    assert set(r[0]["shard"]) | set(r[1]["shard"]) == set(range(9))
+    assert len(set(r[0]["shard"]) & set(r[1]["shard"])) <= 1
 
 
 def test_single_process_is_a_no_op():
