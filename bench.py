@@ -246,12 +246,14 @@ def supervise(script=None):
 
 
 # ------------------------------------------------------------------------------------------ sample -> batch leg
-def data_path_leg(dev, B, reps=30):
+def data_path_leg(dev, B, reps=30, train_step=None, steps=10):
     """Informational: the sample -> batch path (pose2room_b200/dataloader.py) at the BASELINE shape.
     96 raw samples of 1100-1500 frames resident in HBM; every launch builds a batch of B augmented sequences from a
     different third of them into a different set of output buffers (264 MB rotating footprint > the 126 MB L2).
     `kernel_*` = the p2r_make_batch launch alone (CUDA events), `loader_*` = the public make_batch call including the
-    host-side draws, box labels and parameter upload (wall clock around a synchronised loop)."""
+    host-side draws, box labels and parameter upload (wall clock around a synchronised loop), `train_from_loader_*` =
+    the same train step as the headline fed by that loader (make_batch -> step -> loss read back each step; the
+    46 MB-per-step host -> device copy of the contract's `e2e` leg is replaced by 18 KB of parameters and labels)."""
     from pose2room_b200 import _lib, dataloader as DL
     rng = np.random.default_rng(99)
     n = 3 * B
@@ -304,11 +306,24 @@ def data_path_leg(dev, B, reps=30):
     kernel_ms = e0.elapsed_time(e1) / reps
     algo_bytes = B * T_FRAMES * JOINTS * (13 * 4 + 12 * 4 + 8)      # 52 B read + 56 B written per (frame, joint)
     peaks = measured_peaks()
-    return {"what": "sample -> batch (frame picking + flip/rotate/translate + casts + collate) from HBM-resident raw samples",
+    train = {}
+    if train_step is not None:
+        for i in range(2):
+            train_step(ds.make_batch(sets[i % 3])).item()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(steps):
+            train_step(ds.make_batch(sets[i % 3])).item()
+        g1.record()
+        torch.cuda.synchronize()
+        t_ms = g0.elapsed_time(g1) / steps
+        train = {"train_from_loader_ms_per_step": t_ms, "train_from_loader_sequences_per_s": B / (t_ms * 1e-3)}
+    return dict(train, **{"what": "sample -> batch (frame picking + flip/rotate/translate + casts + collate) from HBM-resident raw samples",
             "kernel_ms": kernel_ms, "kernel_GBps": algo_bytes / (kernel_ms * 1e-3) / 1e9,
             "kernel_frac_of_hbm_peak": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": algo_bytes,
             "loader_ms_per_batch": loader_ms, "loader_sequences_per_s": B / (loader_ms * 1e-3),
-            "h2d_bytes_per_batch": B * (16 * 8 + 4 + 10 * 9 * 4 + 10 * 8)}
+            "h2d_bytes_per_batch": B * (16 * 8 + 4 + 10 * 9 * 4 + 10 * 8)})
 
 
 # ------------------------------------------------------------------------------------------ our arm (GPU)
@@ -573,7 +588,7 @@ def main():
     data_path = None
     if rank == 0 and world == 1 and os.environ.get("P2R_BENCH_DATA_PATH", "1") != "0":
         try:
-            data_path = data_path_leg(dev, B)
+            data_path = data_path_leg(dev, B, train_step=step, steps=args.steps)
         except Exception as e:      # informational leg: report, never lose the headline line over it
             data_path = {"error": repr(e)}
         beat("data-path leg done")
