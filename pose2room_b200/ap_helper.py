@@ -121,38 +121,61 @@ def _voc_ap(rec, prec):
     return np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
 
 
+# Pairwise IoU is only ever needed between a detection and the ground-truth boxes of ITS OWN scene.  Scenes are packed
+# into chunks whose (detections x ground truths) rectangle stays below this many entries, one IoU launch per chunk:
+# the waste is the off-diagonal part of each chunk instead of the whole (all detections x all ground truths) matrix,
+# which at 10 k scenes would be ~2 GB of float64 per class.
+_IOU_CHUNK_ENTRIES = 1 << 22
+
+
+def _same_scene_iou_rows(pred, gt):
+    """pred: {img: [(box, score), ...]}, gt: {img: [box, ...]} of one class -> {img: (n_det_img, n_gt_img) float64
+    ndarray} for the scenes that have both detections and ground truth."""
+    imgs = [img for img in pred if len(pred[img]) and len(gt.get(img, ()))]
+    out = {}
+    start = 0
+    while start < len(imgs):
+        end, np_, ng_ = start, 0, 0
+        while end < len(imgs):
+            a, b = len(pred[imgs[end]]), len(gt[imgs[end]])
+            if end > start and (np_ + a) * (ng_ + b) > _IOU_CHUNK_ENTRIES:
+                break
+            np_, ng_, end = np_ + a, ng_ + b, end + 1
+        chunk = imgs[start:end]
+        det = np.stack([box for img in chunk for box, _ in pred[img]])
+        gtb = np.stack([box for img in chunk for box in gt[img]])
+        iou = geometry.box3d_iou_matrix(det, gtb)[0].cpu().numpy()
+        r = c = 0
+        for img in chunk:
+            a, b = len(pred[img]), len(gt[img])
+            out[img] = iou[r:r + a, c:c + b]
+            r, c = r + a, c + b
+        start = end
+    return out
+
+
 def _eval_class(pred, gt, ovthresh):
-    """eval_det.py:259-343 for one class with the pairwise OBB IoU computed on the GPU in one launch."""
+    """eval_det.py:259-343 for one class; the OBB IoUs come from the GPU, a launch per chunk of scenes."""
     npos = sum(len(v) for v in gt.values())
     claimed = {img: [False] * len(v) for img, v in gt.items()}
-    ids, conf, boxes = [], [], []
+    ids, conf, local = [], [], []
     for img, lst in pred.items():
-        for box, score in lst:
+        for j, (box, score) in enumerate(lst):
             ids.append(img)
             conf.append(score)
-            boxes.append(box)
+            local.append(j)                      # row of this detection in its scene's IoU block
     nd = len(ids)
     tp = np.zeros(nd)
     fp = np.zeros(nd)
     if nd:
-        gt_imgs = [img for img, v in gt.items() if len(v)]
-        gt_boxes = [b for img in gt_imgs for b in gt[img]]
-        offs = {}
-        o = 0
-        for img in gt_imgs:
-            offs[img] = (o, o + len(gt[img]))
-            o += len(gt[img])
-        iou = None
-        if gt_boxes:
-            iou = geometry.box3d_iou_matrix(np.stack(boxes), np.stack(gt_boxes))[0].cpu().numpy()
+        blocks = _same_scene_iou_rows(pred, gt)
         order = np.argsort(-np.asarray(conf))
         for d, k in enumerate(order):
             img = ids[k]
             ovmax, jmax = -np.inf, -1
-            if img in offs:
-                lo, hi = offs[img]
-                row = iou[k, lo:hi]
-                for j in range(hi - lo):  # first strict maximum, like the reference's `if iou > ovmax`
+            if img in blocks:
+                row = blocks[img][local[k]]
+                for j in range(row.shape[0]):  # first strict maximum, like the reference's `if iou > ovmax`
                     if row[j] > ovmax:
                         ovmax, jmax = row[j], j
             if ovmax > ovthresh and not claimed[img][jmax]:
