@@ -124,7 +124,8 @@ class PackedSamples:
         ship the pack."""
         try:
             import h5py
-        except ImportError as e:
+            h5py.File
+        except (ImportError, AttributeError) as e:      # absent, or a stub module standing in for it
             raise ImportError("h5py is needed to read the reference's .hdf5 samples; pack them on a machine "
                               "that has it (PackedSamples.from_hdf5(...).save(path)) and load the pack here") from e
 
