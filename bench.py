@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("P2R_PRECISION", "auto"), choices=["auto", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--data-path-variants", action="store_true", help="internal: A/B of the make_batch kernel variants")
     return ap.parse_args()
 
 
@@ -214,6 +215,26 @@ def start_watchdog():
     threading.Thread(target=run, daemon=True).start()
 
 
+def _variants_subprocess(script):
+    """Kernel-variant A/B of the sample -> batch path in a process of its own, bounded in time; never raises."""
+    import signal
+    if os.environ.get("P2R_BENCH_VARIANTS", "1") == "0":
+        return None
+    try:
+        p = subprocess.Popen([sys.executable, script, "--data-path-variants"], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=float(os.environ.get("P2R_BENCH_VARIANTS_TIMEOUT_S", "120")))
+        except subprocess.TimeoutExpired:
+            os.killpg(p.pid, signal.SIGKILL)
+            p.wait()
+            return {"error": "timed out"}
+        lines = [l for l in out.decode().splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"error": "no output (exit code %s)" % p.returncode}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def supervise(script=None):
     import signal
     script = script or os.path.abspath(__file__)
@@ -231,12 +252,12 @@ def supervise(script=None):
             continue
         lines = [l for l in out.decode().splitlines() if l.startswith("{")]
         if p.returncode == 0 and lines:
-            if label is None:
-                print(lines[-1], flush=True)
-            else:
-                d = json.loads(lines[-1])
+            d = json.loads(lines[-1])
+            if label is not None:
                 d["config"]["fallback"] = label
-                print(json.dumps(d), flush=True)
+            if isinstance(d.get("data_path"), dict) and "error" not in d["data_path"]:
+                d["data_path"]["variants"] = _variants_subprocess(script)
+            print(json.dumps(d), flush=True)
             return 0
         if p.returncode != 17:          # a real failure, not a stall: do not hide it behind a retry
             sys.stdout.write(out.decode())
@@ -246,15 +267,10 @@ def supervise(script=None):
 
 
 # ------------------------------------------------------------------------------------------ sample -> batch leg
-def data_path_leg(dev, B, reps=30, train_step=None, steps=10):
-    """Informational: the sample -> batch path (pose2room_b200/dataloader.py, SURVEY 8f row 2) at the BASELINE shape.
-    96 raw samples of 1100-1500 frames resident in HBM; every launch builds a batch of B augmented sequences from a
-    different third of them into a different set of output buffers (264 MB rotating footprint > the 126 MB L2).
-    `kernel_*` = the p2r_make_batch launch alone (CUDA events), `loader_*` = the public make_batch call including the
-    host-side draws, box labels and parameter upload (wall clock around a synchronised loop), `train_from_loader_*` =
-    the same train step as the headline fed by that loader (make_batch -> step -> loss read back each step; the
-    46 MB-per-step host -> device copy of the contract's `e2e` leg is replaced by 18 KB of parameters and labels)."""
-    from pose2room_b200 import _lib, dataloader as DL
+def _data_path_store(dev, B):
+    """96 synthetic raw samples (random values: the kernel's work does not depend on them) of 1100-1500 frames each,
+    packed, plus the train-mode dataset over them."""
+    from pose2room_b200 import dataloader as DL
     rng = np.random.default_rng(99)
     n = 3 * B
     frames = rng.integers(1100, 1500, size=n)
@@ -272,7 +288,70 @@ def data_path_leg(dev, B, reps=30, train_step=None, steps=10):
     class _Cfg:
         config = {"data": {"num_frames": T_FRAMES, "no_height": True, "max_gt_boxes": 10}}
         dataset_config = None
-    ds = DL.P2RNet_VirtualHome(_Cfg(), "train", packed=store, device=dev)
+    return store, DL.P2RNet_VirtualHome(_Cfg(), "train", packed=store, device=dev)
+
+
+def data_path_variants(B=B_PER_GPU, reps=30):
+    """A/B of the two data-movement variants of the make_batch kernel (csrc/dataloader_ops.cu) on the data_path_leg
+    workload.  Runs in its OWN process (the supervisor starts it after the headline measurement has been printed by the
+    measuring child), because variant 2 had not run on a GPU when this was written: whatever it does cannot touch the
+    headline numbers.  Prints one JSON object."""
+    from pose2room_b200 import _lib, dataloader as DL
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    store, ds = _data_path_store(dev, B)
+    jd, vd, fsd = store.device_arrays(dev)
+    sets = [list(range(k * B, (k + 1) * B)) for k in range(3)]
+    draws = [[DL.draw_augmentation() for _ in range(B)] for _ in range(3)]
+    params = [torch.from_numpy(ds.host_side(sets[k], draws[k])[0]).to(dev) for k in range(3)]
+    ids = [torch.tensor(sets[k], dtype=torch.int32, device=dev) for k in range(3)]
+    stream = torch.cuda.current_stream().cuda_stream
+    algo_bytes = B * T_FRAMES * JOINTS * (13 * 4 + 12 * 4 + 8)
+    peaks = measured_peaks()
+    out, ref = {}, None
+    for variant in (1, 2):
+        try:
+            outs = [(torch.empty(B, T_FRAMES, JOINTS, 3, device=dev), torch.empty(B, T_FRAMES, JOINTS, 9, device=dev),
+                     torch.empty(B, T_FRAMES, JOINTS, dtype=torch.int64, device=dev)) for _ in range(3)]
+
+            def launch(k):
+                _lib.call("p2r_make_batch_variant", variant, jd.data_ptr(), vd.data_ptr(), fsd.data_ptr(), ids[k].data_ptr(),
+                          params[k].data_ptr(), B, T_FRAMES, JOINTS, 3, outs[k][0].data_ptr(), outs[k][1].data_ptr(),
+                          outs[k][2].data_ptr(), stream)
+            for k in range(3):
+                launch(k)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                launch(i % 3)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            rec = {"kernel_ms": ms, "kernel_GBps": algo_bytes / (ms * 1e-3) / 1e9,
+                   "kernel_frac_of_hbm_peak": algo_bytes / (ms * 1e-3) / 1e9 / peaks["hbm"]}
+            if ref is None:
+                ref = outs
+            else:
+                rec["bit_identical_to_v1"] = all(torch.equal(a, b) for o, r in zip(outs, ref) for a, b in zip(o, r))
+            out["v%d" % variant] = rec
+        except Exception as e:
+            out["v%d" % variant] = {"error": repr(e)}
+            break
+    print(json.dumps(out), flush=True)
+
+
+def data_path_leg(dev, B, reps=30, train_step=None, steps=10):
+    """Informational: the sample -> batch path (pose2room_b200/dataloader.py, SURVEY 8f row 2) at the BASELINE shape.
+    96 raw samples of 1100-1500 frames resident in HBM; every launch builds a batch of B augmented sequences from a
+    different third of them into a different set of output buffers (264 MB rotating footprint > the 126 MB L2).
+    `kernel_*` = the p2r_make_batch launch alone (CUDA events), `loader_*` = the public make_batch call including the
+    host-side draws, box labels and parameter upload (wall clock around a synchronised loop), `train_from_loader_*` =
+    the same train step as the headline fed by that loader (make_batch -> step -> loss read back each step; the
+    46 MB-per-step host -> device copy of the contract's `e2e` leg is replaced by 18 KB of parameters and labels)."""
+    from pose2room_b200 import _lib, dataloader as DL
+    store, ds = _data_path_store(dev, B)
     sets = [list(range(k * B, (k + 1) * B)) for k in range(3)]
     for k in range(3):
         ds.make_batch(sets[k])
@@ -331,6 +410,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.data_path_variants:
+        return data_path_variants(args.batch)
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 and os.environ.get("P2R_BENCH_CHILD") != "1" and \
             os.environ.get("P2R_BENCH_SUPERVISE", "1") != "0":
         sys.exit(supervise())

@@ -15,6 +15,7 @@
 #include "p2r_common.cuh"
 #include "p2r_b200.h"
 #include "augment_math.h"
+#include <stdlib.h>
 
 #define P2R_DL_FRAMES 8
 #define P2R_DL_THREADS 256
@@ -76,14 +77,146 @@ make_batch_kernel(const float* __restrict__ joints, const float* __restrict__ vo
   for (int i = threadIdx.x; i < nf * J; i += P2R_DL_THREADS) gm[i] = s_mask[i];
 }
 
-extern "C" int p2r_make_batch(const float* joints, const float* votes, const long long* frame_start,
-                              const int* sample_ids, const double* params, int b, int num_frames, int j,
-                              int out_channels, float* input_joints, float* vote_label,
-                              long long* vote_label_mask, void* stream) {
+// ---------------------------------------------------------------------------------------------------------------
+// Variant 2 (opt-in until it has been measured against variant 1 on a B200: bench.py's data_path.variants A/B).
+// Same arithmetic, different data movement: persistent CTAs walk over (batch item, group of 8 frames) work items with
+// a 3-stage cp.async ring, so the raw rows of the next two groups are in flight (no registers, no thread waiting on
+// them) while the current group is transformed and stored -- variant 1 exposes the full load latency of every CTA.
+// One warp per frame: a warp copies its frame's two rows (joints in 4-byte, votes in 8-byte pieces: raw frames are
+// only 4- / 8-byte aligned), then transforms that frame's joints.  Only __syncthreads and cp.async.wait_group: there
+// is no spin-wait in this kernel.
+#define P2R_DL_STAGES 3
+
+__device__ __forceinline__ void p2r_cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(p2r_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void p2r_cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(p2r_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void p2r_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void p2r_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(P2R_DL_THREADS)
+make_batch_pipe_kernel(const float* __restrict__ joints, const float* __restrict__ votes,
+                       const long long* __restrict__ frame_start, const int* __restrict__ sample_ids,
+                       const double* __restrict__ params, int num_frames, int J, int out_c, int groups_per_item,
+                       int total_groups, float* __restrict__ input_joints, float* __restrict__ vote_label,
+                       long long* __restrict__ vote_label_mask) {
+  static_assert(P2R_DL_THREADS == 32 * P2R_DL_FRAMES, "one warp per frame of a group");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int rowj = J * 3, rowv = J * 10, rowo = J * out_c, rowl = J * 9;
+  // layout (8-byte quantities first): mask | stage[3] { votes rows | joint rows } | out joints | out votes
+  long long* s_mask = reinterpret_cast<long long*>(smem_raw);                      // [FR * J]
+  float* s_stage = reinterpret_cast<float*>(s_mask + P2R_DL_FRAMES * J);            // 8-byte aligned
+  const int stage_floats = P2R_DL_FRAMES * (rowv + rowj + (rowj & 1));              // keeps every stage 8-byte aligned
+  float* s_out_j = s_stage + P2R_DL_STAGES * stage_floats;
+  float* s_out_v = s_out_j + P2R_DL_FRAMES * rowo;
+  __shared__ double s_p[P2R_DL_STAGES][P2R_AUG_STRIDE];
+  __shared__ long long s_src[P2R_DL_STAGES][P2R_DL_FRAMES];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // (1) per work item: source frames + parameter block into slot `slot` (threads 0..7 and 32..47)
+  auto prepare = [&](int w, int slot) {
+    if (w >= total_groups) return;
+    const int b = w / groups_per_item, t0 = (w - b * groups_per_item) * P2R_DL_FRAMES;
+    if (threadIdx.x < P2R_DL_FRAMES && t0 + (int)threadIdx.x < num_frames) {
+      const int sample = sample_ids[b];
+      const long long f0 = frame_start[sample];
+      const int n_raw = (int)(frame_start[sample + 1] - f0);
+      s_src[slot][threadIdx.x] = f0 + p2r_frame_id(n_raw, num_frames, t0 + threadIdx.x);
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + P2R_AUG_STRIDE)
+      s_p[slot][threadIdx.x - 32] = params[(size_t)b * P2R_AUG_STRIDE + (threadIdx.x - 32)];
+  };
+  // (2) asynchronous copy of the raw rows of item w into stage `slot`: warp f copies frame f
+  auto issue = [&](int w, int slot) {
+    if (w < total_groups) {
+      const int b = w / groups_per_item, t0 = (w - b * groups_per_item) * P2R_DL_FRAMES;
+      if (t0 + warp < num_frames) {
+        const long long src = s_src[slot][warp];
+        float* dv = s_stage + slot * stage_floats + warp * rowv;
+        float* dj = s_stage + slot * stage_floats + P2R_DL_FRAMES * rowv + warp * rowj;
+        const float* gv = votes + src * rowv;        // 40 J bytes per frame: 8-byte aligned
+        const float* gj = joints + src * rowj;       // 12 J bytes per frame: 4-byte aligned
+        for (int c = lane; c < rowv / 2; c += 32) p2r_cp_async8(dv + 2 * c, gv + 2 * c);
+        for (int c = lane; c < rowj; c += 32) p2r_cp_async4(dj + c, gj + c);
+      }
+    }
+    p2r_cp_async_commit();     // always: the group count per iteration stays uniform
+  };
+
+  const int w0 = blockIdx.x, wstep = gridDim.x;
+#pragma unroll
+  for (int s = 0; s < P2R_DL_STAGES - 1; ++s) prepare(w0 + s * wstep, s);
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < P2R_DL_STAGES - 1; ++s) issue(w0 + s * wstep, s);
+
+  int k = 0;
+  for (int w = w0; w < total_groups; w += wstep, ++k) {
+    const int cur = k % P2R_DL_STAGES, nxt = (k + P2R_DL_STAGES - 1) % P2R_DL_STAGES;
+    prepare(w + (P2R_DL_STAGES - 1) * wstep, nxt);
+    __syncthreads();                               // slot nxt: written above, last read two syncs ago (item k-1)
+    issue(w + (P2R_DL_STAGES - 1) * wstep, nxt);
+    p2r_cp_async_wait<P2R_DL_STAGES - 1>();        // this thread's copies of item k have landed ...
+    __syncthreads();                               // ... and so have everybody else's
+    const int b = w / groups_per_item, t0 = (w - b * groups_per_item) * P2R_DL_FRAMES;
+    const int nf = min(P2R_DL_FRAMES, num_frames - t0);
+    if (warp < nf) {
+      const float* in_v = s_stage + cur * stage_floats + warp * rowv;
+      const float* in_j = s_stage + cur * stage_floats + P2R_DL_FRAMES * rowv + warp * rowj;
+      for (int j = lane; j < J; j += 32) {
+        float oj[4], ov[9];
+        const int i = warp * J + j;
+        s_mask[i] = p2r_augment_joint(in_j + j * 3, in_v + j * 10, s_p[cur], out_c, oj, ov);
+        for (int c = 0; c < out_c; ++c) s_out_j[(size_t)i * out_c + c] = oj[c];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) s_out_v[(size_t)i * 9 + c] = ov[c];
+      }
+    }
+    __syncthreads();
+    const size_t frame0 = (size_t)b * num_frames + t0;
+    float* gj = input_joints + frame0 * rowo;
+    for (int i = threadIdx.x; i < nf * rowo; i += P2R_DL_THREADS) gj[i] = s_out_j[i];
+    float* gv = vote_label + frame0 * rowl;
+    for (int i = threadIdx.x; i < nf * rowl; i += P2R_DL_THREADS) gv[i] = s_out_v[i];
+    long long* gm = vote_label_mask + frame0 * J;
+    for (int i = threadIdx.x; i < nf * J; i += P2R_DL_THREADS) gm[i] = s_mask[i];
+    // the next iteration's first __syncthreads orders these reads of s_out_* / s_mask before they are rewritten
+  }
+  p2r_cp_async_wait<0>();
+}
+
+static int make_batch_launch(int variant, const float* joints, const float* votes, const long long* frame_start,
+                             const int* sample_ids, const double* params, int b, int num_frames, int j, int out_channels,
+                             float* input_joints, float* vote_label, long long* vote_label_mask, void* stream) {
   P2R_CHECK_ARG(b >= 0 && num_frames >= 0 && j > 0, "p2r_make_batch");
   P2R_CHECK_ARG(out_channels == 3 || out_channels == 4, "p2r_make_batch");
   P2R_CHECK_ARG(b <= 65535, "p2r_make_batch");
+  P2R_CHECK_ARG(variant == 1 || variant == 2, "p2r_make_batch");
   if (b == 0 || num_frames == 0) return 0;
+  if (variant == 2) {
+    const int rowj = j * 3;
+    const size_t stage = (size_t)P2R_DL_FRAMES * (j * 10 + rowj + (rowj & 1)) * sizeof(float);
+    const size_t smem = (size_t)P2R_DL_FRAMES * j * sizeof(long long) + P2R_DL_STAGES * stage +
+                        (size_t)P2R_DL_FRAMES * j * (out_channels + 9) * sizeof(float);
+    P2R_CHECK_ARG(smem <= 200 * 1024, "p2r_make_batch");
+    cudaError_t e = cudaFuncSetAttribute(make_batch_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { p2r_set_last_error("p2r_make_batch", (int)e); return (int)e; }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, make_batch_pipe_kernel, P2R_DL_THREADS, smem);
+    if (e != cudaSuccess || per_sm < 1) { p2r_set_last_error("p2r_make_batch (occupancy query)", (int)e); return e ? (int)e : -1; }
+    const int groups_per_item = p2r_ceil_div(num_frames, P2R_DL_FRAMES);
+    const long long total = (long long)groups_per_item * b;
+    const long long resident = (long long)P2R_SM_COUNT * per_sm;
+    const int grid = (int)(total < resident ? total : resident);
+    make_batch_pipe_kernel<<<grid, P2R_DL_THREADS, smem, (cudaStream_t)stream>>>(
+        joints, votes, frame_start, sample_ids, params, num_frames, j, out_channels, groups_per_item, (int)total,
+        input_joints, vote_label, vote_label_mask);
+    P2R_RETURN_LAUNCH("p2r_make_batch");
+  }
   const size_t smem = (size_t)P2R_DL_FRAMES * j * (sizeof(long long) + sizeof(float) * (3 + 10 + out_channels + 9));
   P2R_CHECK_ARG(smem <= 200 * 1024, "p2r_make_batch");
   if (smem > 48 * 1024) {
@@ -95,4 +228,25 @@ extern "C" int p2r_make_batch(const float* joints, const float* votes, const lon
       joints, votes, frame_start, sample_ids, params, num_frames, j, out_channels, input_joints, vote_label,
       vote_label_mask);
   P2R_RETURN_LAUNCH("p2r_make_batch");
+}
+
+extern "C" int p2r_make_batch(const float* joints, const float* votes, const long long* frame_start,
+                              const int* sample_ids, const double* params, int b, int num_frames, int j,
+                              int out_channels, float* input_joints, float* vote_label,
+                              long long* vote_label_mask, void* stream) {
+  static int variant = 0;
+  if (variant == 0) {
+    const char* e = getenv("P2R_MAKE_BATCH_VARIANT");
+    variant = (e != nullptr && atoi(e) == 2) ? 2 : 1;
+  }
+  return make_batch_launch(variant, joints, votes, frame_start, sample_ids, params, b, num_frames, j, out_channels,
+                           input_joints, vote_label, vote_label_mask, stream);
+}
+
+extern "C" int p2r_make_batch_variant(int variant, const float* joints, const float* votes, const long long* frame_start,
+                                      const int* sample_ids, const double* params, int b, int num_frames, int j,
+                                      int out_channels, float* input_joints, float* vote_label,
+                                      long long* vote_label_mask, void* stream) {
+  return make_batch_launch(variant, joints, votes, frame_start, sample_ids, params, b, num_frames, j, out_channels,
+                           input_joints, vote_label, vote_label_mask, stream);
 }

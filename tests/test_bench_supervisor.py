@@ -56,3 +56,41 @@ def test_healthy_child_line_is_passed_through_unchanged(tmp_path, monkeypatch, c
         print('{"value": 3.5, "config": {"workload": "w"}}')
     ''', monkeypatch, capsys, timeout="30")
     assert rc == 0 and io.out.strip() == '{"value": 3.5, "config": {"workload": "w"}}'
+
+
+def test_variant_ab_runs_in_its_own_process_and_cannot_lose_the_line(tmp_path, monkeypatch, capsys):
+    """The kernel-variant A/B of the sample -> batch path is merged into data_path.variants when it succeeds and becomes
+    an {"error": ...} entry when its process crashes, prints nothing or hangs -- the headline line survives every time."""
+    body = '''
+        import json, os, sys, time
+        if "--data-path-variants" in sys.argv:
+            mode = os.environ["FAKE_VARIANTS"]
+            if mode == "ok":
+                print(json.dumps({"v1": {"kernel_ms": 0.05}, "v2": {"kernel_ms": 0.02, "bit_identical_to_v1": True}}))
+            elif mode == "crash":
+                os.abort()
+            elif mode == "hang":
+                time.sleep(60)
+            sys.exit(0)
+        print(json.dumps({"value": 4.0, "config": {}, "data_path": {"kernel_ms": 0.05}}))
+    '''
+    monkeypatch.setenv("FAKE_VARIANTS", "ok")
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    d = json.loads(io.out.strip())
+    assert rc == 0 and d["value"] == 4.0 and d["data_path"]["variants"]["v2"]["bit_identical_to_v1"] is True
+    monkeypatch.setenv("FAKE_VARIANTS", "crash")
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    d = json.loads(io.out.strip())
+    assert rc == 0 and d["value"] == 4.0 and "error" in d["data_path"]["variants"]
+    monkeypatch.setenv("FAKE_VARIANTS", "hang")
+    monkeypatch.setenv("P2R_BENCH_VARIANTS_TIMEOUT_S", "2")
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    d = json.loads(io.out.strip())
+    assert rc == 0 and d["value"] == 4.0 and d["data_path"]["variants"] == {"error": "timed out"}
+    # a failed data-path leg in the child (or none at all) starts no second process
+    rc, io = _run(tmp_path, '''
+        import sys
+        assert "--data-path-variants" not in sys.argv
+        print('{"value": 5.0, "config": {}, "data_path": {"error": "boom"}}')
+    ''', monkeypatch, capsys, timeout="30")
+    assert rc == 0 and json.loads(io.out.strip())["data_path"] == {"error": "boom"}

@@ -132,3 +132,19 @@ def test_full_size_properties_and_loader(cuda):
         want = R.get_item(samples[order[b]], draws[b], T)
         for k in H.KEYS:
             H.assert_same(got[k][b], want[k], "full/%d/%s" % (b, k))
+
+
+@pytest.mark.xfail(strict=False, reason="variant 2 of the kernel (persistent CTAs, cp.async ring) was written after the "
+                                        "round's GPU budget was spent: checked here in a process of its own, non-gating "
+                                        "until it has passed on a B200 and been timed (bench.py data_path.variants)")
+def test_pipelined_variant_passes_the_same_three_tests(cuda):
+    import os
+    import subprocess
+    import sys
+    code = ("import torch, tests.test_dataloader_gpu as T; dev = torch.device('cuda:0'); "
+            "T.test_make_batch_matches_reference_goldens(dev); T.test_ragged_batches_vs_oracle(dev); "
+            "T.test_full_size_properties_and_loader(dev); print('VARIANT2-OK')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, P2R_MAKE_BATCH_VARIANT="2"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "VARIANT2-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
