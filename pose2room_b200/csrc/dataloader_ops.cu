@@ -198,6 +198,8 @@ static int make_batch_launch(int variant, const float* joints, const float* vote
   P2R_CHECK_ARG(variant == 1 || variant == 2, "p2r_make_batch");
   if (b == 0 || num_frames == 0) return 0;
   if (variant == 2) {
+    P2R_CHECK_ARG((reinterpret_cast<uintptr_t>(votes) & 7) == 0 && (reinterpret_cast<uintptr_t>(joints) & 3) == 0,
+                  "p2r_make_batch (variant 2 copies votes in 8-byte pieces)");
     const int rowj = j * 3;
     const size_t stage = (size_t)P2R_DL_FRAMES * (j * 10 + rowj + (rowj & 1)) * sizeof(float);
     const size_t smem = (size_t)P2R_DL_FRAMES * j * sizeof(long long) + P2R_DL_STAGES * stage +
