@@ -247,6 +247,36 @@ int p2r_make_batch_variant(int variant, const float* joints, const float* votes,
                            const int* sample_ids, const double* params, int b, int num_frames, int j, int out_channels,
                            float* input_joints, float* vote_label, long long* vote_label_mask, void* stream);
 
+/* ---- detection loss (ref: models/loss.py:42-189 BoxNetDetectionLoss) ------------------------------------------------
+ * The whole loss in one launch (csrc/loss_ops.cu, arithmetic in csrc/loss_math.h): vote loss (compute_vote_loss, :90-115),
+ * proposal <-> ground-truth correspondence + objectness (compute_correspondence, :117-150), centre / size / heading /
+ * class losses (compute_box_and_sem_cls_loss, :42-88) and the statistics of __call__ (:152-189).
+ * Predictions: vote_xyz f32 [B,S,3]; center, size, agg (aggregated_vote_xyz) f32 [B,P,3]; heading [B,P,2] float64 when
+ * heading_f64 else float32; obj f32 [B,P,2] and sem f32 [B,P,C] with ROW strides obj_stride / sem_stride in elements (the
+ * two are slices of one [B,P,2+C] tensor in the model); skeleton (seed_skeleton) f32 [B,S,J,3]; seed_inds i64 [B,S].
+ * Ground truth (the `data` dict, dataloader.py:137-146): vote_label f32 [B,T,J,9], vote_mask i64 [B,T,J], gt_center /
+ * gt_size f32 [B,G,3], gt_mask f32 [B,G], gt_heading f32 [B,G,2], gt_cls i64 [B,G]; origin = origin_joint_id.
+ * Outputs: out32 f32 [8] = vote, objectness, center, size, sem_cls loss, pos_ratio, neg_ratio, obj_acc; out64 f64 [2] =
+ * heading loss, total (float64 in the reference too: the heading mixture is float64); scales f64 [4] and the
+ * un-normalised gradients u_* (shapes of the matching predictions; u_c1 / u_c2: the two halves of the centre loss) for
+ * p2r_detection_loss_grad.  workspace: p2r_detection_loss_workspace(b, s) doubles, ZEROED by the caller.            */
+long long p2r_detection_loss_workspace(int b, int s);
+int p2r_detection_loss(const float* vote_xyz, const float* center, const float* size, const void* heading,
+                       int heading_f64, const float* obj, int obj_stride, const float* sem, int sem_stride,
+                       const float* agg, const float* skeleton, const long long* seed_inds, const float* vote_label,
+                       const long long* vote_mask, const float* gt_center, const float* gt_mask, const float* gt_size,
+                       const float* gt_heading, const long long* gt_cls, int b, int s, int j, int t, int p, int g, int c,
+                       int origin, float* out32, double* out64, double* scales, float* u_vote, float* u_c1, float* u_c2,
+                       float* u_size, void* u_head, float* u_obj, float* u_sem, double* workspace,
+                       long long workspace_doubles, void* stream);
+/* backward: g32 f32 [8] / g64 f64 [2] = upstream gradients of out32 / out64 -> gradients of vote_xyz, center, size,
+ * heading (dtype as in the forward), obj [B,P,2] and sem [B,P,C] (both contiguous), every element written.            */
+int p2r_detection_loss_grad(const float* g32, const double* g64, const double* scales, const float* u_vote,
+                            const float* u_c1, const float* u_c2, const float* u_size, const void* u_head,
+                            int heading_f64, const float* u_obj, const float* u_sem, int b, int s, int p, int c,
+                            float* d_vote, float* d_center, float* d_size, void* d_head, float* d_obj, float* d_sem,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,8 +70,14 @@ SIGNATURES = {
     "p2r_maxpool_rows_grad": [_vp, _c_int, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_make_batch": [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "p2r_make_batch_variant": [_c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
+    "p2r_detection_loss_workspace": [_c_int, _c_int],
+    "p2r_detection_loss": [_vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
+                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _vp],
+    "p2r_detection_loss_grad": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
-_RESTYPES = {"p2r_last_error": ctypes.c_char_p}
+_RESTYPES = {"p2r_last_error": ctypes.c_char_p, "p2r_detection_loss_workspace": _c_ll}
 
 _lib = None
 

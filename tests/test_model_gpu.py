@@ -196,3 +196,54 @@ def test_overlapped_weight_gradients_match_plain_backward(cuda, golden):
             assert (a - b).abs().max().item() <= 2e-3 * scale, (k, (a - b).abs().max().item(), scale)
     finally:
         gemm_sm100.uninstall()
+
+
+def _fused_vs_chain_on_random_predictions(dev):
+    """Fused loss kernel vs the chain of torch kernels on predictions that hit every branch (near / far / in-between
+    proposals, both sides of the huber knee, masked seeds): ten numbers and the six input gradients."""
+    import os
+    from pose2room_b200.config import P2RConfig
+    from pose2room_b200.p2rnet.loss import BoxNetDetectionLoss
+    from tests.test_loss_math import make_case
+    crit = BoxNetDetectionLoss(1, 0, P2RConfig(mode="train", joint_num=25))
+    for seed, hd in [(1, torch.float64), (3, torch.float32)]:
+        est, gt, sem_obj = make_case(seed, B=4, T=64, S=40, P=32, heading_dtype=hd)
+        results = []
+        for flag in ("0", "1"):
+            os.environ["P2R_FUSED_LOSS"] = flag
+            leaves = {k: est[k].clone().to(dev).requires_grad_(True) for k in ("vote_xyz", "center", "size", "heading")}
+            so = sem_obj.clone().to(dev).requires_grad_(True)
+            e = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in est.items()}
+            e.update(leaves)
+            e["objectness_scores"], e["sem_cls_scores"] = so[..., 0:2], so[..., 2:]
+            g = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in gt.items()}
+            out = crit(e, g, None)
+            out["total"].backward()
+            torch.cuda.synchronize()
+            results.append(({k: v.item() for k, v in out.items()},
+                            dict({k: v.grad.double().cpu() for k, v in leaves.items()}, sem_obj=so.grad.double().cpu()),
+                            {k: v.dtype for k, v in out.items()}))
+        (a, ga, da), (b, gb, db) = results
+        assert da == db, (da, db)
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-6 * max(1.0, abs(a[k])), (k, a[k], b[k])
+        for k in ga:
+            assert (ga[k] - gb[k]).abs().max().item() <= 2e-6 * max(1e-3, ga[k].abs().max().item()), k
+
+
+@pytest.mark.xfail(strict=False, reason="the fused detection-loss kernel (csrc/loss_ops.cu, P2R_FUSED_LOSS=1) was written "
+                                        "after the round's GPU budget was spent: its arithmetic is held to the oracle on the "
+                                        "CPU (test_loss_math.py); the kernel is checked here in a process of its own, "
+                                        "non-gating until it has passed on a B200")
+def test_fused_detection_loss_passes_the_parity_tests(cuda):
+    import os
+    import subprocess
+    import sys
+    code = ("import torch, tests.test_model_gpu as T, tests.model_helpers as H; dev = torch.device('cuda:0'); "
+            "torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 = False; "
+            "T._fused_vs_chain_on_random_predictions(dev); import os; os.environ['P2R_FUSED_LOSS'] = '1'; g = H.load_golden(); "
+            "[T.test_train_forward_loss_backward(dev, g, n) for n in ('small', 'ref53', 'bl')]; print('FUSED-LOSS-OK')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "FUSED-LOSS-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
