@@ -277,6 +277,23 @@ int p2r_detection_loss_grad(const float* g32, const double* g64, const double* s
                             float* d_vote, float* d_center, float* d_size, void* d_head, float* d_obj, float* d_sem,
                             void* stream);
 
+/* ---- Gaussian-mixture box heads (ref: models/p2rnet/modules/mdn.py:31-84 MixtureDensityHead) ---------------------------
+ * Training-time point prediction with n_samples = 1 (the configuration proposal_net.py:141-147 builds):
+ *   out[r,:] = sum_g sigmoid(logits[r,g]) * (mu[g,:] + exp(log_sigma[g,:]) * eps[r,g,:])
+ * logits [rows,G] float32, or bfloat16 when logits_bf16 (the output of the pi 1x1 conv); mu [G,d] and eps [rows,G,1,d]
+ * float64 when mu_f64 (the heading head, whose mu grid is float64 in the reference) else float32; log_sigma f32 [G,d];
+ * out [rows,d] in mu's type.  eps ~ N(0,1) is drawn by the caller with the reference's torch call (mdn.py:44).
+ * G <= 256, d <= 4.  csrc/gmm_ops.cu, arithmetic in csrc/gmm_math.h.                                                 */
+int p2r_gmm_mix(const void* logits, int logits_bf16, const void* mu, int mu_f64, const float* log_sigma, const void* eps,
+                long long rows, int g, int d, void* out, void* stream);
+/* backward: dout [rows,d] (mu's type) -> dlogits [rows,G] (logits' type), dmu [G,d] (mu's type), dls f32 [G,d], all
+ * written in full (deterministic two-level sum over rows).  workspace: p2r_gmm_mix_workspace(rows, g, d) doubles,
+ * ZEROED by the caller.                                                                                             */
+long long p2r_gmm_mix_workspace(long long rows, int g, int d);
+int p2r_gmm_mix_grad(const void* logits, int logits_bf16, const void* mu, int mu_f64, const float* log_sigma,
+                     const void* eps, const void* dout, long long rows, int g, int d, void* dlogits, void* dmu, float* dls,
+                     double* workspace, long long workspace_doubles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,19 +231,67 @@ def _fused_vs_chain_on_random_predictions(dev):
             assert (ga[k] - gb[k]).abs().max().item() <= 2e-6 * max(1e-3, ga[k].abs().max().item()), k
 
 
-@pytest.mark.xfail(strict=False, reason="the fused detection-loss kernel (csrc/loss_ops.cu, P2R_FUSED_LOSS=1) was written "
-                                        "after the round's GPU budget was spent: its arithmetic is held to the oracle on the "
-                                        "CPU (test_loss_math.py); the kernel is checked here in a process of its own, "
-                                        "non-gating until it has passed on a B200")
-def test_fused_detection_loss_passes_the_parity_tests(cuda):
+def _fused_gmm_vs_torch_path(dev):
+    """Fused mixture-head kernels vs the module's torch path on the same eps (real sigma, f32 and f64 heads, f32 and bf16
+    logits): prediction and the gradients of logits / mu / log_sigma."""
+    import os
+    from pose2room_b200.p2rnet.mdn import MixtureDensityHead, Struct, _FusedGMMPredict
+    for G, D, mu_dtype, lg_dtype in [(100, 3, torch.float32, torch.float32), (100, 2, torch.float64, torch.float32),
+                                     (100, 3, torch.float32, torch.bfloat16), (33, 2, torch.float64, torch.bfloat16)]:
+        rows = 4096 + 5
+        gen = torch.Generator().manual_seed(G + D)
+        head = MixtureDensityHead(Struct(input_dim=8, num_gaussian=G, out_dim=D, n_samples=1, central_tendency="mean",
+                                         mu_bias_init=torch.randn(G, D, generator=gen).to(mu_dtype))).to(dev)
+        with torch.no_grad():
+            head.log_sigma.copy_((0.5 * torch.randn(G, D, generator=gen) - 0.5).to(dev))
+        base = (2.0 * torch.randn(rows, G, generator=gen) - 1.0).to(lg_dtype).to(dev)
+        dout = torch.randn(rows, D, generator=gen).to(mu_dtype).to(dev)
+        res = []
+        for fused in (False, True):
+            for p in head.parameters():
+                p.grad = None
+            logits = base.clone().requires_grad_(True)
+            torch.manual_seed(11)
+            if fused:
+                eps = head.mu.data.new(rows, G, 1, D).normal_()
+                out = _FusedGMMPredict.apply(logits, head.mu, head.log_sigma, eps)
+            else:
+                out = head.point_prediction(torch.sigmoid(logits.float()))
+            out.backward(dout)
+            torch.cuda.synchronize()
+            res.append([t.detach().double().cpu() for t in (out, logits.grad, head.mu.grad, head.log_sigma.grad)] + [out.dtype])
+        assert res[0][4] == res[1][4]
+        lg_tol = 1e-2 if lg_dtype == torch.bfloat16 else 3e-6        # d logits is rounded to bf16 on the fused path
+        for name, a, b, tol in zip(("out", "dlogits", "dmu", "dls"), res[0], res[1], (3e-6, lg_tol, 2e-5, 2e-5)):
+            assert (a - b).abs().max().item() <= tol * max(1e-3, a.abs().max().item()), (G, D, name, (a - b).abs().max().item())
+
+
+_FUSED_REASON = ("the fused %s kernel(s) were written after the round's GPU budget was spent: the arithmetic is held to the "
+                 "oracle on the CPU (test_loss_math.py / test_gmm_math.py); the kernels are checked here in a process of "
+                 "their own, non-gating until they have passed on a B200")
+
+
+def _run_isolated(flags, extra=""):
     import os
     import subprocess
     import sys
-    code = ("import torch, tests.test_model_gpu as T, tests.model_helpers as H; dev = torch.device('cuda:0'); "
-            "torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 = False; "
-            "T._fused_vs_chain_on_random_predictions(dev); import os; os.environ['P2R_FUSED_LOSS'] = '1'; g = H.load_golden(); "
-            "[T.test_train_forward_loss_backward(dev, g, n) for n in ('small', 'ref53', 'bl')]; print('FUSED-LOSS-OK')")
+    code = ("import os, torch, tests.test_model_gpu as T, tests.model_helpers as H; dev = torch.device('cuda:0'); "
+            "torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 = False; " + extra +
+            "".join("os.environ['%s'] = '1'; " % f for f in flags) + "g = H.load_golden(); "
+            "[T.test_train_forward_loss_backward(dev, g, n) for n in ('small', 'ref53', 'bl')]; "
+            "T.test_bf16_throughput_mode_tracks_fp32_reference(dev, g); "
+            "T.test_overlapped_weight_gradients_match_plain_backward(dev, g); print('ISOLATED-OK')")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ), capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0 and "FUSED-LOSS-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+                       timeout=900)
+    assert r.returncode == 0 and "ISOLATED-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
+@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "detection-loss (csrc/loss_ops.cu, P2R_FUSED_LOSS=1)")
+def test_fused_detection_loss_passes_the_parity_tests(cuda):
+    _run_isolated(["P2R_FUSED_LOSS"], "T._fused_vs_chain_on_random_predictions(dev); ")
+
+
+@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "mixture-head (csrc/gmm_ops.cu, P2R_FUSED_GMM=1)")
+def test_fused_mixture_heads_pass_the_parity_tests(cuda):
+    _run_isolated(["P2R_FUSED_GMM"], "T._fused_gmm_vs_torch_path(dev); ")
