@@ -235,6 +235,56 @@ def _variants_subprocess(script):
         return {"error": repr(e)}
 
 
+# Opt-in code paths that were written after this round's GPU budget was spent (fused detection loss, fused mixture heads)
+# or whose gain was inside the box-to-box spread (internal joint permutation).  After the headline measurement is safe,
+# each is measured by a fresh child of this same script on the same box with the same step count, bounded in time, and
+# reported next to the headline -- never instead of it, and whatever happens in these processes cannot change it.
+EXPERIMENTS = [
+    ("fused_loss+fused_gmm", {"P2R_FUSED_LOSS": "1", "P2R_FUSED_GMM": "1"}),
+    ("joint_perm", {"P2R_JOINT_PERM": "1"}),
+    ("fused_loss", {"P2R_FUSED_LOSS": "1"}),
+    ("fused_gmm", {"P2R_FUSED_GMM": "1"}),
+]
+
+
+def _experiments(script, headline):
+    import signal
+    if os.environ.get("P2R_BENCH_EXPERIMENTS", "1") == "0":
+        return None
+    deadline = time.time() + float(os.environ.get("P2R_BENCH_EXPERIMENTS_BUDGET_S", "150"))
+    per_run = float(os.environ.get("P2R_BENCH_EXPERIMENT_TIMEOUT_S", "75"))
+    out = {"baseline": {"ms_per_step": headline.get("ms_per_step"), "first_step_loss": headline.get("first_step_loss")}}
+    for name, extra in EXPERIMENTS:
+        left = deadline - time.time()
+        if left < 40.0:
+            out[name] = {"skipped": "time budget of the experiments leg spent"}
+            continue
+        try:
+            env = dict(os.environ, P2R_BENCH_CHILD="1", P2R_BENCH_DATA_PATH="0", **extra)
+            args = [sys.executable, script, "--steps", str(headline.get("steps", 10)), "--warmup",
+                    str(headline.get("warmup", 3)), "--no-cpu-baseline"]
+            p = subprocess.Popen(args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, start_new_session=True)
+            try:
+                o, e = p.communicate(timeout=min(per_run, left))
+            except subprocess.TimeoutExpired:
+                os.killpg(p.pid, signal.SIGKILL)
+                p.wait()
+                out[name] = {"error": "timed out"}
+                continue
+            lines = [l for l in o.decode().splitlines() if l.startswith("{")]
+            if p.returncode != 0 or not lines:
+                out[name] = {"error": "exit code %s: %s" % (p.returncode, e.decode()[-300:])}
+                continue
+            d = json.loads(lines[-1])
+            out[name] = {"ms_per_step": d.get("ms_per_step"), "value": d.get("value"),
+                         "first_step_loss": d.get("first_step_loss"), "gpu_launches": d.get("gpu_launches"),
+                         "e2e_ms_per_step": (d.get("e2e") or {}).get("ms_per_step"),
+                         "cuda_graph": (d.get("config") or {}).get("cuda_graph")}
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+    return out
+
+
 def supervise(script=None):
     import signal
     script = script or os.path.abspath(__file__)
@@ -257,6 +307,8 @@ def supervise(script=None):
                 d["config"]["fallback"] = label
             if isinstance(d.get("data_path"), dict) and "error" not in d["data_path"]:
                 d["data_path"]["variants"] = _variants_subprocess(script)
+            if label is None and isinstance(d.get("roofline"), dict) and d.get("n_gpus") == 1:
+                d["experiments"] = _experiments(script, d)
             print(json.dumps(d), flush=True)
             return 0
         if p.returncode != 17:          # a real failure, not a stall: do not hide it behind a retry
@@ -499,16 +551,20 @@ def main():
     for k in static:
         static[k].copy_(resident[k])
     graph, static_loss, use_graph = None, None, os.environ.get("P2R_CUDA_GRAPH", "1") != "0"
+    first_step_loss = None      # loss of the very first step (same weights, same batch in every process: a parity signal)
     opt_graph = None
     if use_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(3):
-                    step(static)
+                for i in range(3):
+                    l = step(static)
+                    if i == 0:
+                        first_step_loss = l.detach().clone()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            first_step_loss = float(first_step_loss.item())
             beat("eager warm-up done")
             dbg("eager warm-up done, capturing")
             graph = torch.cuda.CUDAGraph()
@@ -694,7 +750,7 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "roofline": roofline, "cpu_baseline": cpu, "data_path": data_path,
+            "roofline": roofline, "cpu_baseline": cpu, "data_path": data_path, "first_step_loss": first_step_loss,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

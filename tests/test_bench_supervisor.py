@@ -94,3 +94,34 @@ def test_variant_ab_runs_in_its_own_process_and_cannot_lose_the_line(tmp_path, m
         print('{"value": 5.0, "config": {}, "data_path": {"error": "boom"}}')
     ''', monkeypatch, capsys, timeout="30")
     assert rc == 0 and json.loads(io.out.strip())["data_path"] == {"error": "boom"}
+
+
+def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_path, monkeypatch, capsys):
+    """Opt-in code paths are measured by fresh children after the headline is safe: results (or an error / a skip) land in
+    `experiments`, the headline numbers stay the first child's."""
+    body = '''
+        import json, os, sys, time
+        if os.environ.get("P2R_BENCH_DATA_PATH") == "0":           # an experiment child
+            assert "--no-cpu-baseline" in sys.argv and sys.argv[sys.argv.index("--steps") + 1] == "2"
+            if os.environ.get("P2R_JOINT_PERM") == "1":
+                os.abort()
+            both = os.environ.get("P2R_FUSED_LOSS") == "1" and os.environ.get("P2R_FUSED_GMM") == "1"
+            print(json.dumps({"value": 9.0 if both else 8.0, "ms_per_step": 1.0 if both else 2.0, "first_step_loss": 0.5,
+                              "gpu_launches": 7, "config": {"cuda_graph": True}, "e2e": {"ms_per_step": 3.0}}))
+            sys.exit(0)
+        print(json.dumps({"value": 4.0, "ms_per_step": 5.0, "steps": 2, "warmup": 3, "n_gpus": 1, "config": {},
+                          "roofline": {"frac": 0.5}, "first_step_loss": 0.5}))
+    '''
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    d = json.loads(io.out.strip())
+    ex = d["experiments"]
+    assert rc == 0 and d["value"] == 4.0 and ex["baseline"] == {"ms_per_step": 5.0, "first_step_loss": 0.5}
+    assert ex["fused_loss+fused_gmm"]["ms_per_step"] == 1.0 and ex["fused_loss"]["ms_per_step"] == 2.0
+    assert ex["fused_gmm"]["e2e_ms_per_step"] == 3.0 and "error" in ex["joint_perm"]
+    monkeypatch.setenv("P2R_BENCH_EXPERIMENTS_BUDGET_S", "1")      # no time left: every experiment is skipped, line intact
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    d = json.loads(io.out.strip())
+    assert rc == 0 and d["value"] == 4.0 and all("skipped" in v for k, v in d["experiments"].items() if k != "baseline")
+    monkeypatch.setenv("P2R_BENCH_EXPERIMENTS", "0")
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    assert rc == 0 and json.loads(io.out.strip())["experiments"] is None
