@@ -279,11 +279,10 @@ def _run_isolated(flags, extra=""):
             "torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 = False; " + extra +
             "".join("os.environ['%s'] = '1'; " % f for f in flags) + "g = H.load_golden(); "
             "[T.test_train_forward_loss_backward(dev, g, n) for n in ('small', 'ref53', 'bl')]; "
-            "T.test_bf16_throughput_mode_tracks_fp32_reference(dev, g); "
-            "T.test_overlapped_weight_gradients_match_plain_backward(dev, g); print('ISOLATED-OK')")
+            "T.test_bf16_throughput_mode_tracks_fp32_reference(dev, g); print('ISOLATED-OK')")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ), capture_output=True, text=True,
-                       timeout=900)
+                       timeout=600)
     assert r.returncode == 0 and "ISOLATED-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
 
 
