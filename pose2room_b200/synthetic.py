@@ -156,3 +156,68 @@ def deterministic_state_dict(reference_state_dict, seed=0):
             out[k] = torch.randn(v.shape, generator=g) / float(v[0].numel()) ** 0.5
         out[k] = out[k].to(v.dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Evaluation set of BASELINE.json config #5 / SURVEY.md section 8(d): scenes whose K = 128 predictions are drawn as
+# ground truth + noise, so that NMS has duplicates to remove, the far-box filter has something to drop and mAP is far
+# from both 0 and 1.  Every scene is generated from (seed, scene index) alone: any subset can be rebuilt anywhere.
+def make_eval_scene(seed, index, T=256, K=128):
+    """-> dict of numpy arrays: input_joints f32 (T,1,3) (the hip joint is all parse_predictions reads), the ground-truth
+    label arrays of make_scene, and the network-output arrays center f32 (K,3), size f32 (K,3) = log size, heading f64
+    (K,2) = (sin, cos) (the reference's heading head is float64), objectness_scores f32 (K,2), sem_cls_scores f32 (K,22)."""
+    rng = np.random.default_rng([int(seed), int(index)])
+    hip = np.cumsum(rng.normal(0.0, 0.05, size=(T, 3)), axis=0)
+    hip[:, 1] = np.clip(0.9 + hip[:, 1], 0.8, 1.0)
+    n_gt = int(rng.integers(1, MAX_GT + 1))
+    g_center = hip[rng.integers(0, T, size=n_gt)] + rng.normal(0.0, 0.3, size=(n_gt, 3))
+    g_size = rng.uniform(0.2, 1.7, size=(n_gt, 3))
+    g_theta = rng.uniform(-np.pi, np.pi, size=n_gt)
+    g_cls = rng.integers(0, NUM_CLASS, size=n_gt)
+
+    which = rng.integers(0, n_gt, size=K)
+    sigma = rng.choice([0.03, 0.1, 0.25, 0.5], size=K)
+    junk = rng.random(K) < 0.15
+    center = g_center[which] + sigma[:, None] * rng.normal(size=(K, 3))
+    log_size = np.log(g_size[which]) + 0.6 * sigma[:, None] * rng.normal(size=(K, 3))
+    theta = g_theta[which] + 0.8 * sigma * rng.normal(size=K)
+    center[junk] = hip[rng.integers(0, T, size=int(junk.sum()))] + rng.normal(0.0, 1.0, size=(int(junk.sum()), 3))
+    log_size[junk] = np.log(rng.uniform(0.1, 2.5, size=(int(junk.sum()), 3)))
+    theta[junk] = rng.uniform(-np.pi, np.pi, size=int(junk.sum()))
+    center[0:3] += 30.0                         # far from the trajectory: removed by remove_far_box
+    log_size[3:5, 0] = np.log(0.004)            # degenerate / absurd sizes: removed
+    log_size[5, 1] = np.log(14.0)
+    radius = 1.0 + 0.1 * rng.normal(size=K)     # (sin, cos) off the unit circle, like a regressed heading
+    objectness = np.zeros((K, 2))
+    objectness[:, 1] = np.where(junk, -1.0, 3.0 - 8.0 * sigma) + 0.7 * rng.normal(size=K)
+    sem = rng.normal(size=(K, NUM_CLASS))
+    right = rng.random(K) < 0.8
+    boosted = np.where(right & ~junk, g_cls[which], rng.integers(0, NUM_CLASS, size=K))
+    sem[np.arange(K), boosted] += 4.0
+
+    out = dict(
+        input_joints=hip[:, None, :].astype(np.float32),
+        box_label_mask=np.zeros(MAX_GT, np.float32), sem_cls_label=np.zeros(MAX_GT, np.int64),
+        center_label=np.zeros((MAX_GT, 3), np.float32), size=np.zeros((MAX_GT, 3), np.float32),
+        heading=np.zeros((MAX_GT, 2), np.float32),
+        pred_center=center.astype(np.float32), pred_size=log_size.astype(np.float32),
+        pred_heading=np.stack([radius * np.sin(theta), radius * np.cos(theta)], -1),
+        pred_objectness_scores=objectness.astype(np.float32), pred_sem_cls_scores=sem.astype(np.float32))
+    out["box_label_mask"][:n_gt] = 1
+    out["sem_cls_label"][:n_gt] = g_cls
+    out["center_label"][:n_gt] = g_center
+    out["size"][:n_gt] = np.log(g_size)
+    out["heading"][:n_gt, 0] = np.sin(g_theta)
+    out["heading"][:n_gt, 1] = np.cos(g_theta)
+    return out
+
+
+def make_eval_batch(seed, start, count, T=256, K=128):
+    """Scenes [start, start + count) collated -> (est_data, gt_data) dicts of torch CPU tensors in the schema
+    parse_predictions / parse_groundtruths read (net_utils/ap_helper.py:133-292)."""
+    import torch
+    scenes = [make_eval_scene(seed, i, T, K) for i in range(start, start + count)]
+    stack = lambda k: torch.from_numpy(np.stack([s[k] for s in scenes]))
+    est = {k: stack("pred_" + k) for k in ("center", "size", "heading", "objectness_scores", "sem_cls_scores")}
+    gt = {k: stack(k) for k in ("input_joints", "box_label_mask", "sem_cls_label", "center_label", "size", "heading")}
+    return est, gt
