@@ -208,7 +208,7 @@ def start_watchdog():
     def run():
         while True:
             time.sleep(2.0)
-            if time.time() - _HEARTBEAT["t"] > limit:
+            if time.time() - _HEARTBEAT["t"] > _HEARTBEAT.get("limit", limit):
                 sys.stderr.write("bench.py: no progress for %.0f s in phase '%s' -- aborting\n" % (limit, _HEARTBEAT["phase"]))
                 sys.stderr.flush()
                 os._exit(17)
@@ -253,7 +253,8 @@ def _experiments(script, headline):
         return None
     deadline = time.time() + float(os.environ.get("P2R_BENCH_EXPERIMENTS_BUDGET_S", "150"))
     per_run = float(os.environ.get("P2R_BENCH_EXPERIMENT_TIMEOUT_S", "75"))
-    out = {"baseline": {"ms_per_step": headline.get("ms_per_step"), "first_step_loss": headline.get("first_step_loss")}}
+    out = {"baseline": {"ms_per_step": headline.get("ms_per_step"), "first_step_loss": headline.get("first_step_loss"),
+                        "kernels_per_step": (headline.get("census") or {}).get("kernels")}}
     for name, extra in EXPERIMENTS:
         left = deadline - time.time()
         if left < 40.0:
@@ -279,7 +280,9 @@ def _experiments(script, headline):
             out[name] = {"ms_per_step": d.get("ms_per_step"), "value": d.get("value"),
                          "first_step_loss": d.get("first_step_loss"), "gpu_launches": d.get("gpu_launches"),
                          "e2e_ms_per_step": (d.get("e2e") or {}).get("ms_per_step"),
-                         "cuda_graph": (d.get("config") or {}).get("cuda_graph")}
+                         "cuda_graph": (d.get("config") or {}).get("cuda_graph"),
+                         "kernels_per_step": (d.get("census") or {}).get("kernels"),
+                         "torch_glue_kernels": (d.get("census") or {}).get("torch_glue_kernels")}
         except Exception as e:
             out[name] = {"error": repr(e)}
     return out
@@ -297,12 +300,16 @@ def supervise(script=None):
             out, _ = p.communicate(timeout=float(os.environ.get("P2R_BENCH_TIMEOUT_S", "420")))
         except subprocess.TimeoutExpired:
             os.killpg(p.pid, signal.SIGKILL)
-            p.wait()
+            out, _ = p.communicate()            # what it had printed before it was killed
             sys.stderr.write("bench.py: attempt timed out\n")
-            continue
+            if not any(l.startswith("{") and '"census": null' in l for l in out.decode().splitlines()):
+                continue
         lines = [l for l in out.decode().splitlines() if l.startswith("{")]
-        if p.returncode == 0 and lines:
+        if lines and (p.returncode == 0 or '"census": null' in lines[-1]):
+            # (a child that died AFTER printing its complete line -- in the informational census leg -- still counts)
             d = json.loads(lines[-1])
+            if p.returncode != 0:
+                d["census"] = {"error": "the census leg ended the measuring process (exit code %s)" % p.returncode}
             if label is not None:
                 d["config"]["fallback"] = label
             if isinstance(d.get("data_path"), dict) and "error" not in d["data_path"]:
@@ -455,6 +462,41 @@ def data_path_leg(dev, B, reps=30, train_step=None, steps=10):
             "kernel_frac_of_hbm_peak": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": algo_bytes,
             "loader_ms_per_batch": loader_ms, "loader_sequences_per_s": B / (loader_ms * 1e-3),
             "h2d_bytes_per_batch": B * (16 * 8 + 4 + 10 * 9 * 4 + 10 * 8)})
+
+
+def kernel_census(replay):
+    """Informational: every kernel of ONE step (one graph replay) by name, from torch.profiler / CUPTI -- how many launches a
+    step is, how much of its kernel time is this library's kernels and how much is torch glue (at::*).  Run after all the
+    timed legs; never inside one."""
+    import re
+    import tempfile
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        replay()
+        torch.cuda.synchronize()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "trace.json")
+        prof.export_chrome_trace(path)
+        events = json.load(open(path))["traceEvents"]
+    ker = [e for e in events if e.get("cat") == "kernel" and "dur" in e]
+    if not ker:
+        return {"error": "no kernel events (CUPTI unavailable?)"}
+    by = {}
+    for e in ker:
+        name = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", e["name"])
+        name = re.sub(r"^void ", "", name)
+        key = name.split("(")[0][:72]
+        c = by.setdefault(key, [0, 0.0])
+        c[0] += 1
+        c[1] += float(e["dur"])
+    glue = [k for k in by if k.startswith("at::") or k.startswith("at_cuda") or "cub::" in k or k.startswith("nccl")]
+    t0 = min(e["ts"] for e in ker)
+    t1 = max(e["ts"] + e["dur"] for e in ker)
+    top = sorted(by.items(), key=lambda kv: -kv[1][1])[:14]
+    return {"kernels": len(ker), "kernel_time_us": sum(v[1] for v in by.values()), "span_us": t1 - t0,
+            "torch_glue_kernels": sum(by[k][0] for k in glue), "torch_glue_time_us": sum(by[k][1] for k in glue),
+            "memcpy_memset": sum(1 for e in events if e.get("cat") in ("gpu_memcpy", "gpu_memset")),
+            "top_by_time": [{"kernel": k, "launches": v[0], "us": round(v[1], 1)} for k, v in top]}
 
 
 # ------------------------------------------------------------------------------------------ our arm (GPU)
@@ -750,8 +792,18 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "roofline": roofline, "cpu_baseline": cpu, "data_path": data_path, "first_step_loss": first_step_loss,
+            "roofline": roofline, "cpu_baseline": cpu, "data_path": data_path, "first_step_loss": first_step_loss, "census": None,
         }
+        if world == 1 and graph is not None and os.environ.get("P2R_BENCH_CENSUS", "1") != "0":
+            # The census drives CUPTI over a graph replay.  The complete line goes out FIRST: should the profiler take the
+            # process down, the supervisor keeps this line (it reads the last one; it prints exactly one).
+            print(json.dumps(line), flush=True)
+            beat("kernel census")
+            _HEARTBEAT["limit"] = 45.0          # the line is out: a profiler that hangs costs 45 s, not the full stall limit
+            try:
+                line["census"] = kernel_census(lambda: step(static))
+            except Exception as e:      # informational leg: report, never lose the headline line over it
+                line["census"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -115,7 +115,7 @@ def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_pat
     rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
     d = json.loads(io.out.strip())
     ex = d["experiments"]
-    assert rc == 0 and d["value"] == 4.0 and ex["baseline"] == {"ms_per_step": 5.0, "first_step_loss": 0.5}
+    assert rc == 0 and d["value"] == 4.0 and ex["baseline"] == {"ms_per_step": 5.0, "first_step_loss": 0.5, "kernels_per_step": None}
     assert ex["fused_loss+fused_gmm"]["ms_per_step"] == 1.0 and ex["fused_loss"]["ms_per_step"] == 2.0
     assert ex["fused_gmm"]["e2e_ms_per_step"] == 3.0 and "error" in ex["joint_perm"]
     monkeypatch.setenv("P2R_BENCH_EXPERIMENTS_BUDGET_S", "1")      # no time left: every experiment is skipped, line intact
@@ -125,3 +125,34 @@ def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_pat
     monkeypatch.setenv("P2R_BENCH_EXPERIMENTS", "0")
     rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
     assert rc == 0 and json.loads(io.out.strip())["experiments"] is None
+
+
+def test_child_that_dies_in_the_census_leg_keeps_its_line(tmp_path, monkeypatch, capsys):
+    """The measuring child prints its complete line before it drives CUPTI; if the profiler takes the process down the
+    supervisor still reports that line (once), with the census marked as failed."""
+    rc, io = _run(tmp_path, '''
+        import json, os, sys
+        print(json.dumps({"value": 6.0, "config": {}, "census": None}), flush=True)
+        os.abort()
+    ''', monkeypatch, capsys, timeout="30")
+    lines = [l for l in io.out.splitlines() if l.startswith("{")]
+    d = json.loads(lines[0])
+    assert rc == 0 and len(lines) == 1 and d["value"] == 6.0 and "error" in d["census"]
+    rc, io = _run(tmp_path, '''
+        import json
+        print(json.dumps({"value": 6.0, "config": {}, "census": None}), flush=True)
+        print(json.dumps({"value": 6.0, "config": {}, "census": {"kernels": 1234}}), flush=True)
+    ''', monkeypatch, capsys, timeout="30")
+    lines = [l for l in io.out.splitlines() if l.startswith("{")]
+    assert rc == 0 and len(lines) == 1 and json.loads(lines[0])["census"] == {"kernels": 1234}
+
+
+def test_child_that_hangs_in_the_census_leg_keeps_its_line(tmp_path, monkeypatch, capsys):
+    rc, io = _run(tmp_path, '''
+        import json, time
+        print(json.dumps({"value": 7.0, "config": {}, "census": None}), flush=True)
+        time.sleep(60)
+    ''', monkeypatch, capsys, timeout="3")
+    lines = [l for l in io.out.splitlines() if l.startswith("{")]
+    d = json.loads(lines[0])
+    assert rc == 0 and len(lines) == 1 and d["value"] == 7.0 and "error" in d["census"] and "fallback" not in d["config"]
