@@ -42,7 +42,7 @@ template <typename MuT, typename LogitT>
 __global__ void __launch_bounds__(256)
 gmm_mix_fwd_kernel(const LogitT* __restrict__ logits, const MuT* __restrict__ mu, const float* __restrict__ log_sigma,
                    const MuT* __restrict__ eps, long long rows, int G, int D, MuT* __restrict__ out) {
-  extern __shared__ __align__(16) double s_par[];      // mu[G*D] | sigma[G*D]
+  P2R_DYN_SMEM(double, s_par);                          // mu[G*D] | sigma[G*D]
   double* s_mu = s_par;
   double* s_sig = s_par + G * D;
   p2rg_stage_params(mu, log_sigma, G * D, s_mu, s_sig);
@@ -70,7 +70,7 @@ gmm_mix_bwd_kernel(const LogitT* __restrict__ logits, const MuT* __restrict__ mu
                    const MuT* __restrict__ eps, const MuT* __restrict__ dout, long long rows, int G, int D,
                    int rows_per_block, LogitT* __restrict__ dlogits, double* __restrict__ partials,
                    unsigned int* __restrict__ counter, MuT* __restrict__ dmu, float* __restrict__ dls) {
-  extern __shared__ __align__(16) double s_par[];      // mu[G*D] | sigma[G*D] | dout[rows_per_block*D]
+  P2R_DYN_SMEM(double, s_par);                          // mu[G*D] | sigma[G*D] | dout[rows_per_block*D]
   double* s_mu = s_par;
   double* s_sig = s_par + G * D;
   double* s_dout = s_sig + G * D;
@@ -133,8 +133,11 @@ extern "C" int p2r_gmm_mix(const void* logits, int logits_bf16, const void* mu, 
   if (grid > P2R_SM_COUNT * 8) grid = P2R_SM_COUNT * 8;
   cudaStream_t st = (cudaStream_t)stream;
 #define P2RG_FWD(MuT, LogitT)                                                                                       \
-  gmm_mix_fwd_kernel<MuT, LogitT><<<grid, 256, smem, st>>>((const LogitT*)logits, (const MuT*)mu, log_sigma,       \
-                                                           (const MuT*)eps, rows, g, d, (MuT*)out)
+  do {                                                                                                              \
+    auto kern = gmm_mix_fwd_kernel<MuT, LogitT>;                                                                    \
+    P2R_LAUNCH(kern, grid, 256, smem, st, (const LogitT*)logits, (const MuT*)mu, log_sigma, (const MuT*)eps, rows,  \
+               g, d, (MuT*)out);                                                                                    \
+  } while (0)
   if (mu_f64) { if (logits_bf16) P2RG_FWD(double, __nv_bfloat16); else P2RG_FWD(double, float); }
   else { if (logits_bf16) P2RG_FWD(float, __nv_bfloat16); else P2RG_FWD(float, float); }
 #undef P2RG_FWD
@@ -154,9 +157,12 @@ extern "C" int p2r_gmm_mix_grad(const void* logits, int logits_bf16, const void*
   double* partials = workspace + 1;
   cudaStream_t st = (cudaStream_t)stream;
 #define P2RG_BWD(MuT, LogitT)                                                                                       \
-  gmm_mix_bwd_kernel<MuT, LogitT><<<grid, threads, smem, st>>>(                                                     \
-      (const LogitT*)logits, (const MuT*)mu, log_sigma, (const MuT*)eps, (const MuT*)dout, rows, g, d,             \
-      P2RG_ROWS_PER_BLOCK, (LogitT*)dlogits, partials, counter, (MuT*)dmu, dls)
+  do {                                                                                                              \
+    auto kern = gmm_mix_bwd_kernel<MuT, LogitT>;                                                                    \
+    P2R_LAUNCH(kern, grid, threads, smem, st, (const LogitT*)logits, (const MuT*)mu, log_sigma, (const MuT*)eps,    \
+               (const MuT*)dout, rows, g, d, P2RG_ROWS_PER_BLOCK, (LogitT*)dlogits, partials, counter, (MuT*)dmu,   \
+               dls);                                                                                                \
+  } while (0)
   if (mu_f64) { if (logits_bf16) P2RG_BWD(double, __nv_bfloat16); else P2RG_BWD(double, float); }
   else { if (logits_bf16) P2RG_BWD(float, __nv_bfloat16); else P2RG_BWD(float, float); }
 #undef P2RG_BWD

@@ -59,7 +59,7 @@ __device__ __forceinline__ double p2rl_warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(P2RL_THREADS) detection_loss_kernel(DetLossArgs a) {
-  extern __shared__ __align__(16) float s_center[];                    // [P*3], proposal blocks only
+  P2R_DYN_SMEM(float, s_center);                                       // [P*3], proposal blocks only
   __shared__ float s_gc[P2RL_MAX_GT * 3], s_gm[P2RL_MAX_GT], s_gs[P2RL_MAX_GT * 3], s_gh[P2RL_MAX_GT * 2];
   __shared__ long long s_gcls[P2RL_MAX_GT];
   __shared__ float s_d2[P2RL_MAX_GT];
@@ -215,7 +215,7 @@ extern "C" int p2r_detection_loss(const float* vote_xyz, const float* center, co
     cudaError_t e = cudaFuncSetAttribute(detection_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { p2r_set_last_error("p2r_detection_loss", (int)e); return (int)e; }
   }
-  detection_loss_kernel<<<grid, P2RL_THREADS, smem, (cudaStream_t)stream>>>(a);
+  P2R_LAUNCH(detection_loss_kernel, grid, P2RL_THREADS, smem, (cudaStream_t)stream, a);
   P2R_RETURN_LAUNCH("p2r_detection_loss");
 }
 
@@ -284,6 +284,6 @@ extern "C" int p2r_detection_loss_grad(const float* g32, const double* g64, cons
   const long long total = a.n_vote + 2 * a.n_p3 + 2 * a.n_p2 + a.n_sem;
   int grid = p2r_ceil_div(total, 256);
   if (grid > P2R_SM_COUNT * 8) grid = P2R_SM_COUNT * 8;
-  detection_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  P2R_LAUNCH(detection_loss_grad_kernel, grid, 256, 0, (cudaStream_t)stream, a);
   P2R_RETURN_LAUNCH("p2r_detection_loss_grad");
 }

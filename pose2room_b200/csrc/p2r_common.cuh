@@ -1,7 +1,11 @@
 // p2r_common.cuh -- shared device helpers for the sm_100a kernels of pose2room_b200.
 #pragma once
+#ifdef P2R_HOST_EMULATION
+#include "cuda_emu.h"   // tests/csrc: host emulator for the SIMT-only kernels (tests/test_kernels_emulated.py), never shipped
+#else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#endif
 #include <stdint.h>
 
 #define P2R_SM_COUNT 148
@@ -22,6 +26,23 @@ extern "C" void p2r_set_last_error(const char* where, int code);
   } while (0)
 
 static inline int p2r_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Kernel launch and dynamic shared memory, spelled so that a kernel that needs nothing beyond threads, shared memory,
+// __syncthreads, shuffles and global atomics can ALSO be compiled for the host emulator of the CPU tests (launcher
+// included: its grid / workspace arithmetic is then exercised too).  `kernel` must be a plain identifier (take a
+// function pointer to a template instance first).
+#ifdef P2R_HOST_EMULATION
+#define P2R_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#define P2R_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_dyn_smem)
+#else
+#define P2R_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define P2R_DYN_SMEM(type, name)                                \
+  extern __shared__ __align__(16) unsigned char name##_raw[];   \
+  type* name = reinterpret_cast<type*>(name##_raw)
+#endif
+
+#ifndef P2R_HOST_EMULATION   // everything below is device-only (intrinsics, PTX)
 
 // ---- exact-order fp32 arithmetic -----------------------------------------------------------
 // The reference's kernels are compiled with nvcc's default -fmad=true; its SASS for sm_100a
@@ -107,3 +128,5 @@ __device__ __forceinline__ void p2r_stage_floats(float* dst, const float* __rest
   p2r_mbar_wait(bar, parity);
   __syncthreads();
 }
+
+#endif  // !P2R_HOST_EMULATION

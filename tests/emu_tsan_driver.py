@@ -1,0 +1,35 @@
+"""Run by tests/test_kernels_emulated.py in a process of its own with libtsan preloaded: one pass of every emulated kernel
+(ThreadSanitizer-instrumented build of tests/csrc/kernels_emu.cpp given as argv[1]) on shapes with tail blocks."""
+import ctypes
+import os.path as osp
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
+from pose2room_b200 import _lib  # noqa: E402
+from tests import test_kernels_emulated as TE  # noqa: E402
+from tests import test_loss_math as TL  # noqa: E402
+
+lib = ctypes.CDLL(sys.argv[1])
+for name in ("p2r_detection_loss", "p2r_detection_loss_grad", "p2r_gmm_mix", "p2r_gmm_mix_grad",
+             "p2r_detection_loss_workspace", "p2r_gmm_mix_workspace"):
+    fn = getattr(lib, name)
+    fn.argtypes = _lib.SIGNATURES[name]
+    fn.restype = _lib._RESTYPES.get(name, ctypes.c_int)
+lib.emu_last_error.restype = ctypes.c_char_p
+est, gt, so = TL.make_case(11, B=2, T=300, S=200, P=150, heading_dtype=torch.float32)
+TE.emulated_loss(lib, est, gt, so)
+rows, G, D = 77, 33, 3
+rng = np.random.default_rng(0)
+lg, mu = rng.normal(size=(rows, G)).astype(np.float32), rng.normal(size=(G, D)).astype(np.float32)
+ls, eps = np.zeros((G, D), np.float32), rng.normal(size=(rows, G, 1, D)).astype(np.float32)
+dout, out = rng.normal(size=(rows, D)).astype(np.float32), np.zeros((rows, D), np.float32)
+p = lambda a: a.ctypes.data
+assert lib.p2r_gmm_mix(p(lg), 0, p(mu), 0, p(ls), p(eps), rows, G, D, p(out), None) == 0
+n = lib.p2r_gmm_mix_workspace(rows, G, D)
+ws, dl = np.zeros(n), np.zeros((rows, G), np.float32)
+dmu, dls = np.zeros((G, D), np.float32), np.zeros((G, D), np.float32)
+assert lib.p2r_gmm_mix_grad(p(lg), 0, p(mu), 0, p(ls), p(eps), p(dout), rows, G, D, p(dl), p(dmu), p(dls), p(ws), n, None) == 0
+print("TSAN-DRIVER-DONE")
