@@ -79,7 +79,7 @@ def test_packed_batch_of_ragged_samples_and_height_channel(host_lib):
 
 def test_frame_id_matches_numpy_linspace(host_lib):
     rng = np.random.default_rng(5)
-    pairs = [(1, 1), (1, 7), (2, 2), (5, 1), (40, 16), (23, 32), (1000, 768), (1024, 1024), (1531, 1024), (65536, 3)]
+    pairs = [(1, 1), (1, 7), (2, 2), (5, 1), (40, 16), (23, 32), (341, 768), (1000, 768), (1024, 1024), (1531, 1024), (65536, 3)]
     pairs += [(int(a), int(b)) for a, b in zip(rng.integers(1, 5000, 300), rng.integers(1, 1200, 300))]
     for n_raw, nf in pairs:
         want = np.linspace(0, n_raw - 1, nf).round().astype(np.uint16)
