@@ -235,15 +235,15 @@ def _variants_subprocess(script):
         return {"error": repr(e)}
 
 
-# Opt-in code paths that were written after this round's GPU budget was spent (fused detection loss, fused mixture heads)
+# Opt-in code paths that were written after this round's GPU budget was spent (fused detection loss, mixture heads, vote tail)
 # or whose gain was inside the box-to-box spread (internal joint permutation).  After the headline measurement is safe,
 # each is measured by a fresh child of this same script on the same box with the same step count, bounded in time, and
 # reported next to the headline -- never instead of it, and whatever happens in these processes cannot change it.
 EXPERIMENTS = [
-    ("fused_loss+fused_gmm", {"P2R_FUSED_LOSS": "1", "P2R_FUSED_GMM": "1"}),
+    ("fused_loss+gmm+vote", {"P2R_FUSED_LOSS": "1", "P2R_FUSED_GMM": "1", "P2R_FUSED_VOTE": "1"}),
     ("joint_perm", {"P2R_JOINT_PERM": "1"}),
     ("fused_loss", {"P2R_FUSED_LOSS": "1"}),
-    ("fused_gmm", {"P2R_FUSED_GMM": "1"}),
+    ("fused_gmm+vote", {"P2R_FUSED_GMM": "1", "P2R_FUSED_VOTE": "1"}),
 ]
 
 

@@ -294,6 +294,18 @@ int p2r_gmm_mix_grad(const void* logits, int logits_bf16, const void* mu, int mu
                      const void* eps, const void* dout, long long rows, int g, int d, void* dlogits, void* dmu, float* dls,
                      double* workspace, long long workspace_doubles, void* stream);
 
+/* ---- vote tail (ref: models/p2rnet/modules/vote_center.py:52-58 + network.py:89-90) -------------------------------------
+ * vote_xyz = seed_xyz + net[:, 0:3];  vote_feat = v / ||v||_2 with v = seed_feat + net[:, 3:]  in one launch.
+ * net [rows, 3+C] float32, or bfloat16 when net_bf16 (the output of the last voting conv); seed_xyz f32 with xyz_stride
+ * floats between rows (the hip joint of seed_skeleton, read in place); seed_feat f32 [rows, C].
+ * Outputs: vote_xyz f32 [rows,3], vote_feat f32 [rows,C] (L2-normalised), norm f32 [rows] (kept for the backward).      */
+int p2r_vote_tail(const void* net, int net_bf16, const float* seed_xyz, long long xyz_stride, const float* seed_feat,
+                  long long rows, int c, float* vote_xyz, float* vote_feat, float* norm, void* stream);
+/* backward: g_xyz f32 [rows,3] / g_feat f32 [rows,C] (either may be NULL = zero) -> d_net [rows,3+C] in net's type and
+ * d_seed_feat f32 [rows,C], every element written.                                                                  */
+int p2r_vote_tail_grad(const float* g_xyz, const float* g_feat, const float* vote_feat, const float* norm,
+                       long long rows, int c, void* d_net, int net_bf16, float* d_seed_feat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,8 @@ SIGNATURES = {
     "p2r_gmm_mix": [_vp, _c_int, _vp, _c_int, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_gmm_mix_workspace": [_c_ll, _c_int, _c_int],
     "p2r_gmm_mix_grad": [_vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_ll, _vp],
+    "p2r_vote_tail": [_vp, _c_int, _vp, _c_ll, _vp, _c_ll, _c_int, _vp, _vp, _vp, _vp],
+    "p2r_vote_tail_grad": [_vp, _vp, _vp, _vp, _c_ll, _c_int, _vp, _c_int, _vp, _vp],
 }
 _RESTYPES = {"p2r_last_error": ctypes.c_char_p, "p2r_detection_loss_workspace": _c_ll, "p2r_gmm_mix_workspace": _c_ll}
 

@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from .. import ap_helper
 from .registers import LOSSES, METHODS, MODULES
+from .vote_center import fused_vote_enabled
 
 
 @METHODS.register_module
@@ -76,8 +77,11 @@ class P2RNet(nn.Module):
     # ---- model API ------------------------------------------------------------------------------
     def _trunk(self, data):
         end_points = self.backbone(data["input_joints"], {})
-        xyz, features = self.centervoting(end_points["seed_skeleton"], end_points["seed_features"])
-        features = features.div(torch.norm(features, p=2, dim=2).unsqueeze(2))   # network.py:89-90
+        if fused_vote_enabled():     # residual adds + the normalisation below as one kernel (opt-in, vote_center.py)
+            xyz, features = self.centervoting(end_points["seed_skeleton"], end_points["seed_features"], normalize=True)
+        else:
+            xyz, features = self.centervoting(end_points["seed_skeleton"], end_points["seed_features"])
+            features = features.div(torch.norm(features, p=2, dim=2).unsqueeze(2))   # network.py:89-90
         end_points["vote_xyz"] = xyz
         end_points["vote_features"] = features
         return end_points, xyz, features

@@ -70,6 +70,19 @@ static inline T __shfl_down_sync(unsigned, T v, int off) {
   return r;
 }
 
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+  static_assert(sizeof(T) <= 16, "shuffle payload");
+  EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  memcpy(w.slot[lane], &v, sizeof(T));
+  pthread_barrier_wait(&w.bar);
+  T r;
+  memcpy(&r, w.slot[src & 31], sizeof(T));
+  pthread_barrier_wait(&w.bar);
+  return r;
+}
+
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }

@@ -105,7 +105,7 @@ def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_pat
             assert "--no-cpu-baseline" in sys.argv and sys.argv[sys.argv.index("--steps") + 1] == "2"
             if os.environ.get("P2R_JOINT_PERM") == "1":
                 os.abort()
-            both = os.environ.get("P2R_FUSED_LOSS") == "1" and os.environ.get("P2R_FUSED_GMM") == "1"
+            both = all(os.environ.get(k) == "1" for k in ("P2R_FUSED_LOSS", "P2R_FUSED_GMM", "P2R_FUSED_VOTE"))
             print(json.dumps({"value": 9.0 if both else 8.0, "ms_per_step": 1.0 if both else 2.0, "first_step_loss": 0.5,
                               "gpu_launches": 7, "config": {"cuda_graph": True}, "e2e": {"ms_per_step": 3.0}}))
             sys.exit(0)
@@ -116,8 +116,8 @@ def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_pat
     d = json.loads(io.out.strip())
     ex = d["experiments"]
     assert rc == 0 and d["value"] == 4.0 and ex["baseline"] == {"ms_per_step": 5.0, "first_step_loss": 0.5, "kernels_per_step": None}
-    assert ex["fused_loss+fused_gmm"]["ms_per_step"] == 1.0 and ex["fused_loss"]["ms_per_step"] == 2.0
-    assert ex["fused_gmm"]["e2e_ms_per_step"] == 3.0 and "error" in ex["joint_perm"]
+    assert ex["fused_loss+gmm+vote"]["ms_per_step"] == 1.0 and ex["fused_loss"]["ms_per_step"] == 2.0
+    assert ex["fused_gmm+vote"]["e2e_ms_per_step"] == 3.0 and "error" in ex["joint_perm"]
     monkeypatch.setenv("P2R_BENCH_EXPERIMENTS_BUDGET_S", "1")      # no time left: every experiment is skipped, line intact
     rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
     d = json.loads(io.out.strip())

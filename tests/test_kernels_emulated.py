@@ -29,7 +29,7 @@ def emu(tmp_path_factory):
                    [osp.join(ROOT, "tests", "csrc", "kernels_emu.cpp"), "-o", so], check=True)
     lib = ctypes.CDLL(so)
     for name in ("p2r_detection_loss", "p2r_detection_loss_grad", "p2r_gmm_mix", "p2r_gmm_mix_grad",
-                 "p2r_detection_loss_workspace", "p2r_gmm_mix_workspace"):
+                 "p2r_detection_loss_workspace", "p2r_gmm_mix_workspace", "p2r_vote_tail", "p2r_vote_tail_grad"):
         fn = getattr(lib, name)
         fn.argtypes = _lib.SIGNATURES[name]            # the product's own ctypes signatures
         fn.restype = _lib._RESTYPES.get(name, ctypes.c_int)
@@ -154,6 +154,46 @@ def test_mixture_kernels_under_emulation_equal_the_sequential_harness(emu, host_
 
 def _vp(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_vote_tail_kernels_under_emulation_match_torch_autograd(emu, bf16):
+    """vote_ops.cu (kernels + launchers) against the torch expressions they replace (vote_center.py:52-58, network.py:89-90)
+    and torch autograd of them; seed_xyz read in place out of a (B,S,J,3) skeleton tensor."""
+    B, S, J, C = 3, 43, 5, 256                                           # 129 rows: tail warps in the last block
+    gen = torch.Generator().manual_seed(3)
+    skel = torch.randn(B, S, J, 3, generator=gen)
+    seed_xyz = skel[:, :, 0]                                             # strided view, rows J*3 floats apart
+    sf = torch.randn(B, S, C, generator=gen).requires_grad_(True)
+    net = torch.randn(B * S, 3 + C, generator=gen)
+    if bf16:
+        net = net.bfloat16().float()
+    net.requires_grad_(True)
+    n3 = net.reshape(B, S, 3 + C)
+    want_xyz = seed_xyz + n3[..., 0:3]
+    v = sf + n3[..., 3:]
+    want_feat = v.div(torch.norm(v, p=2, dim=2).unsqueeze(2))
+    g_xyz, g_feat = torch.randn(B, S, 3, generator=gen), torch.randn(B, S, C, generator=gen)
+    torch.autograd.backward([want_xyz, want_feat], [g_xyz, g_feat])
+
+    rows = B * S
+    net_np = net.detach().numpy()
+    store = (net_np.view(np.uint32) >> 16).astype(np.uint16) if bf16 else net_np
+    skel_np, sf_np = skel.numpy(), sf.detach().numpy()
+    xyz, feat, norm = np.full((rows, 3), np.nan, np.float32), np.full((rows, C), np.nan, np.float32), np.full(rows, np.nan, np.float32)
+    assert emu.p2r_vote_tail(_p(store), int(bf16), _p(skel_np), J * 3, _p(sf_np), rows, C, _p(xyz), _p(feat), _p(norm), None) == 0
+    assert np.abs(xyz - want_xyz.detach().numpy().reshape(rows, 3)).max() <= 1e-6
+    assert np.abs(feat - want_feat.detach().numpy().reshape(rows, C)).max() <= 2e-7
+    d_net = np.full((rows, 3 + C), 0x7fc0 if bf16 else np.nan, np.uint16 if bf16 else np.float32)
+    d_sf = np.full((rows, C), np.nan, np.float32)
+    gx, gf = g_xyz.numpy().reshape(rows, 3).copy(), g_feat.numpy().reshape(rows, C).copy()
+    assert emu.p2r_vote_tail_grad(_p(gx), _p(gf), _p(feat), _p(norm), rows, C, _p(d_net), int(bf16), _p(d_sf), None) == 0
+    got_dnet = (d_net.astype(np.uint32) << 16).view(np.float32) if bf16 else d_net
+    assert np.abs(got_dnet - net.grad.numpy()).max() <= (8e-3 if bf16 else 2e-6) * np.abs(net.grad.numpy()).max()
+    assert np.abs(d_sf - sf.grad.numpy().reshape(rows, C)).max() <= 2e-6 * np.abs(sf.grad.numpy()).max()
+    # missing upstream gradients are zeros
+    assert emu.p2r_vote_tail_grad(None, None, _p(feat), _p(norm), rows, C, _p(d_net), int(bf16), _p(d_sf), None) == 0
+    assert not d_sf.any() and not d_net.any()
 
 
 def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):

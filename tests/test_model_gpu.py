@@ -267,8 +267,9 @@ def _fused_gmm_vs_torch_path(dev):
 
 
 _FUSED_REASON = ("the fused %s kernel(s) were written after the round's GPU budget was spent: the arithmetic is held to the "
-                 "oracle on the CPU (test_loss_math.py / test_gmm_math.py); the kernels are checked here in a process of "
-                 "their own, non-gating until they have passed on a B200")
+                 "oracle on the CPU (test_loss_math.py / test_gmm_math.py) and the kernels run under the host emulator "
+                 "(test_kernels_emulated.py); on the GPU they are checked here in a process of their own, non-gating "
+                 "until they have passed on a B200")
 
 
 def _run_isolated(flags, extra=""):
@@ -294,3 +295,44 @@ def test_fused_detection_loss_passes_the_parity_tests(cuda):
 @pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "mixture-head (csrc/gmm_ops.cu, P2R_FUSED_GMM=1)")
 def test_fused_mixture_heads_pass_the_parity_tests(cuda):
     _run_isolated(["P2R_FUSED_GMM"], "T._fused_gmm_vs_torch_path(dev); ")
+
+
+def _fused_vote_vs_torch_path(dev):
+    """CenterVoteModule with the fused tail vs its torch path + the normalisation of P2RNet._trunk (fp32 and bf16)."""
+    import os
+    from pose2room_b200.config import P2RConfig
+    from pose2room_b200.p2rnet.vote_center import CenterVoteModule
+    for precision in ("fp32", "bf16"):
+        if precision == "bf16":
+            from pose2room_b200 import gemm_sm100
+            gemm_sm100.install()
+        try:
+            torch.manual_seed(0)
+            mod = CenterVoteModule(P2RConfig(mode="train", joint_num=25, precision=precision)).to(dev).train()
+            skel = torch.randn(4, 512, 25, 3, device=dev)
+            base = torch.randn(4, 512, 256, device=dev)
+            g_xyz, g_feat = torch.randn(4, 512, 3, device=dev), torch.randn(4, 512, 256, device=dev)
+            res = []
+            for fused in (False, True):
+                mod.zero_grad(set_to_none=True)
+                sf = base.clone().requires_grad_(True)
+                if fused:
+                    xyz, feat = mod(skel, sf, normalize=True)
+                else:
+                    xyz, feat = mod(skel, sf)
+                    feat = feat.div(torch.norm(feat, p=2, dim=2).unsqueeze(2))
+                torch.autograd.backward([xyz, feat], [g_xyz, g_feat])
+                torch.cuda.synchronize()
+                res.append([t.detach().double().cpu() for t in (xyz, feat, sf.grad, mod.conv_input[2].conv.weight.grad,
+                                                                mod.conv_input[0].conv.weight.grad)])
+            tol = 2e-2 if precision == "bf16" else 1e-5      # bf16: d net is rounded to bf16 on the fused path
+            for name, a, b in zip(("xyz", "feat", "d_seed_features", "dW2", "dW0"), res[0], res[1]):
+                assert (a - b).abs().max().item() <= tol * max(1e-3, a.abs().max().item()), (precision, name)
+        finally:
+            if precision == "bf16":
+                gemm_sm100.uninstall()
+
+
+@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "vote-tail (csrc/vote_ops.cu, P2R_FUSED_VOTE=1)")
+def test_fused_vote_tail_passes_the_parity_tests(cuda):
+    _run_isolated(["P2R_FUSED_VOTE"], "T._fused_vote_vs_torch_path(dev); ")

@@ -5,7 +5,7 @@
 # 3. the bench (headline + data-path variants + experiments + census); 4. ncu: launch list of a step and a full capture of
 # the kernels that have none yet.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-python -m pytest tests/test_model_gpu.py tests/test_dataloader_gpu.py -m gpu -q --runxfail -k "fused or pipelined" \
+python -m pytest tests/test_model_gpu.py tests/test_dataloader_gpu.py tests/test_demo_sequence.py -m gpu -q --runxfail -k "fused or pipelined or demo" \
     > gpurun_out/r02_fused_tests.log 2>&1
 python -m pytest tests/test_zz_eval_1k_gpu.py -m gpu -q -s --runxfail > gpurun_out/r02_eval1k.log 2>&1
 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
