@@ -14,7 +14,7 @@ from tests import test_loss_math as TL  # noqa: E402
 
 lib = ctypes.CDLL(sys.argv[1])
 for name in ("p2r_detection_loss", "p2r_detection_loss_grad", "p2r_gmm_mix", "p2r_gmm_mix_grad",
-             "p2r_detection_loss_workspace", "p2r_gmm_mix_workspace"):
+             "p2r_detection_loss_workspace", "p2r_gmm_mix_workspace", "p2r_vote_tail", "p2r_vote_tail_grad"):
     fn = getattr(lib, name)
     fn.argtypes = _lib.SIGNATURES[name]
     fn.restype = _lib._RESTYPES.get(name, ctypes.c_int)
@@ -32,4 +32,11 @@ n = lib.p2r_gmm_mix_workspace(rows, G, D)
 ws, dl = np.zeros(n), np.zeros((rows, G), np.float32)
 dmu, dls = np.zeros((G, D), np.float32), np.zeros((G, D), np.float32)
 assert lib.p2r_gmm_mix_grad(p(lg), 0, p(mu), 0, p(ls), p(eps), p(dout), rows, G, D, p(dl), p(dmu), p(dls), p(ws), n, None) == 0
+C = 256
+net, sf = rng.normal(size=(rows, 3 + C)).astype(np.float32), rng.normal(size=(rows, C)).astype(np.float32)
+xyz_in, xyz, feat, norm = rng.normal(size=(rows, 3)).astype(np.float32), np.zeros((rows, 3), np.float32), \
+    np.zeros((rows, C), np.float32), np.zeros(rows, np.float32)
+assert lib.p2r_vote_tail(p(net), 0, p(xyz_in), 3, p(sf), rows, C, p(xyz), p(feat), p(norm), None) == 0
+dn, ds = np.zeros_like(net), np.zeros_like(sf)
+assert lib.p2r_vote_tail_grad(p(xyz), p(feat), p(feat), p(norm), rows, C, p(dn), 0, p(ds), None) == 0
 print("TSAN-DRIVER-DONE")

@@ -225,7 +225,7 @@ def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):
         d.mkdir()
         src = osp.join(ROOT, "pose2room_b200", "csrc")
         for f in os.listdir(src):
-            if f.endswith((".h", ".cuh")) or f in ("loss_ops.cu", "gmm_ops.cu"):
+            if f.endswith((".h", ".cuh")) or f in ("loss_ops.cu", "gmm_ops.cu", "vote_ops.cu"):
                 shutil.copy(osp.join(src, f), d / f)
         entry = open(osp.join(ROOT, "tests", "csrc", "kernels_emu.cpp")).read().replace("../../pose2room_b200/csrc/", "")
         (d / "kernels_emu_entry.cpp").write_text(entry)
