@@ -19,7 +19,7 @@
 #define KNN_TILE 256
 __global__ void __launch_bounds__(128)
 knn_kernel(int c, int n, int k, const float* __restrict__ x, long long* __restrict__ idx) {
-  extern __shared__ float s_x[];  // [c][KNN_TILE] + xx[KNN_TILE]
+  P2R_DYN_SMEM(float, s_x);  // [c][KNN_TILE] + xx[KNN_TILE]
   float* s_xx = s_x + (size_t)c * KNN_TILE;
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,7 +86,7 @@ extern "C" int p2r_knn_graph(const float* x, int b, int c, int n, int k, long lo
   P2R_CHECK_ARG(smem <= 200 * 1024, "p2r_knn_graph (feature dim too large for the smem tile)");
   if (smem > 48 * 1024) cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(p2r_ceil_div(n, 128), b);
-  knn_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(c, n, k, x, idx);
+  P2R_LAUNCH(knn_kernel, grid, 128, smem, (cudaStream_t)stream, c, n, k, x, idx);
   P2R_RETURN_LAUNCH("p2r_knn_graph");
 }
 
@@ -110,7 +110,7 @@ extern "C" int p2r_graph_offset(const float* x, const long long* idx, int b, int
   P2R_CHECK_ARG(b >= 0 && d3 > 0 && n > 0 && k > 0, "p2r_graph_offset");
   const long long total = (long long)b * n * k * d3;
   if (total == 0) return 0;
-  graph_offset_kernel<<<p2r_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d3, n, k, x, idx, out, total);
+  P2R_LAUNCH(graph_offset_kernel, p2r_ceil_div(total, 256), 256, 0, (cudaStream_t)stream, d3, n, k, x, idx, out, total);
   P2R_RETURN_LAUNCH("p2r_graph_offset");
 }
 
@@ -126,7 +126,7 @@ extern "C" int p2r_graph_offset(const float* x, const long long* idx, int b, int
 // ================================================================================================
 __global__ void __launch_bounds__(256)
 uniform_seed_kernel(int T, int S, int stride, const float* __restrict__ hip, long long* __restrict__ seed) {
-  extern __shared__ float s_cum[];  // [T]
+  P2R_DYN_SMEM(float, s_cum);  // [T]
   const int b = blockIdx.x;
   const float* h = hip + (size_t)b * T * stride;
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -168,7 +168,7 @@ extern "C" int p2r_uniform_seed_inds(const float* hip, int stride, int b, int t,
   const size_t smem = (size_t)t * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(uniform_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  uniform_seed_kernel<<<b, 256, smem, (cudaStream_t)stream>>>(t, s, stride, hip, seed_inds);
+  P2R_LAUNCH(uniform_seed_kernel, b, 256, smem, (cudaStream_t)stream, t, s, stride, hip, seed_inds);
   P2R_RETURN_LAUNCH("p2r_uniform_seed_inds");
 }
 
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128)
 nn_distance_kernel(int n, int m, int c, int mode, float delta, const float* __restrict__ pc1,
                    const float* __restrict__ pc2, float* __restrict__ dist1, long long* __restrict__ idx1,
                    float* __restrict__ dist2, long long* __restrict__ idx2) {
-  extern __shared__ float s_other[];  // [tile][c]
+  P2R_DYN_SMEM(float, s_other);  // [tile][c]
   const int b = blockIdx.y;
   const bool second = blockIdx.z == 1;
   const int nr = second ? m : n, no = second ? n : m;
@@ -239,8 +239,7 @@ extern "C" int p2r_nn_distance(const float* pc1, const float* pc2, int b, int n,
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(nn_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(p2r_ceil_div(mx, 128), b, 2);
-  nn_distance_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(n, m, c, mode, delta, pc1, pc2, dist1, idx1, dist2,
-                                                                idx2);
+  P2R_LAUNCH(nn_distance_kernel, grid, 128, smem, (cudaStream_t)stream, n, m, c, mode, delta, pc1, pc2, dist1, idx1, dist2, idx2);
   P2R_RETURN_LAUNCH("p2r_nn_distance");
 }
 
@@ -294,8 +293,7 @@ extern "C" int p2r_nn_distance_grad(const float* pc1, const float* pc2, const lo
   P2R_CHECK_ARG(b >= 0 && n > 0 && m > 0 && c > 0 && mode >= 0 && mode <= 2, "p2r_nn_distance_grad");
   const long long total = (long long)b * (n + m) * c;
   if (total == 0) return 0;
-  nn_distance_grad_kernel<<<p2r_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      n, m, c, mode, delta, pc1, pc2, idx1, idx2, g1, g2, grad_pc1, grad_pc2, b);
+  P2R_LAUNCH(nn_distance_grad_kernel, p2r_ceil_div(total, 256), 256, 0, (cudaStream_t)stream, n, m, c, mode, delta, pc1, pc2, idx1, idx2, g1, g2, grad_pc1, grad_pc2, b);
   P2R_RETURN_LAUNCH("p2r_nn_distance_grad");
 }
 
@@ -391,8 +389,7 @@ extern "C" int p2r_decode_boxes(const float* center, const float* log_size, cons
   P2R_CHECK_ARG(b >= 0 && k > 0 && t > 0 && hip_stride >= 3, "p2r_decode_boxes");
   if (b == 0) return 0;
   const int total = b * k;
-  decode_boxes_kernel<<<p2r_ceil_div((long long)total * 32, 128), 128, 0, (cudaStream_t)stream>>>(
-      k, t, center, log_size, heading_sincos, hip, hip_stride, contact, corners, aabb, nonempty, total);
+  P2R_LAUNCH(decode_boxes_kernel, p2r_ceil_div((long long)total * 32, 128), 128, 0, (cudaStream_t)stream, k, t, center, log_size, heading_sincos, hip, hip_stride, contact, corners, aabb, nonempty, total);
   P2R_RETURN_LAUNCH("p2r_decode_boxes");
 }
 
@@ -488,7 +485,7 @@ extern "C" int p2r_nms3d(const double* boxes, const double* score, const unsigne
                          int k, double thr, int old_type, unsigned char* keep, int* order, void* stream) {
   P2R_CHECK_ARG(b >= 0 && k > 0 && k <= NMS_MAXK, "p2r_nms3d");
   if (b == 0) return 0;
-  nms3d_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(k, thr, old_type, boxes, score, valid, cls, keep, order);
+  P2R_LAUNCH(nms3d_kernel, b, 256, 0, (cudaStream_t)stream, k, thr, old_type, boxes, score, valid, cls, keep, order);
   P2R_RETURN_LAUNCH("p2r_nms3d");
 }
 
@@ -574,7 +571,6 @@ extern "C" int p2r_box3d_iou(const double* corners1, const double* corners2, int
                              double* iou2d, void* stream) {
   P2R_CHECK_ARG(np_ >= 0 && ng >= 0, "p2r_box3d_iou");
   if (np_ == 0 || ng == 0) return 0;
-  box3d_iou_kernel<<<p2r_ceil_div((long long)np_ * ng, 128), 128, 0, (cudaStream_t)stream>>>(np_, ng, corners1,
-                                                                                              corners2, iou3d, iou2d);
+  P2R_LAUNCH(box3d_iou_kernel, p2r_ceil_div((long long)np_ * ng, 128), 128, 0, (cudaStream_t)stream, np_, ng, corners1, corners2, iou3d, iou2d);
   P2R_RETURN_LAUNCH("p2r_box3d_iou");
 }

@@ -33,7 +33,7 @@ static inline int p2r_ceil_div(long long a, long long b) { return (int)((a + b -
 // function pointer to a template instance first).
 #ifdef P2R_HOST_EMULATION
 #define P2R_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+  emu_launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
 #define P2R_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_dyn_smem)
 #else
 #define P2R_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
@@ -41,8 +41,6 @@ static inline int p2r_ceil_div(long long a, long long b) { return (int)((a + b -
   extern __shared__ __align__(16) unsigned char name##_raw[];   \
   type* name = reinterpret_cast<type*>(name##_raw)
 #endif
-
-#ifndef P2R_HOST_EMULATION   // everything below is device-only (intrinsics, PTX)
 
 // ---- exact-order fp32 arithmetic -----------------------------------------------------------
 // The reference's kernels are compiled with nvcc's default -fmad=true; its SASS for sm_100a
@@ -65,6 +63,8 @@ __device__ __forceinline__ float p2r_sqnorm3_xyz(float x, float y, float z) {
   t = __fmaf_rn(z, z, t);
   return t;
 }
+
+#ifndef P2R_HOST_EMULATION   // everything below is device-only (PTX)
 
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk, SASS: UBLKCP) ---------------------------------
 __device__ __forceinline__ uint32_t p2r_smem_u32(const void* p) {

@@ -1,14 +1,17 @@
 // cuda_emu.h -- TEST HARNESS (CPU): a minimal CUDA execution-model emulator, enough to run the SIMT kernels of
 // pose2room_b200/csrc that use nothing beyond threads / blocks, static + dynamic shared memory, __syncthreads, warp
-// shuffles, global atomics and __threadfence (loss_ops.cu, gmm_ops.cu) on the host, so that their PLUMBING -- block
-// reductions, the last-block-finalises pattern, arg-min merges, indexing, the launchers' grid / workspace arithmetic --
-// is exercised without a GPU (tests/test_kernels_emulated.py).  Not a performance model and not part of the product:
-// compiled only by the test (g++ -DP2R_HOST_EMULATION), never shipped, never loaded by pose2room_b200/.
+// shuffles / votes, global atomics and __threadfence (loss_ops.cu, gmm_ops.cu, vote_ops.cu, geometry_ops.cu) on the
+// host, so that their PLUMBING -- block reductions, the last-block-finalises pattern, arg-min merges, indexing, tail
+// blocks, the launchers' grid / workspace arithmetic -- is exercised without a GPU (tests/test_kernels_emulated.py,
+// tests/test_eval_kernels_emulated.py).  Not a performance model and not part of the product: compiled only by the
+// tests (g++ -DP2R_HOST_EMULATION), never shipped, never loaded by pose2room_b200/.
 //
-// Execution: blocks run one after the other in a SHUFFLED order (the last block to finish is not always the last index);
-// the threads of a block are real pthreads, __syncthreads is a pthread barrier over the block, a warp shuffle is an
-// exchange through a per-warp slot array between two per-warp barriers.  `__shared__` becomes `static` (blocks are
-// sequential, so one copy is right); dynamic shared memory is one buffer per launch.
+// Execution: one pool of blockDim.x pthreads per launch walks over the blocks of the grid one after the other, in a
+// SHUFFLED order (the last block to finish is not always the last index).  __syncthreads is a barrier over the threads
+// of the block that have not returned from the kernel yet (like the hardware's), a warp shuffle / vote is an exchange
+// through a per-warp slot array between two per-warp barriers.  `__shared__` becomes `static` (blocks are sequential, so
+// one copy is right); dynamic shared memory is one buffer per launch.  Floating-point intrinsics map to the plain
+// operation: compile with -ffp-contract=off so that nothing is fused behind their back.
 #pragma once
 #include <pthread.h>
 #include <math.h>
@@ -44,51 +47,115 @@ template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 
-// ---- block / warp state of the running launch -------------------------------------------------------------------
+// ---- a barrier whose participants may leave (a thread that returns from the kernel stops counting) ----------------
+struct EmuBarrier {
+  pthread_mutex_t m;
+  pthread_cond_t cv;
+  int count, waiting;
+  unsigned gen;
+  EmuBarrier() : count(0), waiting(0), gen(0) { pthread_mutex_init(&m, nullptr); pthread_cond_init(&cv, nullptr); }
+  ~EmuBarrier() { pthread_mutex_destroy(&m); pthread_cond_destroy(&cv); }
+  void reset(int n) { count = n; waiting = 0; }
+  void wait() {
+    pthread_mutex_lock(&m);
+    if (++waiting >= count) {
+      waiting = 0; ++gen;
+      pthread_cond_broadcast(&cv);
+    } else {
+      const unsigned g = gen;
+      while (g == gen) pthread_cond_wait(&cv, &m);
+    }
+    pthread_mutex_unlock(&m);
+  }
+  void leave() {
+    pthread_mutex_lock(&m);
+    --count;
+    if (count > 0 && waiting >= count) {
+      waiting = 0; ++gen;
+      pthread_cond_broadcast(&cv);
+    }
+    pthread_mutex_unlock(&m);
+  }
+};
+
 struct EmuWarp {
-  pthread_barrier_t bar;
+  EmuBarrier bar;
   unsigned char slot[32][16];
 };
-static pthread_barrier_t emu_block_bar;
+static EmuBarrier* emu_block_bar = nullptr;
 static std::vector<EmuWarp>* emu_warps = nullptr;
 static unsigned char* emu_dyn_smem = nullptr;
 static unsigned long long emu_launches = 0;
 
-static inline void __syncthreads() { pthread_barrier_wait(&emu_block_bar); }
+static inline void __syncthreads() { emu_block_bar->wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { (*emu_warps)[threadIdx.x >> 5].bar.wait(); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
+// every lane publishes v, reads the slot of lane `src` (its own value when src is outside the warp)
 template <typename T>
-static inline T __shfl_down_sync(unsigned, T v, int off) {
+static inline T emu_exchange(T v, int src) {
   static_assert(sizeof(T) <= 16, "shuffle payload");
   EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   memcpy(w.slot[lane], &v, sizeof(T));
-  pthread_barrier_wait(&w.bar);
+  w.bar.wait();
   T r = v;
-  if (lane + off < 32) memcpy(&r, w.slot[lane + off], sizeof(T));
-  pthread_barrier_wait(&w.bar);
+  if (src >= 0 && src < 32) memcpy(&r, w.slot[src], sizeof(T));
+  w.bar.wait();
   return r;
 }
-
 template <typename T>
-static inline T __shfl_sync(unsigned, T v, int src) {
-  static_assert(sizeof(T) <= 16, "shuffle payload");
+static inline T __shfl_down_sync(unsigned, T v, int off) { return emu_exchange(v, (int)(threadIdx.x & 31) + off); }
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) { return emu_exchange(v, (int)(threadIdx.x & 31) ^ mask); }
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src & 31); }
+static inline int __any_sync(unsigned, int pred) {
   EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  memcpy(w.slot[lane], &v, sizeof(T));
-  pthread_barrier_wait(&w.bar);
-  T r;
-  memcpy(&r, w.slot[src & 31], sizeof(T));
-  pthread_barrier_wait(&w.bar);
-  return r;
+  const int lane = threadIdx.x & 31, p = pred != 0;
+  memcpy(w.slot[lane], &p, sizeof(int));
+  w.bar.wait();
+  int any = 0;
+  for (int l = 0; l < 32; ++l) { int q; memcpy(&q, w.slot[l], sizeof(int)); any |= q; }
+  w.bar.wait();
+  return any;
 }
 
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float atomicAdd(float* p, float v) {
+  unsigned old, neu;
+  float f;
+  do {
+    old = __atomic_load_n((unsigned*)p, __ATOMIC_SEQ_CST);
+    memcpy(&f, &old, 4); f += v; memcpy(&neu, &f, 4);
+  } while (!__atomic_compare_exchange_n((unsigned*)p, &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  memcpy(&f, &old, 4);
+  return f;
+}
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 template <typename T>
 static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+// round-to-nearest intrinsics = the plain operation (the build uses -ffp-contract=off); fma intrinsics = libm fma
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+template <typename T>
+static inline T min(T a, T b) { return a < b ? a : b; }
+template <typename T>
+static inline T max(T a, T b) { return a > b ? a : b; }
+static inline long long min(long long a, int b) { return a < b ? a : (long long)b; }
+static inline long long min(int a, long long b) { return a < b ? (long long)a : b; }
 
 // bf16 storage type: enough for the template specialisations to compile and round-trip
 struct __nv_bfloat16 { unsigned short x; };
@@ -100,44 +167,67 @@ static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------------------
-struct EmuThreadArg { const std::function<void()>* fn; unsigned tid, bid; };
+struct EmuLaunch {
+  const std::function<void()>* fn;
+  std::vector<unsigned> order;       // linear block ids, shuffled
+  pthread_barrier_t gate;            // all pool threads, between blocks
+  EmuBarrier block_bar;
+  std::vector<EmuWarp> warps;
+  unsigned nthreads;
+};
+struct EmuThreadArg { EmuLaunch* L; unsigned tid; };
+
 static void* emu_thread_main(void* p) {
   EmuThreadArg* a = (EmuThreadArg*)p;
+  EmuLaunch& L = *a->L;
   threadIdx.x = a->tid; threadIdx.y = threadIdx.z = 0;
-  blockIdx.x = a->bid; blockIdx.y = blockIdx.z = 0;
-  (*a->fn)();
+  for (unsigned lin : L.order) {
+    if (a->tid == 0) {               // (the gate below orders this reset after every thread has left the previous block)
+      L.block_bar.reset((int)L.nthreads);
+      for (auto& w : L.warps) w.bar.reset(32);
+    }
+    pthread_barrier_wait(&L.gate);
+    blockIdx.x = lin % gridDim.x;
+    blockIdx.y = (lin / gridDim.x) % gridDim.y;
+    blockIdx.z = lin / (gridDim.x * gridDim.y);
+    (*L.fn)();
+    L.warps[a->tid >> 5].bar.leave();
+    L.block_bar.leave();
+    pthread_barrier_wait(&L.gate);
+  }
   return nullptr;
 }
 
-// 1-D grids and blocks (all the emulated kernels use); block size a multiple of 32
-static inline void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& fn) {
-  if (block % 32 != 0 || block == 0 || grid == 0) abort();
-  gridDim = dim3(grid); blockDim = dim3(block);
+// any grid; 1-D blocks whose size is a multiple of 32
+static inline void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn) {
+  if (block.y != 1 || block.z != 1 || block.x % 32 != 0 || block.x == 0 || grid.x * grid.y * grid.z == 0) abort();
+  gridDim = grid; blockDim = block;
   std::vector<unsigned char> dyn(smem + 16);
   emu_dyn_smem = dyn.data() + ((16 - ((uintptr_t)dyn.data() & 15)) & 15);
-  std::vector<unsigned> order(grid);
-  for (unsigned i = 0; i < grid; ++i) order[i] = i;
+  EmuLaunch L;
+  L.fn = &fn;
+  L.nthreads = block.x;
+  L.order.resize((size_t)grid.x * grid.y * grid.z);
+  for (size_t i = 0; i < L.order.size(); ++i) L.order[i] = (unsigned)i;
   std::mt19937 rng(12345u + (unsigned)(emu_launches++));
-  std::shuffle(order.begin(), order.end(), rng);
-  std::vector<EmuWarp> warps(block / 32);
-  emu_warps = &warps;
-  std::vector<pthread_t> th(block);
-  std::vector<EmuThreadArg> args(block);
+  std::shuffle(L.order.begin(), L.order.end(), rng);
+  L.warps = std::vector<EmuWarp>(block.x / 32);
+  pthread_barrier_init(&L.gate, nullptr, block.x);
+  emu_block_bar = &L.block_bar;
+  emu_warps = &L.warps;
+  std::vector<pthread_t> th(block.x);
+  std::vector<EmuThreadArg> args(block.x);
   pthread_attr_t attr;
   pthread_attr_init(&attr);
-  pthread_attr_setstacksize(&attr, 256 * 1024);
-  for (unsigned b : order) {
-    pthread_barrier_init(&emu_block_bar, nullptr, block);
-    for (auto& w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
-    for (unsigned t = 0; t < block; ++t) {
-      args[t] = EmuThreadArg{&fn, t, b};
-      if (pthread_create(&th[t], &attr, emu_thread_main, &args[t]) != 0) abort();
-    }
-    for (unsigned t = 0; t < block; ++t) pthread_join(th[t], nullptr);
-    pthread_barrier_destroy(&emu_block_bar);
-    for (auto& w : warps) pthread_barrier_destroy(&w.bar);
+  pthread_attr_setstacksize(&attr, 512 * 1024);
+  for (unsigned t = 0; t < block.x; ++t) {
+    args[t] = EmuThreadArg{&L, t};
+    if (pthread_create(&th[t], &attr, emu_thread_main, &args[t]) != 0) abort();
   }
+  for (unsigned t = 0; t < block.x; ++t) pthread_join(th[t], nullptr);
   pthread_attr_destroy(&attr);
+  pthread_barrier_destroy(&L.gate);
+  emu_block_bar = nullptr;
   emu_warps = nullptr;
   emu_dyn_smem = nullptr;
 }

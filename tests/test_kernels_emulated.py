@@ -224,10 +224,12 @@ def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):
         d = tmp_path / tag
         d.mkdir()
         src = osp.join(ROOT, "pose2room_b200", "csrc")
+        entry = open(osp.join(ROOT, "tests", "csrc", "kernels_emu.cpp")).read()
+        emulated = [l.split("/")[-1].rstrip('"\n') for l in entry.splitlines() if l.startswith('#include "../../pose2room_b200/csrc/')]
         for f in os.listdir(src):
-            if f.endswith((".h", ".cuh")) or f in ("loss_ops.cu", "gmm_ops.cu", "vote_ops.cu"):
+            if f.endswith((".h", ".cuh")) or f in emulated:
                 shutil.copy(osp.join(src, f), d / f)
-        entry = open(osp.join(ROOT, "tests", "csrc", "kernels_emu.cpp")).read().replace("../../pose2room_b200/csrc/", "")
+        entry = entry.replace("../../pose2room_b200/csrc/", "")
         (d / "kernels_emu_entry.cpp").write_text(entry)
         if mutate:
             p = d / "loss_ops.cu"
