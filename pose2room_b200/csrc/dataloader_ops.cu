@@ -26,7 +26,7 @@ make_batch_kernel(const float* __restrict__ joints, const float* __restrict__ vo
                   const double* __restrict__ params, int num_frames, int J, int out_c,
                   float* __restrict__ input_joints, float* __restrict__ vote_label,
                   long long* __restrict__ vote_label_mask) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P2R_DYN_SMEM(unsigned char, smem_raw);
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * P2R_DL_FRAMES;
   const int nf = min(P2R_DL_FRAMES, num_frames - t0);
@@ -87,6 +87,15 @@ make_batch_kernel(const float* __restrict__ joints, const float* __restrict__ vo
 // is no spin-wait in this kernel.
 #define P2R_DL_STAGES 3
 
+#ifdef P2R_HOST_EMULATION
+// host emulator: the copy happens at issue time (the strictest schedule: a stage that is overwritten while another
+// thread still reads it, or read before the matching wait + barrier, shows up as a data race / a wrong value)
+__device__ __forceinline__ void p2r_cp_async4(void* dst, const void* src) { memcpy(dst, src, 4); }
+__device__ __forceinline__ void p2r_cp_async8(void* dst, const void* src) { memcpy(dst, src, 8); }
+__device__ __forceinline__ void p2r_cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void p2r_cp_async_wait() {}
+#else
 __device__ __forceinline__ void p2r_cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(p2r_smem_u32(dst)), "l"(src) : "memory");
 }
@@ -96,6 +105,7 @@ __device__ __forceinline__ void p2r_cp_async8(void* dst, const void* src) {
 __device__ __forceinline__ void p2r_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void p2r_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 __global__ void __launch_bounds__(P2R_DL_THREADS)
 make_batch_pipe_kernel(const float* __restrict__ joints, const float* __restrict__ votes,
@@ -104,7 +114,7 @@ make_batch_pipe_kernel(const float* __restrict__ joints, const float* __restrict
                        int total_groups, float* __restrict__ input_joints, float* __restrict__ vote_label,
                        long long* __restrict__ vote_label_mask) {
   static_assert(P2R_DL_THREADS == 32 * P2R_DL_FRAMES, "one warp per frame of a group");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P2R_DYN_SMEM(unsigned char, smem_raw);
   const int rowj = J * 3, rowv = J * 10, rowo = J * out_c, rowl = J * 9;
   // layout (8-byte quantities first): mask | stage[3] { votes rows | joint rows } | out joints | out votes
   long long* s_mask = reinterpret_cast<long long*>(smem_raw);                      // [FR * J]
@@ -214,9 +224,9 @@ static int make_batch_launch(int variant, const float* joints, const float* vote
     const long long total = (long long)groups_per_item * b;
     const long long resident = (long long)P2R_SM_COUNT * per_sm;
     const int grid = (int)(total < resident ? total : resident);
-    make_batch_pipe_kernel<<<grid, P2R_DL_THREADS, smem, (cudaStream_t)stream>>>(
-        joints, votes, frame_start, sample_ids, params, num_frames, j, out_channels, groups_per_item, (int)total,
-        input_joints, vote_label, vote_label_mask);
+    P2R_LAUNCH(make_batch_pipe_kernel, grid, P2R_DL_THREADS, smem, (cudaStream_t)stream, joints, votes, frame_start,
+               sample_ids, params, num_frames, j, out_channels, groups_per_item, (int)total, input_joints, vote_label,
+               vote_label_mask);
     P2R_RETURN_LAUNCH("p2r_make_batch");
   }
   const size_t smem = (size_t)P2R_DL_FRAMES * j * (sizeof(long long) + sizeof(float) * (3 + 10 + out_channels + 9));
@@ -226,9 +236,8 @@ static int make_batch_launch(int variant, const float* joints, const float* vote
     if (e != cudaSuccess) { p2r_set_last_error("p2r_make_batch", (int)e); return (int)e; }
   }
   dim3 grid(p2r_ceil_div(num_frames, P2R_DL_FRAMES), b);
-  make_batch_kernel<<<grid, P2R_DL_THREADS, smem, (cudaStream_t)stream>>>(
-      joints, votes, frame_start, sample_ids, params, num_frames, j, out_channels, input_joints, vote_label,
-      vote_label_mask);
+  P2R_LAUNCH(make_batch_kernel, grid, P2R_DL_THREADS, smem, (cudaStream_t)stream, joints, votes, frame_start, sample_ids,
+             params, num_frames, j, out_channels, input_joints, vote_label, vote_label_mask);
   P2R_RETURN_LAUNCH("p2r_make_batch");
 }
 

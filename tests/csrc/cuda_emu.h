@@ -46,6 +46,8 @@ enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <typename F>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 
 // ---- a barrier whose participants may leave (a thread that returns from the kernel stops counting) ----------------
 struct EmuBarrier {

@@ -39,4 +39,15 @@ xyz_in, xyz, feat, norm = rng.normal(size=(rows, 3)).astype(np.float32), np.zero
 assert lib.p2r_vote_tail(p(net), 0, p(xyz_in), 3, p(sf), rows, C, p(xyz), p(feat), p(norm), None) == 0
 dn, ds = np.zeros_like(net), np.zeros_like(sf)
 assert lib.p2r_vote_tail_grad(p(xyz), p(feat), p(feat), p(norm), rows, C, p(dn), 0, p(ds), None) == 0
+# sample -> batch, both variants (variant 2: several work items per CTA, so its cp.async ring wraps)
+fn = lib.p2r_make_batch_variant
+fn.argtypes = _lib.SIGNATURES["p2r_make_batch_variant"]
+fn.restype = ctypes.c_int
+Jn, Bn, Tn = 7, 2, 81       # 22 work items; the sanitizer build has P2R_SM_COUNT=4 -> 5-6 items per persistent CTA
+fs = np.array([0, 50, 61], np.int64)
+jt, vt = rng.normal(size=(61, Jn, 3)).astype(np.float32), rng.normal(size=(61, Jn, 10)).astype(np.float32)
+ids, par = np.array([1, 0], np.int32), np.zeros((Bn, 16))
+o = [np.zeros((Bn, Tn, Jn, 3), np.float32), np.zeros((Bn, Tn, Jn, 9), np.float32), np.zeros((Bn, Tn, Jn), np.int64)]
+for variant in (1, 2):
+    assert fn(variant, p(jt), p(vt), p(fs), p(ids), p(par), Bn, Tn, Jn, 3, p(o[0]), p(o[1]), p(o[2]), None) == 0
 print("TSAN-DRIVER-DONE")

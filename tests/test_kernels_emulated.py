@@ -212,7 +212,7 @@ def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):
     def build_and_run(csrc_dir, tag):
         so = str(tmp_path / ("emu_tsan_%s.so" % tag))
         subprocess.run(["g++", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-shared", "-fPIC",
-                        "-std=c++17", "-w", "-DP2R_HOST_EMULATION", "-DP2R_EMU_CSRC_DIR", "-I", csrc_dir] +
+                        "-std=c++17", "-w", "-DP2R_HOST_EMULATION", "-DP2R_SM_COUNT=4", "-I", csrc_dir] +
                        sum((["-I", i] for i in inc), []) + [osp.join(csrc_dir, "kernels_emu_entry.cpp"), "-o", so], check=True)
         env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0")
         r = subprocess.run([sys.executable, osp.join(ROOT, "tests", "emu_tsan_driver.py"), so], env=env, capture_output=True,
@@ -241,3 +241,46 @@ def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):
 
     assert build_and_run(stage("clean", False), "clean") == 0
     assert build_and_run(stage("mutant", True), "mutant") > 0
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_make_batch_kernels_under_emulation_equal_the_host_harness(emu_dl, tmp_path_factory, variant):
+    """Both data-movement variants of the sample -> batch kernel (csrc/dataloader_ops.cu, launchers included) against the
+    sequential harness over the same arithmetic header (tests/csrc/make_batch_host.c, itself bit-exact against the
+    reference goldens in test_dataloader_math.py): ragged samples, up- and down-sampling, augmented and plain items, a tail
+    group (T = 513), 4-channel output -- and, for variant 2, several work items per persistent CTA (its 3-stage ring wraps)."""
+    from tests import test_dataloader_math as TD
+    host = TD.host_lib.__wrapped__(tmp_path_factory)
+    rng = np.random.default_rng(5)
+    J, B, T, C = 25, 5, 513, 4
+    frames = np.array([30, 700, 1, 513, 1200])
+    fs = np.zeros(len(frames) + 1, np.int64)
+    fs[1:] = np.cumsum(frames)
+    joints = rng.standard_normal((int(fs[-1]), J, 3)).astype(np.float32)
+    votes = rng.standard_normal((int(fs[-1]), J, 10)).astype(np.float32)
+    votes[..., 0] = rng.integers(0, 2, size=votes.shape[:2])
+    ids = np.array([4, 0, 2, 3, 1], np.int32)
+    params = np.zeros((B, 16))
+    for b in range(B):
+        if b % 2 == 0:                                      # augmented: flip / rotation / shift / floor
+            th = rng.uniform(-np.pi, np.pi)
+            params[b, 0], params[b, 1] = 1.0, float(b % 4 == 0)
+            params[b, 2:11] = np.array([[np.cos(th), 0, -np.sin(th)], [0, 1, 0], [np.sin(th), 0, np.cos(th)]]).ravel()
+            params[b, 11:14] = [0.3, 0.0, -0.2]
+        params[b, 14] = 0.05
+    want = [np.empty((B, T, J, C), np.float32), np.empty((B, T, J, 9), np.float32), np.empty((B, T, J), np.int64)]
+    host.host_make_batch(_vp(joints), _vp(votes), _vp(fs), _vp(ids), _vp(params), B, T, J, C, *[_vp(a) for a in want])
+    got = [np.full((B, T, J, C), np.nan, np.float32), np.full((B, T, J, 9), np.nan, np.float32), np.full((B, T, J), -5, np.int64)]
+    rc = emu_dl.p2r_make_batch_variant(variant, _p(joints), _p(votes), _p(fs), _p(ids), _p(params), B, T, J, C,
+                                       *[_p(a) for a in got], None)
+    assert rc == 0, emu_dl.emu_last_error()
+    for w, g_ in zip(want, got):
+        assert np.array_equal(w.view(np.uint8), g_.view(np.uint8))      # bit-exact, every element written
+
+
+@pytest.fixture(scope="module")
+def emu_dl(emu):
+    fn = emu.p2r_make_batch_variant
+    fn.argtypes = _lib.SIGNATURES["p2r_make_batch_variant"]
+    fn.restype = ctypes.c_int
+    return emu
