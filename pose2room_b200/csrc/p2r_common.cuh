@@ -131,4 +131,11 @@ __device__ __forceinline__ void p2r_stage_floats(float* dst, const float* __rest
   __syncthreads();
 }
 
+#else   // host emulation: the bulk-TMA staging helper degrades to a plain cooperative copy, the mbarrier to nothing
+__device__ __forceinline__ void p2r_mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void p2r_fence_mbar_init() {}
+__device__ __forceinline__ void p2r_stage_floats(float* dst, const float* __restrict__ src, int nfloats, uint64_t*, uint32_t) {
+  for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
 #endif  // !P2R_HOST_EMULATION

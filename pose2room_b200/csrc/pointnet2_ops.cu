@@ -160,7 +160,8 @@ template <int PPT, int THREADS>
 static void launch_fps(int b, int n, int m, int bs_ref, int cpt, const float* xyz, int* idxs, cudaStream_t st) {
   int log2bs = 0;
   while ((1 << log2bs) < bs_ref) ++log2bs;
-  fps_kernel<PPT, THREADS><<<b, THREADS, 0, st>>>(n, m, bs_ref, log2bs, cpt, xyz, idxs);
+  auto kern = fps_kernel<PPT, THREADS>;
+  P2R_LAUNCH(kern, b, THREADS, 0, st, n, m, bs_ref, log2bs, cpt, xyz, idxs);
 }
 
 extern "C" int p2r_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idxs, float* scratch,
@@ -183,7 +184,7 @@ extern "C" int p2r_furthest_point_sampling(const float* xyz, int b, int n, int m
     P2R_CHECK_ARG(scratch != nullptr, "p2r_furthest_point_sampling (n > 32768 needs b*n floats of scratch)");
     int log2bs = 0;
     while ((1 << log2bs) < bs_ref) ++log2bs;
-    fps_kernel_large<<<b, 1024, 0, st>>>(n, m, bs_ref, log2bs, cpt, xyz, scratch, idxs);
+    P2R_LAUNCH(fps_kernel_large, b, 1024, 0, st, n, m, bs_ref, log2bs, cpt, xyz, scratch, idxs);
   }
   P2R_RETURN_LAUNCH("p2r_furthest_point_sampling");
 }
@@ -213,7 +214,8 @@ extern "C" int p2r_gather_points(const float* points, const int* idx, int b, int
   if (b == 0 || c == 0 || m == 0) return 0;
   const int cpc = c >= 64 ? 16 : (c >= 8 ? 4 : 1);
   dim3 grid(p2r_ceil_div(m, 256), p2r_ceil_div(c, cpc), b);
-  gather_points_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, m, cpc, points, idx, out);
+  auto kern = gather_points_kernel<false>;
+  P2R_LAUNCH(kern, grid, 256, 0, (cudaStream_t)stream, c, n, m, cpc, points, idx, out);
   P2R_RETURN_LAUNCH("p2r_gather_points");
 }
 
@@ -225,7 +227,8 @@ extern "C" int p2r_gather_points_grad(const float* grad_out, const int* idx, int
   if (b == 0 || c == 0 || m == 0) return 0;
   const int cpc = c >= 64 ? 16 : (c >= 8 ? 4 : 1);
   dim3 grid(p2r_ceil_div(m, 256), p2r_ceil_div(c, cpc), b);
-  gather_points_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, m, cpc, grad_out, idx, grad_points);
+  auto kern = gather_points_kernel<true>;
+  P2R_LAUNCH(kern, grid, 256, 0, (cudaStream_t)stream, c, n, m, cpc, grad_out, idx, grad_points);
   P2R_RETURN_LAUNCH("p2r_gather_points_grad");
 }
 
@@ -239,7 +242,7 @@ extern "C" int p2r_gather_points_grad(const float* grad_out, const int* idx, int
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(int n, int m, float radius, int nsample, const float* __restrict__ new_xyz,
                   const float* __restrict__ xyz, int* __restrict__ idx) {
-  extern __shared__ __align__(16) float s_pts[];
+  P2R_DYN_SMEM(float, s_pts);
   __shared__ __align__(8) uint64_t s_bar;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -301,7 +304,7 @@ extern "C" int p2r_ball_query(const float* new_xyz, const float* xyz, int b, int
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  ball_query_kernel<<<grid, BQ_WARPS * 32, smem, (cudaStream_t)stream>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+  P2R_LAUNCH(ball_query_kernel, grid, BQ_WARPS * 32, smem, (cudaStream_t)stream, n, m, radius, nsample, new_xyz, xyz, idx);
   P2R_RETURN_LAUNCH("p2r_ball_query");
 }
 
@@ -353,7 +356,7 @@ extern "C" int p2r_group_points(const float* points, const int* idx, int b, int 
   if (b == 0 || c == 0 || ps == 0) return 0;
   const int cpc = c >= 64 ? 8 : (c >= 8 ? 4 : 1);
   dim3 grid(p2r_ceil_div(p2r_ceil_div(ps, 4), 256), p2r_ceil_div(c, cpc), b);
-  group_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ps, cpc, points, idx, out);
+  P2R_LAUNCH(group_points_kernel, grid, 256, 0, (cudaStream_t)stream, c, n, ps, cpc, points, idx, out);
   P2R_RETURN_LAUNCH("p2r_group_points");
 }
 
@@ -365,7 +368,7 @@ extern "C" int p2r_group_points_grad(const float* grad_out, const int* idx, int 
   if (b == 0 || c == 0 || ps == 0) return 0;
   const int cpc = c >= 64 ? 8 : (c >= 8 ? 4 : 1);
   dim3 grid(p2r_ceil_div(ps, 256), p2r_ceil_div(c, cpc), b);
-  group_points_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ps, cpc, grad_out, idx, grad_points);
+  P2R_LAUNCH(group_points_grad_kernel, grid, 256, 0, (cudaStream_t)stream, c, n, ps, cpc, grad_out, idx, grad_points);
   P2R_RETURN_LAUNCH("p2r_group_points_grad");
 }
 
@@ -421,7 +424,7 @@ extern "C" int p2r_three_nn(const float* unknown, const float* known, int b, int
   P2R_CHECK_ARG(b >= 0 && n >= 0 && m >= 0, "p2r_three_nn");
   if (b == 0 || n == 0) return 0;
   dim3 grid(p2r_ceil_div(n, 256), b);
-  three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  P2R_LAUNCH(three_nn_kernel, grid, 256, 0, (cudaStream_t)stream, n, m, unknown, known, dist2, idx);
   P2R_RETURN_LAUNCH("p2r_three_nn");
 }
 
@@ -463,7 +466,8 @@ extern "C" int p2r_three_interpolate(const float* points, const int* idx, const 
   if (b == 0 || c == 0 || n == 0) return 0;
   const int cpc = c >= 64 ? 8 : (c >= 8 ? 4 : 1);
   dim3 grid(p2r_ceil_div(n, 256), p2r_ceil_div(c, cpc), b);
-  three_interpolate_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(c, m, n, cpc, points, idx, weight, out);
+  auto kern = three_interpolate_kernel<false>;
+  P2R_LAUNCH(kern, grid, 256, 0, (cudaStream_t)stream, c, m, n, cpc, points, idx, weight, out);
   P2R_RETURN_LAUNCH("p2r_three_interpolate");
 }
 
@@ -474,7 +478,7 @@ extern "C" int p2r_three_interpolate_grad(const float* grad_out, const int* idx,
   if (b == 0 || c == 0 || n == 0) return 0;
   const int cpc = c >= 64 ? 8 : (c >= 8 ? 4 : 1);
   dim3 grid(p2r_ceil_div(n, 256), p2r_ceil_div(c, cpc), b);
-  three_interpolate_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(c, m, n, cpc, grad_out, idx, weight,
-                                                                         grad_points);
+  auto kern = three_interpolate_kernel<true>;
+  P2R_LAUNCH(kern, grid, 256, 0, (cudaStream_t)stream, c, m, n, cpc, grad_out, idx, weight, grad_points);
   P2R_RETURN_LAUNCH("p2r_three_interpolate_grad");
 }

@@ -38,7 +38,10 @@ static dim3 blockDim, gridDim;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
+
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -122,6 +125,36 @@ static inline int __any_sync(unsigned, int pred) {
   w.bar.wait();
   return any;
 }
+
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31, p = pred != 0;
+  memcpy(w.slot[lane], &p, sizeof(int));
+  w.bar.wait();
+  unsigned bal = 0;
+  for (int l = 0; l < 32; ++l) { int q; memcpy(&q, w.slot[l], sizeof(int)); bal |= (unsigned)(q != 0) << l; }
+  w.bar.wait();
+  return bal;
+}
+// block-wide AND of a predicate: and -> barrier -> read -> barrier -> re-arm -> barrier
+static int emu_and_acc = 1;
+static inline int __syncthreads_and(int pred) {
+  if (!pred) __atomic_store_n(&emu_and_acc, 0, __ATOMIC_SEQ_CST);
+  emu_block_bar->wait();
+  const int r = __atomic_load_n(&emu_and_acc, __ATOMIC_SEQ_CST);
+  emu_block_bar->wait();
+  __atomic_store_n(&emu_and_acc, 1, __ATOMIC_SEQ_CST);
+  emu_block_bar->wait();
+  return r;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __brev(unsigned v) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+  return r;
+}
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline float atomicAdd(float* p, float v) {
