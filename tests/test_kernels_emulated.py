@@ -87,7 +87,7 @@ def emulated_loss(lib, est, gt, sem_obj, g_total=1.0):
 
 
 @pytest.mark.parametrize("shape", [dict(B=3, T=48, S=20, P=16), dict(B=2, T=300, S=200, P=150),
-                                   dict(B=32, T=1024, S=512, P=128)])
+                                   dict(B=8, T=1024, S=512, P=128)])       # the BASELINE shape per sample; 8 of its 32 samples keep the suite short
 def test_detection_loss_kernels_under_emulation_equal_the_sequential_harness(emu, host_loss_lib, shape):
     hd = torch.float32 if shape["P"] == 150 else torch.float64
     est, gt, sem_obj = TL.make_case(11, J=25, heading_dtype=hd, **shape)
@@ -114,7 +114,7 @@ def test_bad_arguments_are_reported_by_the_launchers(emu):
 @pytest.mark.parametrize("G,D,mu_dtype,bf16", [(100, 3, np.float32, False), (100, 2, np.float64, False),
                                                (33, 3, np.float32, True), (256, 4, np.float64, False)])
 def test_mixture_kernels_under_emulation_equal_the_sequential_harness(emu, host_gmm_lib, G, D, mu_dtype, bf16):
-    rows = 4101 if G == 100 else 77                                      # tail block / tail warps
+    rows = 1029 if G == 100 else 77                                      # tail block / tail warps
     rng = np.random.default_rng(G + D)
     logits = (2.0 * rng.normal(size=(rows, G)) - 1.0).astype(np.float32)
     if bf16:                                                             # logits stored as bf16: same values on both sides
