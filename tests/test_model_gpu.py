@@ -287,16 +287,6 @@ def _run_isolated(flags, extra=""):
     assert r.returncode == 0 and "ISOLATED-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
 
 
-@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "detection-loss (csrc/loss_ops.cu, P2R_FUSED_LOSS=1)")
-def test_fused_detection_loss_passes_the_parity_tests(cuda):
-    _run_isolated(["P2R_FUSED_LOSS"], "T._fused_vs_chain_on_random_predictions(dev); ")
-
-
-@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "mixture-head (csrc/gmm_ops.cu, P2R_FUSED_GMM=1)")
-def test_fused_mixture_heads_pass_the_parity_tests(cuda):
-    _run_isolated(["P2R_FUSED_GMM"], "T._fused_gmm_vs_torch_path(dev); ")
-
-
 def _fused_vote_vs_torch_path(dev):
     """CenterVoteModule with the fused tail vs its torch path + the normalisation of P2RNet._trunk (fp32 and bf16)."""
     import os
@@ -333,6 +323,11 @@ def _fused_vote_vs_torch_path(dev):
                 gemm_sm100.uninstall()
 
 
-@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "vote-tail (csrc/vote_ops.cu, P2R_FUSED_VOTE=1)")
-def test_fused_vote_tail_passes_the_parity_tests(cuda):
-    _run_isolated(["P2R_FUSED_VOTE"], "T._fused_vote_vs_torch_path(dev); ")
+@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "detection-loss / mixture-head / vote-tail (csrc/loss_ops.cu, gmm_ops.cu, "
+                                        "vote_ops.cu; P2R_FUSED_LOSS / P2R_FUSED_GMM / P2R_FUSED_VOTE)")
+def test_fused_paths_pass_the_parity_tests(cuda):
+    """One process: each fused kernel against the path it replaces (the first assertion that fails names the kernel), then
+    the reference-golden parity tests and the bf16 check with all three flags on."""
+    _run_isolated(["P2R_FUSED_LOSS", "P2R_FUSED_GMM", "P2R_FUSED_VOTE"],
+                  "T._fused_vs_chain_on_random_predictions(dev); os.environ['P2R_FUSED_LOSS'] = '0'; "
+                  "T._fused_gmm_vs_torch_path(dev); T._fused_vote_vs_torch_path(dev); ")
