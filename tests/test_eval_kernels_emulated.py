@@ -129,3 +129,35 @@ def test_seed_sampling_kernel_under_emulation_on_the_recorded_demo_sequence(emu)
     seeds = np.full((1, 512), -1, np.int64)
     assert emu.p2r_uniform_seed_inds(_p(joints), 53 * 3, 1, 768, 512, _p(seeds), None) == 0   # hip = joint 0, read in place
     assert np.array_equal(seeds, g["gen_seed_inds"])
+
+
+def test_nms_and_iou_kernels_under_emulation_vs_reference_goldens(emu, golden_geometry):
+    """Rehearsal of test_geometry_gpu.py's NMS / IoU checks: the reference's own picks (plain, old-type, same-class, 2-D)
+    on its fixture boxes, random sets against the oracle, pairwise oriented-box IoU against the reference's Qhull values."""
+    g = golden_geometry
+    _, nms, iou = _emulated_geometry(emu)
+
+    def picks(boxes, thr, old_type=False, with_cls=False):
+        boxes = np.asarray(boxes, np.float64)
+        t = torch.from_numpy(boxes)
+        cls = t[None, :, 7].to(torch.int32) if with_cls else None
+        keep, order = nms(t[None, :, 0:6].contiguous(), t[None, :, 6].contiguous(), None, cls, thr, old_type)
+        return [int(i) for i in order[0].numpy() if i >= 0]
+
+    for t in range(4):
+        boxes = g["nms%d_boxes" % t]
+        assert picks(boxes[:, :7], 0.10) == g["nms%d_pick" % t].tolist()
+        assert picks(boxes[:, :7], 0.25, old_type=True) == g["nms%d_pick_old" % t].tolist()
+        assert picks(boxes, 0.10, with_cls=True) == g["nms%d_pick_cls" % t].tolist()
+        k = boxes.shape[0]
+        b3 = np.zeros((k, 7))
+        b3[:, 0:2], b3[:, 3:5], b3[:, 5], b3[:, 6] = boxes[:, 0:2], boxes[:, 3:5], 1.0, boxes[:, 6]   # geometry.nms_2d_faster
+        assert picks(b3, 0.10) == g["nms%d_pick_2d" % t].tolist()
+    rng = np.random.default_rng(5)
+    for k in (1, 2, 31, 128, 200):
+        lo = rng.normal(0, 1.0, size=(k, 3))
+        boxes = np.concatenate([lo, lo + rng.uniform(0.05, 1.5, size=(k, 3)), rng.uniform(size=(k, 1))], 1)
+        assert picks(boxes, 0.1) == G.nms_3d_faster(boxes, 0.1)
+    i3, i2 = iou(g["box_corners"], g["box_corners"])
+    ok = ~np.isnan(g["box_iou3d"]) & ~np.eye(24, dtype=bool)
+    assert np.allclose(i3.numpy()[ok], g["box_iou3d"][ok], atol=1e-9) and np.allclose(i2.numpy()[ok], g["box_iou2d"][ok], atol=1e-9)
