@@ -37,11 +37,18 @@ static inline int p2r_ceil_div(long long a, long long b) { return (int)((a + b -
 #define P2R_LAUNCH(kernel, grid, block, smem, stream, ...) \
   emu_launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
 #define P2R_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_dyn_smem)
+#define P2R_DYN_SMEM_ALIGNED(type, name, align) type* name = reinterpret_cast<type*>(emu_dyn_smem)
+#define P2R_NAMED_BARRIER_SYNC_1_256() emu_named_barrier_256()
 #else
 #define P2R_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define P2R_DYN_SMEM(type, name)                                \
   extern __shared__ __align__(16) unsigned char name##_raw[];   \
   type* name = reinterpret_cast<type*>(name##_raw)
+#define P2R_DYN_SMEM_ALIGNED(type, name, align)                    \
+  extern __shared__ __align__(align) unsigned char name##_raw[];   \
+  type* name = reinterpret_cast<type*>(name##_raw)
+// named barrier 1 over the 256 consumer threads of the streaming kernels (the producer warp does not take part)
+#define P2R_NAMED_BARRIER_SYNC_1_256() asm volatile("bar.sync 1, 256;" ::: "memory")
 #endif
 
 // ---- exact-order fp32 arithmetic -----------------------------------------------------------
@@ -131,11 +138,21 @@ __device__ __forceinline__ void p2r_stage_floats(float* dst, const float* __rest
   __syncthreads();
 }
 
-#else   // host emulation: the bulk-TMA staging helper degrades to a plain cooperative copy, the mbarrier to nothing
-__device__ __forceinline__ void p2r_mbar_init(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void p2r_fence_mbar_init() {}
-__device__ __forceinline__ void p2r_stage_floats(float* dst, const float* __restrict__ src, int nfloats, uint64_t*, uint32_t) {
-  for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src[i];
+#else   // host emulation: mbarrier / bulk-copy twins come from tests/csrc/cuda_emu.h; the staging helper is the same code
+__device__ __forceinline__ void p2r_stage_floats(float* dst, const float* __restrict__ src, int nfloats,
+                                                 uint64_t* bar, uint32_t parity) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const int bulk = aligned ? (nfloats & ~3) : 0;
+  if (threadIdx.x == 0) {
+    if (bulk > 0) {
+      p2r_mbar_expect_tx(bar, (uint32_t)bulk * 4u);
+      p2r_bulk_g2s(dst, src, (uint32_t)bulk * 4u, bar);
+    } else {
+      p2r_mbar_arrive(bar);
+    }
+  }
+  for (int i = bulk + threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = __ldg(src + i);
+  p2r_mbar_wait(bar, parity);
   __syncthreads();
 }
 #endif  // !P2R_HOST_EMULATION

@@ -72,7 +72,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 template <int MODE, int NIN, int STAGES>
 __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamArgs a) {
-  extern __shared__ __align__(128) uint8_t sb_smem[];
+  P2R_DYN_SMEM_ALIGNED(uint8_t, sb_smem, 128);
   constexpr int STAGE_BYTES = NIN * SB_TILE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sb_smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
 
   if (MODE == BWD_APPLY) {
     if (do_cs) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // every consumer has added its last row
+      P2R_NAMED_BARRIER_SYNC_1_256();   // every consumer has added its last row
       for (int i = tid; i < a.period * SB_C; i += SB_CONSUMERS) {
         const float v = cs_tab[(i / SB_C) * CS_LD + (i % SB_C)];
         if (v != 0.f) atomicAdd(a.colsum + i, (double)v);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
       acc2[i] += __shfl_xor_sync(0xffffffffu, acc2[i], 8);
       acc2[i] += __shfl_xor_sync(0xffffffffu, acc2[i], 16);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // every consumer is past its last tile: the ring is free
+    P2R_NAMED_BARRIER_SYNC_1_256();   // every consumer is past its last tile: the ring is free
     float* red = reinterpret_cast<float*>(sb_smem);  // [2][8 warps][64 channels]
     if (lane < 8) {
 #pragma unroll
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
         red[(1 * 8 + warp) * 64 + c0 + i] = acc2[i];
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    P2R_NAMED_BARRIER_SYNC_1_256();
     if (tid < 128) {
       const int which = tid >> 6, c = tid & 63;
       double t = 0.0;
@@ -287,7 +287,7 @@ int launch_stream(const StreamArgs& a, cudaStream_t st, const char* where) {
   const int grid = (int)min(ntiles, (long long)P2R_SM_COUNT * stream_ctas_per_sm());
   auto kern = stream_bn_kernel<MODE, NIN, STAGES>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-  kern<<<grid, SB_THREADS, SMEM, st>>>(a);
+  P2R_LAUNCH(kern, grid, SB_THREADS, SMEM, st, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) p2r_set_last_error(where, (int)e);
   return (int)e;

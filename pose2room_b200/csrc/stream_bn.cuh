@@ -1,7 +1,7 @@
 // stream_bn.cuh -- internal interface of the bulk-TMA streaming BatchNorm kernels (stream_bn.cu); the C-ABI entry
 // points in dense_ops.cu route [M, 64] bf16 operands here and everything else to their generic kernels.
 #pragma once
-#include <cuda_runtime.h>
+#include "p2r_common.cuh"   // cuda_runtime.h, or the host emulator's twin of it in the CPU tests
 
 bool p2r_stream_bn_ok(int dtype, long long M, int C, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr,
                       const void* p3 = nullptr, const void* p4 = nullptr);

@@ -20,6 +20,9 @@
 #include <string.h>
 #include <algorithm>
 #include <functional>
+#include <map>
+#include <stdio.h>
+#include <time.h>
 #include <random>
 #include <vector>
 
@@ -201,6 +204,60 @@ static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
   __nv_bfloat16 h; h.x = (unsigned short)(u >> 16); return h;
 }
 
+
+// ---- mbarrier + 1-D bulk copy (cp.async.bulk) twins of the helpers in p2r_common.cuh, a few vector types -------------
+// An mbarrier is a side-table entry keyed by the address of the kernel's uint64_t: pending arrivals, outstanding
+// transaction bytes, phase parity.  A bulk copy happens at issue time and then completes its bytes on the barrier.  A
+// wait that makes no progress for 10 s aborts with a diagnostic (a deadlock in a ring protocol would otherwise hang).
+struct uint4 { unsigned x, y, z, w; } __attribute__((aligned(16)));
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { __nv_bfloat162 r; r.x = __float2bfloat16_rn(a); r.y = __float2bfloat16_rn(b); return r; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline double atomicAdd(double* p, double v) {
+  unsigned long long old, neu; double f;
+  do { old = __atomic_load_n((unsigned long long*)p, __ATOMIC_SEQ_CST); memcpy(&f, &old, 8); f += v; memcpy(&neu, &f, 8);
+  } while (!__atomic_compare_exchange_n((unsigned long long*)p, &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  memcpy(&f, &old, 8); return f;
+}
+struct EmuMbar { int init, pending; long long tx; unsigned phase; };
+static pthread_mutex_t emu_mbar_m = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t emu_mbar_cv = PTHREAD_COND_INITIALIZER;
+static std::map<const void*, EmuMbar> emu_mbars;
+static inline void emu_mbar_check(EmuMbar& b) {
+  if (b.pending <= 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.init; pthread_cond_broadcast(&emu_mbar_cv); }
+}
+static inline void p2r_mbar_init(uint64_t* bar, uint32_t count) {
+  pthread_mutex_lock(&emu_mbar_m); emu_mbars[bar] = EmuMbar{(int)count, (int)count, 0, 0u}; pthread_mutex_unlock(&emu_mbar_m);
+}
+static inline void p2r_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  pthread_mutex_lock(&emu_mbar_m); EmuMbar& b = emu_mbars[bar]; b.tx += bytes; b.pending -= 1; emu_mbar_check(b); pthread_mutex_unlock(&emu_mbar_m);
+}
+static inline void p2r_mbar_arrive(uint64_t* bar) {
+  pthread_mutex_lock(&emu_mbar_m); EmuMbar& b = emu_mbars[bar]; b.pending -= 1; emu_mbar_check(b); pthread_mutex_unlock(&emu_mbar_m);
+}
+static inline void p2r_mbar_wait(uint64_t* bar, uint32_t parity) {
+  pthread_mutex_lock(&emu_mbar_m);
+  EmuMbar& b = emu_mbars[bar];
+  struct timespec ts; int spins = 0;
+  while (b.phase == parity) {
+    clock_gettime(CLOCK_REALTIME, &ts); ts.tv_sec += 5;
+    if (pthread_cond_timedwait(&emu_mbar_cv, &emu_mbar_m, &ts) != 0 && ++spins >= 2) {
+      fprintf(stderr, "EMU: mbarrier wait stuck: block %u thread %u bar %p parity %u (pending %d tx %lld phase %u)\n",
+              blockIdx.x, threadIdx.x, (void*)bar, parity, b.pending, b.tx, b.phase);
+      abort();
+    }
+  }
+  pthread_mutex_unlock(&emu_mbar_m);
+}
+static inline void p2r_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  memcpy(dst, src, bytes);
+  pthread_mutex_lock(&emu_mbar_m); EmuMbar& b = emu_mbars[bar]; b.tx -= bytes; emu_mbar_check(b); pthread_mutex_unlock(&emu_mbar_m);
+}
+static EmuBarrier emu_named_256;
+static inline void emu_named_barrier_256() { emu_named_256.wait(); }
+static inline void p2r_fence_mbar_init() {}
+static inline void p2r_fence_proxy_async() {}
+
 // ---- launch ---------------------------------------------------------------------------------------------------------
 struct EmuLaunch {
   const std::function<void()>* fn;
@@ -249,6 +306,7 @@ static inline void emu_launch(dim3 grid, dim3 block, size_t smem, const std::fun
   L.warps = std::vector<EmuWarp>(block.x / 32);
   pthread_barrier_init(&L.gate, nullptr, block.x);
   emu_block_bar = &L.block_bar;
+  emu_named_256.reset(256);
   emu_warps = &L.warps;
   std::vector<pthread_t> th(block.x);
   std::vector<EmuThreadArg> args(block.x);

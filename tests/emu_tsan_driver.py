@@ -43,7 +43,7 @@ assert lib.p2r_vote_tail_grad(p(xyz), p(feat), p(feat), p(norm), rows, C, p(dn),
 fn = lib.p2r_make_batch_variant
 fn.argtypes = _lib.SIGNATURES["p2r_make_batch_variant"]
 fn.restype = ctypes.c_int
-Jn, Bn, Tn = 7, 2, 81       # 22 work items; the sanitizer build has P2R_SM_COUNT=4 -> 5-6 items per persistent CTA
+Jn, Bn, Tn = 7, 2, 81       # 22 work items; the sanitizer build has P2R_SM_COUNT=1 -> one persistent CTA walks all of them
 fs = np.array([0, 50, 61], np.int64)
 jt, vt = rng.normal(size=(61, Jn, 3)).astype(np.float32), rng.normal(size=(61, Jn, 10)).astype(np.float32)
 ids, par = np.array([1, 0], np.int32), np.zeros((Bn, 16))

@@ -212,13 +212,19 @@ def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):
     def build_and_run(csrc_dir, tag):
         so = str(tmp_path / ("emu_tsan_%s.so" % tag))
         subprocess.run(["g++", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-shared", "-fPIC",
-                        "-std=c++17", "-w", "-DP2R_HOST_EMULATION", "-DP2R_SM_COUNT=4", "-I", csrc_dir] +
+                        "-std=c++17", "-w", "-DP2R_HOST_EMULATION", "-DP2R_SM_COUNT=1", "-I", csrc_dir] +
                        sum((["-I", i] for i in inc), []) + [osp.join(csrc_dir, "kernels_emu_entry.cpp"), "-o", so], check=True)
         env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0")
         r = subprocess.run([sys.executable, osp.join(ROOT, "tests", "emu_tsan_driver.py"), so], env=env, capture_output=True,
                            text=True, timeout=600, cwd=ROOT)
         assert "TSAN-DRIVER-DONE" in r.stdout, r.stderr[-2000:]
-        return r.stderr.count("WARNING: ThreadSanitizer: data race")
+        races = r.stderr.count("WARNING: ThreadSanitizer: data race")
+        if tag == "clean":      # + the streaming BatchNorm kernels (mbarrier rings wrapping, column-sum variant included)
+            r = subprocess.run([sys.executable, osp.join(ROOT, "tests", "test_stream_bn_emulated.py"), so], env=env,
+                               capture_output=True, text=True, timeout=600, cwd=ROOT)
+            assert "SBN-DRIVER-DONE" in r.stdout, r.stderr[-2000:]
+            races += r.stderr.count("WARNING: ThreadSanitizer: data race")
+        return races
 
     def stage(tag, mutate):
         d = tmp_path / tag
