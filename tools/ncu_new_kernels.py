@@ -1,7 +1,7 @@
 """Launches the kernels that have no ncu capture yet at their BASELINE shapes, twice each (for one `ncu --set full` pass):
-make_batch (both data-movement variants), detection_loss (+grad), gmm_mix (+grad).  Diagnostic only.
+make_batch (both data-movement variants), detection_loss (+grad), gmm_mix (+grad), vote_tail (+grad).  Diagnostic only.
 
-    ncu --set full --clock-control none --import-source on -k regex:"make_batch|detection_loss|gmm_mix" \
+    ncu --set full --clock-control none --import-source on -k regex:"make_batch|detection_loss|gmm_mix|vote_tail" \
         -o gpurun_out/new_kernels python tools/ncu_new_kernels.py
 """
 import os
@@ -56,5 +56,16 @@ for d, dt in ((3, torch.float32), (2, torch.float64)):
         logits = torch.randn(B * 128, 100, device=dev).bfloat16().requires_grad_(True)
         eps = head.mu.data.new(B * 128, 100, 1, d).normal_()
         _FusedGMMPredict.apply(logits, head.mu, head.log_sigma, eps).sum().backward()
+torch.cuda.synchronize()
+
+# ---- vote tail: 16 384 seed rows, 256 channels ---------------------------------------------------------------------
+from pose2room_b200.p2rnet.vote_center import _VoteTail
+for dt in (torch.bfloat16, torch.float32):
+    for _ in range(2):
+        net = torch.randn(B * 512, 259, device=dev).to(dt).requires_grad_(True)
+        skel = torch.randn(B, 512, J, 3, device=dev)
+        sf = torch.randn(B, 512, 256, device=dev, requires_grad=True)
+        xyz, feat = _VoteTail.apply(net, skel[:, :, 0], sf)
+        (xyz.sum() + feat.sum()).backward()
 torch.cuda.synchronize()
 print("done")

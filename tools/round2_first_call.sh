@@ -9,7 +9,7 @@ python -m pytest tests/test_model_gpu.py tests/test_dataloader_gpu.py tests/test
     > gpurun_out/r02_fused_tests.log 2>&1
 python -m pytest tests/test_zz_eval_1k_gpu.py -m gpu -q -s --runxfail > gpurun_out/r02_eval1k.log 2>&1
 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"make_batch|detection_loss|gmm_mix" \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"make_batch|detection_loss|gmm_mix|vote_tail" \
     -o gpurun_out/r02_new_kernels python tools/ncu_new_kernels.py > gpurun_out/r02_ncu_new.log 2>&1
 tail -5 gpurun_out/r02_fused_tests.log gpurun_out/r02_eval1k.log
 python - <<'PY'
