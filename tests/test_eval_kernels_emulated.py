@@ -161,3 +161,30 @@ def test_nms_and_iou_kernels_under_emulation_vs_reference_goldens(emu, golden_ge
     i3, i2 = iou(g["box_corners"], g["box_corners"])
     ok = ~np.isnan(g["box_iou3d"]) & ~np.eye(24, dtype=bool)
     assert np.allclose(i3.numpy()[ok], g["box_iou3d"][ok], atol=1e-9) and np.allclose(i2.numpy()[ok], g["box_iou2d"][ok], atol=1e-9)
+
+
+def test_knn_and_graph_offset_kernels_under_emulation_vs_reference_goldens(emu, golden_pointnet2):
+    """Rehearsal of test_geometry_gpu.py::test_knn_vs_oracle_and_reference_golden (SURVEY row a8)."""
+    from oracle.pointnet2_ref import knn_ref
+    for name in ("p2r_knn_graph", "p2r_graph_offset"):
+        fn = getattr(emu, name)
+        fn.argtypes = _lib.SIGNATURES[name]
+        fn.restype = ctypes.c_int
+    g = golden_pointnet2
+    x = np.ascontiguousarray(g["knn_x"], np.float32)
+    b, c, n = x.shape
+    idx = np.full((b, n, 8), -1, np.int64)
+    assert emu.p2r_knn_graph(_p(x), b, c, n, 8, _p(idx), None) == 0
+    assert np.array_equal(np.sort(idx, -1), np.sort(g["knn_idx"], -1))                         # the reference's torch.topk sets
+    assert np.array_equal(np.sort(idx, -1), np.sort(knn_ref(torch.from_numpy(x), 8).numpy(), -1))
+    ref_idx = np.ascontiguousarray(g["knn_idx"], np.int64)
+    off = np.full(g["knn_offset"].shape, np.nan, np.float32)
+    assert emu.p2r_graph_offset(_p(x), _p(ref_idx), b, c, n, 8, _p(off), None) == 0
+    assert np.array_equal(off, g["knn_offset"])
+    # live configuration of the backbone: (B,3,T) hip trajectory, k = 20
+    rng = np.random.default_rng(0)
+    xt = np.cumsum(rng.normal(0, 0.05, size=(1, 3, 1024)), axis=2).astype(np.float32)
+    got = np.full((1, 1024, 20), -1, np.int64)
+    assert emu.p2r_knn_graph(_p(xt), 1, 3, 1024, 20, _p(got), None) == 0
+    want = knn_ref(torch.from_numpy(xt), 20).numpy()
+    assert (np.sort(got, -1) == np.sort(want, -1)).mean() > 0.999 and (got[..., 0] == np.arange(1024)[None]).all()
