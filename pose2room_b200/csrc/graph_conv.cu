@@ -79,8 +79,8 @@ gcn_build_weight_kernel(const float* __restrict__ conv_w, const float* __restric
 extern "C" int p2r_gcn_build_weight(const float* conv_w, const float* conv_b, const float* A, int K, int V, int Co, int Ci,
                                     void* w_eff, void* w_eff_t, float* b_eff, void* stream) {
   P2R_CHECK_ARG(K > 0 && V > 0 && Co == GC_C && Ci == GC_C, "p2r_gcn_build_weight (built for 64 -> 64 channel blocks)");
-  gcn_build_weight_kernel<<<dim3(V, V), 256, 0, (cudaStream_t)stream>>>(conv_w, conv_b, A, K, V, (__nv_bfloat16*)w_eff,
-                                                                         (__nv_bfloat16*)w_eff_t, b_eff);
+  P2R_LAUNCH(gcn_build_weight_kernel, dim3(V, V), 256, 0, (cudaStream_t)stream, conv_w, conv_b, A, K, V,
+             (__nv_bfloat16*)w_eff, (__nv_bfloat16*)w_eff_t, b_eff);
   P2R_RETURN_LAUNCH("p2r_gcn_build_weight");
 }
 
@@ -140,7 +140,7 @@ gcn_dA_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff
 __global__ void __launch_bounds__(256)
 gcn_dw_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff, const float* __restrict__ A, int K,
               int V, float* __restrict__ d_conv_w, float* __restrict__ d_conv_b) {
-  extern __shared__ float sA[];                              // A[k] : V x V
+  P2R_DYN_SMEM(float, sA);                                   // A[k] : V x V
   const int k = blockIdx.x, slice = blockIdx.y, t = threadIdx.x;
   for (int i = t; i < V * V; i += 256) sA[i] = __ldg(A + (size_t)k * V * V + i);
   __syncthreads();
@@ -174,8 +174,8 @@ extern "C" int p2r_gcn_reduce_weight_grad(const float* dw_eff, const float* db_e
                                           float* d_conv_w, float* d_conv_b, float* dA, void* stream) {
   P2R_CHECK_ARG(K > 0 && V > 0 && Co == GC_C && Ci == GC_C, "p2r_gcn_reduce_weight_grad (64 -> 64 channel blocks)");
   P2R_CHECK_ARG((size_t)V * V * sizeof(float) <= 48 * 1024, "p2r_gcn_reduce_weight_grad (adjacency too large for shared memory)");
-  gcn_dA_kernel<<<dim3(V, V), 256, 0, (cudaStream_t)stream>>>(dw_eff, db_eff, conv_w, conv_b, A, K, V, dA);
-  gcn_dw_kernel<<<dim3(K, GC_C / 8), 256, (size_t)V * V * sizeof(float), (cudaStream_t)stream>>>(dw_eff, db_eff, A, K, V,
-                                                                                               d_conv_w, d_conv_b);
+  P2R_LAUNCH(gcn_dA_kernel, dim3(V, V), 256, 0, (cudaStream_t)stream, dw_eff, db_eff, conv_w, conv_b, A, K, V, dA);
+  P2R_LAUNCH(gcn_dw_kernel, dim3(K, GC_C / 8), 256, (size_t)V * V * sizeof(float), (cudaStream_t)stream, dw_eff, db_eff, A,
+             K, V, d_conv_w, d_conv_b);
   P2R_RETURN_LAUNCH("p2r_gcn_reduce_weight_grad");
 }

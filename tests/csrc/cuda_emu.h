@@ -45,6 +45,8 @@ static dim3 blockDim, gridDim;
 
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+struct __attribute__((aligned(8))) float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 v; v.x = x; v.y = y; return v; }
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -210,6 +212,7 @@ static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
 // transaction bytes, phase parity.  A bulk copy happens at issue time and then completes its bytes on the barrier.  A
 // wait that makes no progress for 10 s aborts with a diagnostic (a deadlock in a ring protocol would otherwise hang).
 struct uint4 { unsigned x, y, z, w; } __attribute__((aligned(16)));
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 struct __nv_bfloat162 { __nv_bfloat16 x, y; };
 static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { __nv_bfloat162 r; r.x = __float2bfloat16_rn(a); r.y = __float2bfloat16_rn(b); return r; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

@@ -1,4 +1,4 @@
-// TEST HARNESS (CPU): the SIMT-only kernels of the product (loss_ops.cu, gmm_ops.cu, vote_ops.cu, geometry_ops.cu, dataloader_ops.cu, pointnet2_ops.cu, stream_bn.cu) -- kernels AND their C-ABI launchers,
+// TEST HARNESS (CPU): the SIMT-only kernels of the product (loss_ops.cu, gmm_ops.cu, vote_ops.cu, geometry_ops.cu, dataloader_ops.cu, pointnet2_ops.cu, stream_bn.cu, graph_conv.cu) -- kernels AND their C-ABI launchers,
 // unmodified -- compiled for the host on top of the execution-model emulator in cuda_emu.h.  The resulting library
 // exports the same p2r_* symbols as libp2r_b200.so for these entry points; tests/test_kernels_emulated.py calls them with
 // host arrays.  Built by the test (g++ -DP2R_HOST_EMULATION -ffp-contract=off -pthread); never shipped.
@@ -19,6 +19,7 @@ extern "C" const char* emu_last_error() { return g_last_error.c_str(); }
 #include "../../pose2room_b200/csrc/dataloader_ops.cu"
 #include "../../pose2room_b200/csrc/pointnet2_ops.cu"
 #include "../../pose2room_b200/csrc/stream_bn.cu"
+#include "../../pose2room_b200/csrc/graph_conv.cu"
 
 // the streaming BatchNorm kernels have an internal C++ interface (stream_bn.cuh): plain-C doors for the test
 extern "C" int emu_stream_col_stats(const void* x, long long M, double* s1, double* s2) {

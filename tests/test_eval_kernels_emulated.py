@@ -188,3 +188,42 @@ def test_knn_and_graph_offset_kernels_under_emulation_vs_reference_goldens(emu, 
     assert emu.p2r_knn_graph(_p(xt), 1, 3, 1024, 20, _p(got), None) == 0
     want = knn_ref(torch.from_numpy(xt), 20).numpy()
     assert (np.sort(got, -1) == np.sort(want, -1)).mean() > 0.999 and (got[..., 0] == np.arange(1024)[None]).all()
+
+
+@pytest.mark.parametrize("V", [6, 25])        # (53, the reference rig, passes too: 70 s under the emulator)
+def test_graph_conv_weight_kernels_under_emulation_match_the_einsum_formulation(emu, V):
+    """csrc/graph_conv.cu: W_eff = sum_k W_k (x) A_k, b_eff and the fold of their gradients back onto the conv weight,
+    conv bias and A (ref: ConvTemporalGraphical.forward, stgcn_layers.py:58-67 -- conv 64 -> K*64 then
+    einsum('nkctv,kvw->nctw')), against numpy einsums in float64."""
+    for name in ("p2r_gcn_build_weight", "p2r_gcn_reduce_weight_grad"):
+        fn = getattr(emu, name)
+        fn.argtypes = _lib.SIGNATURES[name]
+        fn.restype = ctypes.c_int
+    rng = np.random.default_rng(V)
+    K, Cc = 11, 64
+    W = (rng.normal(size=(K * Cc, Cc)) / 8).astype(np.float32)
+    bias = rng.normal(size=K * Cc).astype(np.float32)
+    A = (rng.random((K, V, V)) * (rng.random((K, V, V)) < 0.15)).astype(np.float32)          # sparse, like adjacency * importance
+    w_eff, w_eff_t = np.zeros((V * Cc, V * Cc), np.uint16), np.zeros((V * Cc, V * Cc), np.uint16)
+    b_eff = np.full(V * Cc, np.nan, np.float32)
+    assert emu.p2r_gcn_build_weight(_p(W), _p(bias), _p(A), K, V, Cc, Cc, _p(w_eff), _p(w_eff_t), _p(b_eff), None) == 0
+    Wk = W.reshape(K, Cc, Cc).astype(np.float64)
+    want = np.einsum("kvw,koi->wovi", A.astype(np.float64), Wk).reshape(V * Cc, V * Cc)
+    got = (w_eff.astype(np.uint32) << 16).view(np.float32)
+    assert np.abs(got - want).max() <= 4e-3 * np.abs(want).max()                            # stored as bf16
+    assert np.array_equal(w_eff_t, w_eff.T)
+    want_b = np.einsum("ko,kw->wo", bias.reshape(K, Cc).astype(np.float64), A.astype(np.float64).sum(1)).reshape(-1)
+    assert np.abs(b_eff - want_b).max() <= 1e-5 * np.abs(want_b).max()
+    # backward fold
+    dWe = rng.normal(size=(V * Cc, V * Cc)).astype(np.float32)
+    dbe = rng.normal(size=V * Cc).astype(np.float32)
+    dW, db, dA = np.full((K * Cc, Cc), np.nan, np.float32), np.full(K * Cc, np.nan, np.float32), np.full((K, V, V), np.nan, np.float32)
+    assert emu.p2r_gcn_reduce_weight_grad(_p(dWe), _p(dbe), _p(W), _p(bias), _p(A), K, V, Cc, Cc, _p(dW), _p(db), _p(dA), None) == 0
+    d4 = dWe.reshape(V, Cc, V, Cc).astype(np.float64)                                        # [w, co, v, ci]
+    want_dW = np.einsum("kvw,wovi->koi", A.astype(np.float64), d4).reshape(K * Cc, Cc)
+    want_db = np.einsum("kw,wo->ko", A.astype(np.float64).sum(1), dbe.reshape(V, Cc).astype(np.float64)).reshape(-1)
+    want_dA = np.einsum("koi,wovi->kvw", Wk, d4) + np.einsum("ko,wo->kw", bias.reshape(K, Cc).astype(np.float64),
+                                                           dbe.reshape(V, Cc).astype(np.float64))[:, None, :]
+    want_dA = np.where(A != 0, want_dA, 0.0)                                                 # dA is 0 where A == 0
+    for name, a, b in (("dW", dW, want_dW), ("db", db, want_db), ("dA", dA, want_dA)):
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max(), (name, np.abs(a - b).max(), np.abs(b).max())
