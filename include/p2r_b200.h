@@ -241,8 +241,8 @@ int p2r_make_batch(const float* joints, const float* votes, const long long* fra
                    const double* params, int b, int num_frames, int j, int out_channels, float* input_joints,
                    float* vote_label, long long* vote_label_mask, void* stream);
 /* Diagnostic twin of p2r_make_batch with the data-movement variant chosen by the caller: 1 = one CTA per 8 output frames
- * (the default), 2 = persistent CTAs with a 3-stage cp.async ring (opt-in: P2R_MAKE_BATCH_VARIANT=2 makes p2r_make_batch
- * use it).  Same arithmetic, bit-identical outputs; bench.py times one against the other.                              */
+ * (P2R_MAKE_BATCH_VARIANT=1 makes p2r_make_batch use it), 2 = persistent CTAs with a 3-stage cp.async ring (the default
+ * since round 2: 2.2x faster on a B200).  Same arithmetic, bit-identical outputs; bench.py times one against the other.                              */
 int p2r_make_batch_variant(int variant, const float* joints, const float* votes, const long long* frame_start,
                            const int* sample_ids, const double* params, int b, int num_frames, int j, int out_channels,
                            float* input_joints, float* vote_label, long long* vote_label_mask, void* stream);

@@ -22,12 +22,33 @@ from . import geometry_ref
 from .pointnet2_ref import RefExt
 
 
+class _RefGrouping(torch.autograd.Function):
+    """pointnet2_utils.py:194-240 (GroupingOperation) over an `_ext`-shaped module holding the reference's kernels."""
+
+    @staticmethod
+    def forward(ctx, ext, features, idx):
+        ctx.ext, ctx.n = ext, features.size(2)
+        ctx.save_for_backward(idx)
+        return ext.group_points(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        return None, ctx.ext.group_points_grad(grad_out.contiguous(), idx, ctx.n), None
+
+
 class RefP2RNet:
     def __init__(self, state_dict, joint_num, num_seeds=512, num_target=128, training=True, origin_joint_id=0,
-                 num_class=22, bn_momentum=0.1):
+                 num_class=22, bn_momentum=0.1, device="cpu", ext=None):
+        """device / ext: the default is the CPU port (oracle/pointnet2_ref.c behind RefExt).  bench.py's `gpu_reference`
+        leg passes device="cuda" and the UNMODIFIED reference extension compiled for sm_100a (oracle/_ref/p2r_ref_ext.so,
+        oracle/build_ref_ext.py): the reference's own kernels + the same fp32 cuDNN / cuBLAS calls the reference makes --
+        "the reference on B200" (second baseline)."""
+        self.dev = torch.device(device)
+        self.ext = ext if ext is not None else RefExt
         self.p = {}
         for k, v in state_dict.items():
-            t = v.detach().clone().cpu()
+            t = v.detach().clone().to(self.dev)
             if t.is_floating_point() and "running_" not in k and k != "backbone.A":
                 t.requires_grad_(True)
             self.p[k] = t
@@ -67,16 +88,16 @@ class RefP2RNet:
         B, T, J, D = joints.shape
         hip = joints[:, :, self.o]
         if self.S >= T:
-            seed_inds = torch.round(torch.linspace(0, T - 1, self.S)).long().repeat(B, 1)
+            seed_inds = torch.round(torch.linspace(0, T - 1, self.S)).long().repeat(B, 1).to(self.dev)
         else:
             move = torch.norm(torch.diff(hip, dim=1), dim=2)
-            cum = torch.cumsum(torch.cat([torch.zeros(B, 1), move], dim=1), dim=1)
+            cum = torch.cumsum(torch.cat([torch.zeros(B, 1, device=self.dev), move], dim=1), dim=1)
             step = cum[:, -1] / (self.S - 1)
-            target = step.unsqueeze(-1) * torch.arange(self.S, dtype=torch.float)
+            target = step.unsqueeze(-1) * torch.arange(self.S, dtype=torch.float, device=self.dev)
             seed_inds = torch.argmin(torch.abs(cum.unsqueeze(-1) - target.unsqueeze(1)), dim=1)
         x = joints - joints[:, :, [self.o]]
         k = 20
-        idx = (torch.arange(T)[:, None] + torch.arange(-k // 2, k // 2)[None]).clamp(0, T - 1)      # (T,k)
+        idx = (torch.arange(T)[:, None] + torch.arange(-k // 2, k // 2)[None]).clamp(0, T - 1).to(self.dev)   # (T,k); built on the host each call like stgcn.py:109-114
         rel = hip[:, idx] - hip[:, :, None]                                                        # (B,T,k,3)
         pos = self._mlp3(rel.reshape(B, T * k, 3).transpose(1, 2), "backbone.pos_embed")
         pos = pos.transpose(1, 2).contiguous().view(B, T, k, -1).mean(dim=2)
@@ -116,11 +137,14 @@ class RefP2RNet:
     # ------------------------------------------------------------------ detection (proposal_net.py:150-252)
     def _sa(self, xyz, features):  # features (B,C,N)
         B, C, N = features.shape
-        inds = RefExt.furthest_point_sampling(xyz.detach().contiguous(), self.P)
+        inds = self.ext.furthest_point_sampling(xyz.detach().contiguous(), self.P)
         new_xyz = torch.gather(xyz, 1, inds.long()[:, :, None].expand(B, self.P, 3)).contiguous()
-        idx = RefExt.ball_query(new_xyz.detach().contiguous(), xyz.detach().contiguous(), 0.3, 16).long()  # (B,P,S)
-        grouped = torch.gather(features[:, :, None, :].expand(B, C, self.P, N), 3,
-                               idx[:, None].expand(B, C, self.P, 16))                                # (B,C,P,16)
+        idx = self.ext.ball_query(new_xyz.detach().contiguous(), xyz.detach().contiguous(), 0.3, 16)       # (B,P,S) i32
+        if self.dev.type == "cuda":       # the reference's GroupingOperation (pointnet2_utils.py:194-240) on its own kernels
+            grouped = _RefGrouping.apply(self.ext, features.contiguous(), idx.contiguous())
+        else:
+            grouped = torch.gather(features[:, :, None, :].expand(B, C, self.P, N), 3,
+                                   idx.long()[:, None].expand(B, C, self.P, 16))                     # (B,C,P,16)
         pre = "detection.vote_aggregation.mlp_module"
         h = F.relu(F.conv2d(grouped, self.p[pre + ".0.weight"], self.p[pre + ".0.bias"]))
         h = F.relu(F.conv2d(h, self.p[pre + ".2.weight"], self.p[pre + ".2.bias"]))
@@ -185,9 +209,10 @@ class RefP2RNet:
     def generate(self, data):
         with torch.no_grad():
             ep = self.forward(data, generate=True)
-        hip = data["input_joints"][:, :, self.o].numpy()
-        parsed = geometry_ref.parse_predictions(ep["center"].numpy(), ep["size"].numpy(), ep["heading"].numpy(),
-                                                ep["objectness_scores"].numpy(), ep["sem_cls_scores"].numpy(), hip)
+        hip = data["input_joints"][:, :, self.o].cpu().numpy()
+        parsed = geometry_ref.parse_predictions(ep["center"].cpu().numpy(), ep["size"].cpu().numpy(),
+                                                ep["heading"].cpu().numpy(), ep["objectness_scores"].cpu().numpy(),
+                                                ep["sem_cls_scores"].cpu().numpy(), hip)
         return ep, parsed
 
     # ------------------------------------------------------------------ loss (models/loss.py:42-189)
@@ -230,7 +255,7 @@ class RefP2RNet:
         eu = torch.sqrt(dist1 + 1e-6)
         obj_label = (eu < 0.3).long()
         obj_mask = ((eu < 0.3) | (eu > 0.6)).float()
-        ce = F.cross_entropy(est["objectness_scores"].transpose(2, 1), obj_label, weight=torch.tensor([0.1, 0.9]),
+        ce = F.cross_entropy(est["objectness_scores"].transpose(2, 1), obj_label, weight=torch.tensor([0.1, 0.9], device=self.dev),
                              reduction="none")
         objectness_loss = torch.sum(ce * obj_mask) / (torch.sum(obj_mask) + 1e-6)
         # box + class

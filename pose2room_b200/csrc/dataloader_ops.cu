@@ -78,7 +78,7 @@ make_batch_kernel(const float* __restrict__ joints, const float* __restrict__ vo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Variant 2 (opt-in until it has been measured against variant 1 on a B200: bench.py's data_path.variants A/B).
+// Variant 2 (the default since round 2; P2R_MAKE_BATCH_VARIANT=1 selects variant 1; bench.py's data_path.variants A/B).
 // Same arithmetic, different data movement: persistent CTAs walk over (batch item, group of 8 frames) work items with
 // a 3-stage cp.async ring, so the raw rows of the next two groups are in flight (no registers, no thread waiting on
 // them) while the current group is transformed and stored -- variant 1 exposes the full load latency of every CTA.
@@ -248,7 +248,7 @@ extern "C" int p2r_make_batch(const float* joints, const float* votes, const lon
   static int variant = 0;
   if (variant == 0) {
     const char* e = getenv("P2R_MAKE_BATCH_VARIANT");
-    variant = (e != nullptr && atoi(e) == 2) ? 2 : 1;
+    variant = (e != nullptr && atoi(e) == 1) ? 1 : 2;   // 2 since round 2: 38.8 vs 86.2 us on a B200, bit-identical
   }
   return make_batch_launch(variant, joints, votes, frame_start, sample_ids, params, b, num_frames, j, out_channels,
                            input_joints, vote_label, vote_label_mask, stream);

@@ -25,10 +25,11 @@ OBJECTNESS_CLS_WEIGHTS = [0.1, 0.9]
 _FAR_AWAY = 1.0e4  # padded GT centres: (1e4)^2 * 3 = 3e8, finite in fp32, never the nearest
 
 
-# The whole loss as one forward + one backward launch (csrc/loss_ops.cu).  Opt-in until it has been measured on a B200
-# against the chain of torch kernels below; read at call time so a test or bench child can flip it per process.
+# The whole loss as one forward + one backward launch (csrc/loss_ops.cu): the default since round 2 (B200: parity-green on
+# the reference goldens with the flag on, 9.29 -> 8.87 ms/step; profiles/r02_first_call_diag.log).  P2R_FUSED_LOSS=0 selects
+# the chain of torch kernels below (kept as the second implementation the fused kernel is tested against); read at call time.
 def fused_loss_enabled():
-    return os.environ.get("P2R_FUSED_LOSS", "0") != "0"
+    return os.environ.get("P2R_FUSED_LOSS", "1") != "0"
 
 
 def _rows(t, width):
@@ -181,8 +182,11 @@ class BoxNetDetectionLoss(BaseLoss):
             est["vote_xyz"], est["center"], est["size"], est["heading"], est["objectness_scores"], est["sem_cls_scores"],
             est["aggregated_vote_xyz"], est["seed_skeleton"], est["seed_inds"], gt["vote_label"], gt["vote_label_mask"],
             gt["center_label"], gt["box_label_mask"], gt["size"], gt["heading"], gt["sem_cls_label"], self.origin_joint_id)
-        return {"total": o64[1], "vote_loss": o32[0], "objectness_loss": o32[1], "center_loss": o32[2],
-                "size_loss": o32[3], "heading_loss": o64[0], "sem_cls_loss": o32[4], "pos_ratio": o32[5],
+        total, heading_loss = o64[1], o64[0]
+        if est["heading"].dtype != torch.float64:    # type promotion of the torch chain: float64 only through a float64 heading
+            total, heading_loss = total.float(), heading_loss.float()
+        return {"total": total, "vote_loss": o32[0], "objectness_loss": o32[1], "center_loss": o32[2],
+                "size_loss": o32[3], "heading_loss": heading_loss, "sem_cls_loss": o32[4], "pos_ratio": o32[5],
                 "neg_ratio": o32[6], "obj_acc": o32[7]}
 
     def __call__(self, est, gt, dataset_config):

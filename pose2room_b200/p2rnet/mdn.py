@@ -20,10 +20,11 @@ from .. import _lib, ops
 from .sub_modules import SingleConv
 
 
-# sigmoid + sampling + mixing of a head as one forward and one backward launch (csrc/gmm_ops.cu).  Opt-in until it has
-# been measured on a B200 against the chain of torch kernels; read at call time (a test / bench child flips it per process).
+# sigmoid + sampling + mixing of a head as one forward and one backward launch (csrc/gmm_ops.cu).  Default since round 2
+# (parity-green on a B200 with the flag on); P2R_FUSED_GMM=0 selects the chain of torch kernels it is tested against.
+# Read at call time (a test / bench child flips it per process).
 def fused_gmm_enabled():
-    return os.environ.get("P2R_FUSED_GMM", "0") != "0"
+    return os.environ.get("P2R_FUSED_GMM", "1") != "0"
 
 
 class _FusedGMMPredict(Function):

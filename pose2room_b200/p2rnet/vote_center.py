@@ -16,9 +16,10 @@ from .sub_modules import SingleConv, run_rows
 
 
 # residual adds + L2 normalisation of the vote features as one forward and one backward launch (csrc/vote_ops.cu).
-# Opt-in until it has been measured on a B200; read at call time (a test / bench child flips it per process).
+# Default since round 2 (parity-green on a B200 with the flag on); P2R_FUSED_VOTE=0 selects the torch path it is tested
+# against.  Read at call time (a test / bench child flips it per process).
 def fused_vote_enabled():
-    return os.environ.get("P2R_FUSED_VOTE", "0") != "0"
+    return os.environ.get("P2R_FUSED_VOTE", "1") != "0"
 
 
 class _VoteTail(Function):

@@ -209,6 +209,7 @@ def _fused_vs_chain_on_random_predictions(dev):
     for seed, hd in [(1, torch.float64), (3, torch.float32)]:
         est, gt, sem_obj = make_case(seed, B=4, T=64, S=40, P=32, heading_dtype=hd)
         results = []
+        before = os.environ.get("P2R_FUSED_LOSS")
         for flag in ("0", "1"):
             os.environ["P2R_FUSED_LOSS"] = flag
             leaves = {k: est[k].clone().to(dev).requires_grad_(True) for k in ("vote_xyz", "center", "size", "heading")}
@@ -223,6 +224,10 @@ def _fused_vs_chain_on_random_predictions(dev):
             results.append(({k: v.item() for k, v in out.items()},
                             dict({k: v.grad.double().cpu() for k, v in leaves.items()}, sem_obj=so.grad.double().cpu()),
                             {k: v.dtype for k, v in out.items()}))
+        if before is None:
+            os.environ.pop("P2R_FUSED_LOSS")
+        else:
+            os.environ["P2R_FUSED_LOSS"] = before
         (a, ga, da), (b, gb, db) = results
         assert da == db, (da, db)
         for k in a:
@@ -264,12 +269,6 @@ def _fused_gmm_vs_torch_path(dev):
         lg_tol = 1e-2 if lg_dtype == torch.bfloat16 else 3e-6        # d logits is rounded to bf16 on the fused path
         for name, a, b, tol in zip(("out", "dlogits", "dmu", "dls"), res[0], res[1], (3e-6, lg_tol, 2e-5, 2e-5)):
             assert (a - b).abs().max().item() <= tol * max(1e-3, a.abs().max().item()), (G, D, name, (a - b).abs().max().item())
-
-
-_FUSED_REASON = ("the fused %s kernel(s) were written after the round's GPU budget was spent: the arithmetic is held to the "
-                 "oracle on the CPU (test_loss_math.py / test_gmm_math.py) and the kernels run under the host emulator "
-                 "(test_kernels_emulated.py); on the GPU they are checked here in a process of their own, non-gating "
-                 "until they have passed on a B200")
 
 
 def _run_isolated(flags, extra=""):
@@ -323,11 +322,20 @@ def _fused_vote_vs_torch_path(dev):
                 gemm_sm100.uninstall()
 
 
-@pytest.mark.xfail(strict=False, reason=_FUSED_REASON % "detection-loss / mixture-head / vote-tail (csrc/loss_ops.cu, gmm_ops.cu, "
-                                        "vote_ops.cu; P2R_FUSED_LOSS / P2R_FUSED_GMM / P2R_FUSED_VOTE)")
-def test_fused_paths_pass_the_parity_tests(cuda):
-    """One process: each fused kernel against the path it replaces (the first assertion that fails names the kernel), then
-    the reference-golden parity tests and the bf16 check with all three flags on."""
-    _run_isolated(["P2R_FUSED_LOSS", "P2R_FUSED_GMM", "P2R_FUSED_VOTE"],
-                  "T._fused_vs_chain_on_random_predictions(dev); os.environ['P2R_FUSED_LOSS'] = '0'; "
-                  "T._fused_gmm_vs_torch_path(dev); T._fused_vote_vs_torch_path(dev); ")
+def test_fused_loss_kernel_vs_torch_chain(cuda):
+    _fused_vs_chain_on_random_predictions(cuda)
+
+
+def test_fused_mixture_head_kernels_vs_torch_path(cuda):
+    _fused_gmm_vs_torch_path(cuda)
+
+
+def test_fused_vote_tail_kernels_vs_torch_path(cuda):
+    _fused_vote_vs_torch_path(cuda)
+
+
+def test_unfused_paths_pass_the_parity_tests(cuda):
+    """The fused detection-loss / mixture-head / vote-tail kernels are the default since round 2, so every parity test of
+    this file runs them.  Here, in a process of its own, the reference-golden parity tests and the bf16 check with all
+    three flags OFF: the chains of torch kernels the fused kernels replaced stay a tested second implementation."""
+    _run_isolated([], "os.environ.update(P2R_FUSED_LOSS='0', P2R_FUSED_GMM='0', P2R_FUSED_VOTE='0'); ")

@@ -2,12 +2,9 @@
 1000 synthetic scenes against what the UNMODIFIED reference produced for the same inputs (tests/golden/eval1k.npz;
 parse_predictions with scipy Delaunay + numpy NMS, APCalculator with Qhull IoU).
 
-  gating    : mAP@0.25 / mAP@0.5 / AR within 5e-3 of the reference's (north_star asks for +-0.1), selection equal on
-              at least 99.9 % of the proposals, prediction counts within 0.1 % in total, corner checksums to fp32-exp
-              rounding.
-  non-gating: selection (pred_mask) bit-exact on all 128 000 proposals and every per-class AP to 1e-6 -- expected to hold
-              (it does on the small fixtures), but written without a GPU at hand, hence xfail(strict=False) for one round.
-The file sorts last on purpose: under `pytest -x` nothing can hide behind it."""
+Both tests gate: mAP@0.25 / mAP@0.5 / AR within 5e-3 of the reference's (north_star asks for +-0.1), corner checksums to
+fp32-exp rounding, AND selection (pred_mask) bit-exact on all 128 000 proposals with every per-class AP to 1e-6 (green on
+a B200 since round 1's end run; the xfail cushion is gone)."""
 import time
 
 import numpy as np
@@ -70,8 +67,6 @@ def test_map_parity_on_1000_scenes(run):
         assert abs(metrics[thr]["AR"] - float(g["ar_" + tag])) < 5e-3, (thr, metrics[thr]["AR"], float(g["ar_" + tag]))
 
 
-@pytest.mark.xfail(strict=False, reason="bit-exact selection and 1e-6 AP at the 1000-scene scale: expected to hold, first run on a "
-                                        "GPU is the round-end one (the set was built after the round's GPU budget was spent)")
 def test_selection_bit_exact_and_per_class_ap_on_1000_scenes(run):
     g, want_mask, mask, counts, checks, metrics = run
     assert np.array_equal(mask, want_mask), int((mask != want_mask).sum())
