@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--data-path-variants", action="store_true", help="internal: A/B of the make_batch kernel variants")
+    ap.add_argument("--leg", default=None, choices=["gpu_reference", "extras"],
+                    help="internal: one of the secondary legs of bench_legs.py (run by the supervisor in a child process)")
     return ap.parse_args()
 
 
@@ -235,15 +237,13 @@ def _variants_subprocess(script):
         return {"error": repr(e)}
 
 
-# Opt-in code paths that were written after this round's GPU budget was spent (fused detection loss, mixture heads, vote tail)
-# or whose gain was inside the box-to-box spread (internal joint permutation).  After the headline measurement is safe,
-# each is measured by a fresh child of this same script on the same box with the same step count, bounded in time, and
-# reported next to the headline -- never instead of it, and whatever happens in these processes cannot change it.
+# Alternative configurations of the SAME workload, each measured by a fresh child of this script on the same box with the
+# same step count after the headline measurement is safe, bounded in time, reported next to the headline -- never instead
+# of it.  `fp32_mode` is the precision whose outputs are held to 1e-4 of the reference goldens (tests/test_model_gpu.py);
+# the headline is the bf16 mode north_star sanctions for the dense layers.
 EXPERIMENTS = [
-    ("fused_loss+gmm+vote", {"P2R_FUSED_LOSS": "1", "P2R_FUSED_GMM": "1", "P2R_FUSED_VOTE": "1"}),
-    ("joint_perm", {"P2R_JOINT_PERM": "1"}),
-    ("fused_loss", {"P2R_FUSED_LOSS": "1"}),
-    ("fused_gmm+vote", {"P2R_FUSED_GMM": "1", "P2R_FUSED_VOTE": "1"}),
+    ("fp32_mode", {}, ["--precision", "fp32"]),
+    ("unfused_loss+gmm+vote", {"P2R_FUSED_LOSS": "0", "P2R_FUSED_GMM": "0", "P2R_FUSED_VOTE": "0"}, []),
 ]
 
 
@@ -255,15 +255,16 @@ def _experiments(script, headline):
     per_run = float(os.environ.get("P2R_BENCH_EXPERIMENT_TIMEOUT_S", "75"))
     out = {"baseline": {"ms_per_step": headline.get("ms_per_step"), "first_step_loss": headline.get("first_step_loss"),
                         "kernels_per_step": (headline.get("census") or {}).get("kernels")}}
-    for name, extra in EXPERIMENTS:
+    for name, extra, extra_args in EXPERIMENTS:
         left = deadline - time.time()
         if left < 40.0:
             out[name] = {"skipped": "time budget of the experiments leg spent"}
             continue
         try:
             env = dict(os.environ, P2R_BENCH_CHILD="1", P2R_BENCH_DATA_PATH="0", **extra)
+            env["P2R_BENCH_CENSUS"] = "0" if "--precision" in extra_args else env.get("P2R_BENCH_CENSUS", "1")
             args = [sys.executable, script, "--steps", str(headline.get("steps", 10)), "--warmup",
-                    str(headline.get("warmup", 3)), "--no-cpu-baseline"]
+                    str(headline.get("warmup", 3)), "--no-cpu-baseline"] + extra_args
             p = subprocess.Popen(args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, start_new_session=True)
             try:
                 o, e = p.communicate(timeout=min(per_run, left))
@@ -277,7 +278,7 @@ def _experiments(script, headline):
                 out[name] = {"error": "exit code %s: %s" % (p.returncode, e.decode()[-300:])}
                 continue
             d = json.loads(lines[-1])
-            out[name] = {"ms_per_step": d.get("ms_per_step"), "value": d.get("value"),
+            out[name] = {"ms_per_step": d.get("ms_per_step"), "value": d.get("value"), "dtype": d.get("dtype"),
                          "first_step_loss": d.get("first_step_loss"), "gpu_launches": d.get("gpu_launches"),
                          "e2e_ms_per_step": (d.get("e2e") or {}).get("ms_per_step"),
                          "cuda_graph": (d.get("config") or {}).get("cuda_graph"),
@@ -286,6 +287,26 @@ def _experiments(script, headline):
         except Exception as e:
             out[name] = {"error": repr(e)}
     return out
+
+
+def _leg(script, name, timeout_s):
+    """One secondary leg (bench_legs.py) in a process of its own, bounded in time; never raises."""
+    import signal
+    if os.environ.get("P2R_BENCH_LEGS", "1") == "0":
+        return None
+    try:
+        p = subprocess.Popen([sys.executable, script, "--leg", name], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                             start_new_session=True, env=dict(os.environ, P2R_BENCH_CHILD="1"))
+        try:
+            o, e = p.communicate(timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            os.killpg(p.pid, signal.SIGKILL)
+            p.wait()
+            return {"error": "timed out after %.0f s" % timeout_s}
+        lines = [l for l in o.decode().splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"error": "exit code %s: %s" % (p.returncode, e.decode()[-400:])}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def supervise(script=None):
@@ -316,6 +337,28 @@ def supervise(script=None):
                 d["data_path"]["variants"] = _variants_subprocess(script)
             if label is None and isinstance(d.get("roofline"), dict) and d.get("n_gpus") == 1:
                 d["experiments"] = _experiments(script, d)
+                # "the reference on B200" + BASELINE configs #2 (forward only / SA operators) and #5 (eval), bench_legs.py
+                d["gpu_reference"] = _leg(script, "gpu_reference", float(os.environ.get("P2R_BENCH_GPU_REF_TIMEOUT_S", "150")))
+                ref = d["gpu_reference"] if isinstance(d["gpu_reference"], dict) else {}
+                if "fp32" in ref:
+                    d["vs_gpu_reference"] = {
+                        "what": "this line's value and its fp32_mode sibling over the reference formulation + reference "
+                                "kernels on the same B200 (gpu_reference.fp32 / .tf32), same batch, same step",
+                        "bf16_over_reference_fp32": d["value"] / ref["fp32"]["train_sequences_per_s"],
+                        "bf16_over_reference_tf32": d["value"] / ref["tf32"]["train_sequences_per_s"],
+                        "fp32_mode_over_reference_fp32": ((d["experiments"] or {}).get("fp32_mode") or {}).get("value", 0.0) /
+                                                         ref["fp32"]["train_sequences_per_s"] or None}
+                extras = _leg(script, "extras", float(os.environ.get("P2R_BENCH_EXTRAS_TIMEOUT_S", "150")))
+                if isinstance(extras, dict) and "error" in extras and "forward_only" not in extras:
+                    d["extras_error"] = extras["error"]
+                elif isinstance(extras, dict):
+                    d["forward_only"] = extras.get("forward_only")
+                    if isinstance(d["forward_only"], dict) and "fp32" in ref:
+                        d["forward_only"]["gpu_reference_fp32_forward_ms"] = ref["fp32"]["forward_ms"]
+                        d["forward_only"]["gpu_reference_tf32_forward_ms"] = ref["tf32"]["forward_ms"]
+                    d["sa_module_forward"] = extras.get("sa_module_forward")
+                    d["sa_operators"] = extras.get("sa_operators")
+                    d["eval_1k"] = extras.get("eval_1k")
             print(json.dumps(d), flush=True)
             return 0
         if p.returncode != 17:          # a real failure, not a stall: do not hide it behind a retry
@@ -506,6 +549,9 @@ def main():
         return run_reference(args)
     if args.data_path_variants:
         return data_path_variants(args.batch)
+    if args.leg:
+        import bench_legs
+        return bench_legs.main(args.leg)
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 and os.environ.get("P2R_BENCH_CHILD") != "1" and \
             os.environ.get("P2R_BENCH_SUPERVISE", "1") != "0":
         sys.exit(supervise())
@@ -584,9 +630,12 @@ def main():
         finish()
         return loss
 
-    # On one GPU the whole step is captured; with several ranks the graph holds forward + loss + backward and the
-    # all-reduce + fused AdamW (3 launches) run eagerly right after the replay (no NCCL call inside a capture).
-    captured = step if world == 1 else fwd_bwd
+    # The whole step is ONE captured graph on every rank count: forward + loss + backward + the flat NCCL gradient
+    # all-reduce + fused AdamW (NCCL collectives are capturable; the capture is thread-local so the process group's
+    # watchdog thread cannot invalidate it).  Should that capture fail, the round-1 arrangement is the fallback: the graph
+    # holds forward + loss + backward, the all-reduce runs eagerly after the replay and AdamW is a second small graph.
+    graph_allreduce = world > 1 and os.environ.get("P2R_GRAPH_ALLREDUCE", "1") != "0"
+    captured = step if (world == 1 or graph_allreduce) else fwd_bwd
 
     # ---- whole-step CUDA graph: ~3000 launches per step would otherwise be bound by the Python launch path ------
     static = {k: torch.empty_like(v) for k, v in resident.items()}
@@ -611,12 +660,29 @@ def main():
             dbg("eager warm-up done, capturing")
             graph = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
-            with torch.cuda.graph(graph):
-                static_loss = captured(static)
+            if graph_allreduce:
+                ok = 1.0
+                try:
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        static_loss = captured(static)
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    print("bench.py: capture with the NCCL all-reduce inside failed (%r); all-reduce after the replay instead" % (e,),
+                          file=sys.stderr)
+                    ok = 0.0
+                t_ok = torch.tensor([ok], device=dev)
+                dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)          # every rank takes the same branch
+                if float(t_ok.item()) < 1.0:
+                    graph_allreduce, captured = False, fwd_bwd
+                    graph = torch.cuda.CUDAGraph()
+                    opt.zero_grad(set_to_none=True)
+            if not graph_allreduce:
+                with torch.cuda.graph(graph):
+                    static_loss = captured(static)
             torch.cuda.synchronize()
             beat("graph captured")
             dbg("captured")
-            if world > 1 and os.environ.get("P2R_OPT_GRAPH", "1") != "0":
+            if world > 1 and not graph_allreduce and os.environ.get("P2R_OPT_GRAPH", "1") != "0":
                 # several ranks: the NCCL all-reduce stays outside the captures, but the fused AdamW (whose host-side
                 # launch path costs more than its kernels) becomes a second small graph replayed right after it
                 try:
@@ -644,7 +710,7 @@ def main():
             for k in static:
                 static[k].copy_(data[k], non_blocking=True)
         graph.replay()
-        if world > 1:
+        if world > 1 and not graph_allreduce:
             if opt_graph is not None:
                 parallel.allreduce_gradients(params)
                 opt_graph.replay()
@@ -712,10 +778,29 @@ def main():
           [r for r in ops.PROFILE["log"] if r[0] == "fwd" and r[2] == vj and r[3] == vj]
     peaks = measured_peaks()
     roofline = None
+    def live_fraction(kind):
+        """Executed / dense FLOPs of the block-sparse graph-conv GEMMs (64x64 blocks of W_eff that are structurally zero
+        are skipped): forward = the k-block lists of the 256-wide n-tiles, dW = the non-zero 128x128 output tiles."""
+        try:
+            from pose2room_b200 import gemm_sm100
+            sp = net.backbone._w_sparsity
+            if precision != "bf16" or not gemm_sm100.USE_SPARSITY:
+                return 1.0
+            if kind == "fwd":
+                tab = sp.kb_list(gemm_sm100.PAIR_BLOCK_N, False, "cpu").numpy()
+                widths = [min(gemm_sm100.PAIR_BLOCK_N, vj - i * gemm_sm100.PAIR_BLOCK_N) for i in range(tab.shape[0])]
+                return float(sum(w * c * 64 for w, c in zip(widths, tab[:, 0]))) / float(vj * vj)
+            bm, bn = DW_TILE
+            mask = sp.tile_mask(bm, bn, "cpu").numpy()
+            return float(mask.sum() * bm * bn) / float(vj * vj)      # (edge tiles counted whole: what the kernel executes)
+        except Exception:
+            return 1.0
+    from pose2room_b200 import gemm_sm100 as _g
+    DW_TILE = getattr(_g, "DW_TILE", (128, 128))
     if gcn:
         t_ms = sum(r[4].elapsed_time(r[5]) for r in gcn) / len(gcn)
         algo_flops = GCN_ALGO_GFLOP_PER_SEQ * 1e9 * B
-        exec_flops = 2.0 * gcn[0][1] * vj * vj
+        exec_flops = 2.0 * gcn[0][1] * vj * vj * live_fraction("fwd")
         achieved = algo_flops / (t_ms * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -723,8 +808,21 @@ def main():
                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_kernels_summary.txt)",
                     "kernel": "graph-conv GEMM fwd (M=%d,N=K=%d) %s, CTA-pair tcgen05, block-sparse K, fused BN statistics" % (gcn[0][1], vj, precision),
                     "avg_launch_ms": t_ms, "launches_timed": len(gcn), "executed_tflops": exec_flops / (t_ms * 1e-3) / 1e12,
+                    "executed_over_dense": live_fraction("fwd"),
                     "peak_source": peaks["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
                     "share_of_step": t_ms * 6 / (ms / args.steps)}
+    # the other large GEMM of a block: the graph convolution's weight gradient dW_eff = dG^T . X (same algorithmic FLOPs).
+    # Timed here alone on the main stream; in the step it runs on the weight-gradient stream beside the BatchNorm chain.
+    gdw = [r for r in ops.PROFILE["log"] if r[0] == "gcn_dw"]
+    if gdw and roofline is not None:
+        t_dw = sum(r[4].elapsed_time(r[5]) for r in gdw) / len(gdw)
+        dw = {"bound": "tensor", "achieved": GCN_ALGO_GFLOP_PER_SEQ * 1e9 * B / (t_dw * 1e-3) / 1e12, "peak": peaks["tf_sustained"],
+              "unit": "TFLOP/s", "kernel": "graph-conv weight gradient dW_eff[%d,%d] = dG^T.X over %d rows, %s" % (vj, vj, gdw[0][1], precision),
+              "avg_launch_ms": t_dw, "launches_timed": len(gdw), "executed_over_dense": live_fraction("dw"),
+              "executed_tflops": 2.0 * gdw[0][1] * vj * vj * live_fraction("dw") / (t_dw * 1e-3) / 1e12,
+              "share_of_step": t_dw * 6 / (ms / args.steps), "traffic": None}
+        dw["frac"] = dw["achieved"] / dw["peak"]
+        roofline["other_kernels"] = [dw]
     ops.PROFILE["log"] = []
 
     # ---- end to end: pinned host batch -> H2D -> step -> loss read back --------------------------------
@@ -834,6 +932,7 @@ def main():
             "config": {"workload": "P2RNet train step fwd+loss+bwd+AdamW (+grad all-reduce), B=%d/GPU, T=1024, J=25, "
                                    "512 seeds, 128 proposals, 22 classes" % B,
                        "parallelism": "dp%d" % world, "precision": precision, "cuda_graph": graph is not None, "overlap_dw": overlap,
+                       "allreduce_in_graph": bool(world > 1 and graph is not None and graph_allreduce),
                        "l2": "no flush needed: per-layer activations (105-420 MB) exceed the 126 MB L2"},
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes,

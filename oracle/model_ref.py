@@ -255,7 +255,7 @@ class RefP2RNet:
         eu = torch.sqrt(dist1 + 1e-6)
         obj_label = (eu < 0.3).long()
         obj_mask = ((eu < 0.3) | (eu > 0.6)).float()
-        ce = F.cross_entropy(est["objectness_scores"].transpose(2, 1), obj_label, weight=torch.tensor([0.1, 0.9], device=self.dev),
+        ce = F.cross_entropy(est["objectness_scores"].transpose(2, 1), obj_label, weight=torch.tensor([0.1, 0.9], device=est["objectness_scores"].device),
                              reduction="none")
         objectness_loss = torch.sum(ce * obj_mask) / (torch.sum(obj_mask) + 1e-6)
         # box + class

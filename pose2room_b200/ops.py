@@ -367,7 +367,8 @@ class _GraphConv(Function):
                 dx = tc.linear_dx_pretransposed(dy, w_eff_t, sp)
 
         def weight_grads():
-            dw_eff = tc.linear_dw(dy, x, sp)                     # fp32 [V*Co, V*Ci], structurally-zero tiles stay 0
+            with _Timed("gcn_dw", dy.shape[0], v * co, v * ci):
+                dw_eff = tc.linear_dw(dy, x, sp)                 # fp32 [V*Co, V*Ci], structurally-zero tiles stay 0
             db_eff = None
             if cb is not None:
                 db_eff = fused_cs.reshape(-1).float() if fused_cs is not None else _col_sum(dy)

@@ -96,18 +96,33 @@ def test_variant_ab_runs_in_its_own_process_and_cannot_lose_the_line(tmp_path, m
     assert rc == 0 and json.loads(io.out.strip())["data_path"] == {"error": "boom"}
 
 
-def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_path, monkeypatch, capsys):
-    """Opt-in code paths are measured by fresh children after the headline is safe: results (or an error / a skip) land in
-    `experiments`, the headline numbers stay the first child's."""
+def test_experiments_and_legs_report_next_to_the_headline_and_cannot_lose_it(tmp_path, monkeypatch, capsys):
+    """Alternative configurations (fp32 parity mode, the unfused loss / head paths) and the secondary legs (the reference on
+    the same GPU, forward only / SA operators / eval) are measured by fresh children after the headline is safe: results (or
+    an error / a skip) land next to it, the headline numbers stay the first child's."""
     body = '''
         import json, os, sys, time
+        if "--leg" in sys.argv:
+            leg = sys.argv[sys.argv.index("--leg") + 1]
+            if leg == "gpu_reference":
+                print(json.dumps({"fp32": {"train_sequences_per_s": 2.0, "forward_ms": 7.0},
+                                  "tf32": {"train_sequences_per_s": 4.0, "forward_ms": 6.0}}))
+            elif os.environ.get("FAKE_EXTRAS") == "crash":
+                os.abort()
+            else:
+                print(json.dumps({"forward_only": {"bf16": {"forward_ms": 1.0}}, "sa_operators": [], "sa_module_forward": {},
+                                  "eval_1k": {"total_ms_per_scene": 0.5}}))
+            sys.exit(0)
         if os.environ.get("P2R_BENCH_DATA_PATH") == "0":           # an experiment child
             assert "--no-cpu-baseline" in sys.argv and sys.argv[sys.argv.index("--steps") + 1] == "2"
-            if os.environ.get("P2R_JOINT_PERM") == "1":
+            fp32 = "--precision" in sys.argv and sys.argv[sys.argv.index("--precision") + 1] == "fp32"
+            unfused = all(os.environ.get(k) == "0" for k in ("P2R_FUSED_LOSS", "P2R_FUSED_GMM", "P2R_FUSED_VOTE"))
+            assert fp32 != unfused
+            if unfused and os.environ.get("FAKE_UNFUSED") == "crash":
                 os.abort()
-            both = all(os.environ.get(k) == "1" for k in ("P2R_FUSED_LOSS", "P2R_FUSED_GMM", "P2R_FUSED_VOTE"))
-            print(json.dumps({"value": 9.0 if both else 8.0, "ms_per_step": 1.0 if both else 2.0, "first_step_loss": 0.5,
-                              "gpu_launches": 7, "config": {"cuda_graph": True}, "e2e": {"ms_per_step": 3.0}}))
+            print(json.dumps({"value": 1.0 if fp32 else 8.0, "ms_per_step": 64.0 if fp32 else 2.0, "first_step_loss": 0.5,
+                              "dtype": "f32" if fp32 else "bf16", "gpu_launches": 7, "config": {"cuda_graph": True},
+                              "e2e": {"ms_per_step": 3.0}}))
             sys.exit(0)
         print(json.dumps({"value": 4.0, "ms_per_step": 5.0, "steps": 2, "warmup": 3, "n_gpus": 1, "config": {},
                           "roofline": {"frac": 0.5}, "first_step_loss": 0.5}))
@@ -116,15 +131,26 @@ def test_experiments_leg_reports_next_to_the_headline_and_cannot_lose_it(tmp_pat
     d = json.loads(io.out.strip())
     ex = d["experiments"]
     assert rc == 0 and d["value"] == 4.0 and ex["baseline"] == {"ms_per_step": 5.0, "first_step_loss": 0.5, "kernels_per_step": None}
-    assert ex["fused_loss+gmm+vote"]["ms_per_step"] == 1.0 and ex["fused_loss"]["ms_per_step"] == 2.0
-    assert ex["fused_gmm+vote"]["e2e_ms_per_step"] == 3.0 and "error" in ex["joint_perm"]
+    assert ex["fp32_mode"]["ms_per_step"] == 64.0 and ex["fp32_mode"]["dtype"] == "f32"
+    assert ex["unfused_loss+gmm+vote"]["e2e_ms_per_step"] == 3.0
+    assert d["gpu_reference"]["tf32"]["train_sequences_per_s"] == 4.0
+    assert d["vs_gpu_reference"]["bf16_over_reference_fp32"] == 2.0 and d["vs_gpu_reference"]["fp32_mode_over_reference_fp32"] == 0.5
+    assert d["forward_only"]["bf16"]["forward_ms"] == 1.0 and d["forward_only"]["gpu_reference_fp32_forward_ms"] == 7.0
+    assert d["eval_1k"]["total_ms_per_scene"] == 0.5
+    monkeypatch.setenv("FAKE_UNFUSED", "crash")
+    monkeypatch.setenv("FAKE_EXTRAS", "crash")
+    rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
+    d = json.loads(io.out.strip())
+    assert rc == 0 and d["value"] == 4.0 and "error" in d["experiments"]["unfused_loss+gmm+vote"] and "forward_only" not in d
     monkeypatch.setenv("P2R_BENCH_EXPERIMENTS_BUDGET_S", "1")      # no time left: every experiment is skipped, line intact
     rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
     d = json.loads(io.out.strip())
     assert rc == 0 and d["value"] == 4.0 and all("skipped" in v for k, v in d["experiments"].items() if k != "baseline")
     monkeypatch.setenv("P2R_BENCH_EXPERIMENTS", "0")
+    monkeypatch.setenv("P2R_BENCH_LEGS", "0")
     rc, io = _run(tmp_path, body, monkeypatch, capsys, timeout="30")
-    assert rc == 0 and json.loads(io.out.strip())["experiments"] is None
+    d = json.loads(io.out.strip())
+    assert rc == 0 and d["experiments"] is None and d["gpu_reference"] is None
 
 
 def test_child_that_dies_in_the_census_leg_keeps_its_line(tmp_path, monkeypatch, capsys):
