@@ -539,7 +539,9 @@ def kernel_census(replay):
     return {"kernels": len(ker), "kernel_time_us": sum(v[1] for v in by.values()), "span_us": t1 - t0,
             "torch_glue_kernels": sum(by[k][0] for k in glue), "torch_glue_time_us": sum(by[k][1] for k in glue),
             "memcpy_memset": sum(1 for e in events if e.get("cat") in ("gpu_memcpy", "gpu_memset")),
-            "top_by_time": [{"kernel": k, "launches": v[0], "us": round(v[1], 1)} for k, v in top]}
+            "top_by_time": [{"kernel": k, "launches": v[0], "us": round(v[1], 1)} for k, v in top],
+            "glue_by_count": [{"kernel": k[:60], "launches": by[k][0], "us": round(by[k][1], 1)}
+                              for k in sorted(glue, key=lambda k: -by[k][0])[:16]]}
 
 
 # ------------------------------------------------------------------------------------------ our arm (GPU)
@@ -556,6 +558,9 @@ def main():
             os.environ.get("P2R_BENCH_SUPERVISE", "1") != "0":
         sys.exit(supervise())
     start_watchdog()
+    if os.environ.get("P2R_BENCH_TRACE_AFTER_S"):     # diagnostic: where is the host when a step does not come back
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["P2R_BENCH_TRACE_AFTER_S"]), repeat=False, file=sys.stderr)
 
     import torch.distributed as dist
     from pose2room_b200 import _lib, ops, synthetic
@@ -596,6 +601,8 @@ def main():
     parallel.broadcast_parameters(net)  # identical replicas, like DDP's initial broadcast
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-3, fused=True, capturable=True)
+    if precision == "bf16" and os.environ.get("P2R_WEIGHT_SHADOWS", "1") != "0":
+        ops.register_weight_shadows(net)      # one multi-tensor fp32 -> bf16 copy per step instead of ~45 casts
 
     beat("model built")
     B = args.batch

@@ -159,6 +159,16 @@ int p2r_group_rows_grad(const void* grad, int dtype, const int* idx, int B, int 
 int p2r_maxpool_rows(const void* x, int dtype, long long R, int S, int C, void* out, unsigned char* arg, void* stream);
 int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg, long long R, int S, int C, void* dx,
                           void* stream);
+/* The set-abstraction layer's group -> shared MLP (two 1x1 convs + ReLU) -> max over nsample as ONE tcgen05 kernel
+ * (ref: PointnetSAModuleVotes.forward, pointnet2_modules.py:220-256, with QueryAndGroup's grouping_operation,
+ * pointnet2_utils.py:319-346; csrc/sa_fused.cu): the (B, C, P, S) grouped tensor and the MLP activations are never
+ * written to memory.  feats bf16 [B,N,C] channel-last, idx i32 [B,P,S], w1 / w2 bf16 [C,C] (Conv2d 1x1 weights), b1 / b2
+ * f32 [C] or NULL; C = 256; S a power of two <= 128.  out [B*P, C] (out_dtype 0 = f32, 1 = bf16) = max_s relu(w2 .
+ * relu(w1 . feats[idx[.., s]] + b1) + b2); argmax u8 [B*P, C] or NULL (first maximum, for the backward pass); h1 bf16
+ * [B*P*S, C] or NULL: when given, the first activation is also stored (training keeps it for the backward pass).   */
+int p2r_sa_fused(const void* feats, const int* idx, const void* w1, const float* b1, const void* w2, const float* b2,
+                 int b, int n, int p, int s, int c, void* out, int out_dtype, unsigned char* argmax, void* h1,
+                 void* stream);
 
 /* x[f,j,:] = sk[f,j,:] + mean_k pos[f,k,:] and its backward dpos[f,k,:] = (1/K) sum_j dx[f,j,:]
  * (ref: models/p2rnet/modules/stgcn.py:121,129)                                                                 */
@@ -171,6 +181,10 @@ int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, int J, int K
 int p2r_smallk_linear(const void* x, const float* W, const float* bias, int dtype, long long M, int N, int K, void* y,
                       void* stream);
 int p2r_smallk_dw(const void* dz, const void* x, int dtype, long long M, int N, int K, float* dW, void* stream);
+/* The same two maps with float32 x (point coordinates are never rounded to bf16) and bf16 y / dz: throughput mode. */
+int p2r_smallk_linear_mixed(const float* x, const float* W, const float* bias, long long M, int N, int K, void* y,
+                            void* stream);
+int p2r_smallk_dw_mixed(const void* dz, const float* x, long long M, int N, int K, float* dW, void* stream);
 
 /* bf16 tensor-core GEMM (tcgen05 + TMA + TMEM), the throughput-mode backend of every dense layer, above all the
  * fused graph-convolution GEMM that replaces conv 64->704 + einsum (ref: stgcn_layers.py:58-67).

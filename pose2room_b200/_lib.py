@@ -53,6 +53,8 @@ SIGNATURES = {
     "p2r_embed_sum_grad": [_vp, _c_int, _c_ll, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_linear": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_dw": [_vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],
+    "p2r_smallk_linear_mixed": [_vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
+    "p2r_smallk_dw_mixed": [_vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_col_sum_wide": [_vp, _c_int, _c_ll, _c_int, _vp, _vp],
     "p2r_col_stats": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp],
     "p2r_col_bwd_stats": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
@@ -68,6 +70,7 @@ SIGNATURES = {
     "p2r_group_rows_grad": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_maxpool_rows": [_vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp, _vp],
     "p2r_maxpool_rows_grad": [_vp, _c_int, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
+    "p2r_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp],
     "p2r_make_batch": [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "p2r_make_batch_variant": [_c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "p2r_detection_loss_workspace": [_c_int, _c_int],

@@ -930,9 +930,9 @@ extern "C" int p2r_embed_sum_grad(const void* dx, int dtype, long long frames, i
 //   d weight: dW[n, c] = sum_m dz[m, n] * x[m, c]                  column reduction with K accumulators per channel
 // (no input gradient: the inputs are data).  N % VEC == 0 and (256 * VEC) % N == 0.
 // ================================================================================================
-template <typename T>
+template <typename T, typename TX = T>
 __global__ void __launch_bounds__(256)
-smallk_linear_kernel(long long M, int N, int K, const T* __restrict__ x, const float* __restrict__ W,
+smallk_linear_kernel(long long M, int N, int K, const TX* __restrict__ x, const float* __restrict__ W,
                      const float* __restrict__ bias, T* __restrict__ y) {
   constexpr int V = VecN<T>::N;
   const int n0 = (threadIdx.x * V) % N;
@@ -949,7 +949,7 @@ smallk_linear_kernel(long long M, int N, int K, const T* __restrict__ x, const f
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += stride) {
     const long long m = e / tpr;
     float xv[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < K; ++c) xv[c] = ldf<T>(x + (size_t)m * K + c);
+    for (int c = 0; c < K; ++c) xv[c] = ldf<TX>(x + (size_t)m * K + c);
     float o[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -962,9 +962,9 @@ smallk_linear_kernel(long long M, int N, int K, const T* __restrict__ x, const f
   }
 }
 
-template <typename T>
+template <typename T, typename TX = T>
 __global__ void __launch_bounds__(256)
-smallk_dw_kernel(long long M, int N, int K, const T* __restrict__ dz, const T* __restrict__ x, int rows_per_cta,
+smallk_dw_kernel(long long M, int N, int K, const T* __restrict__ dz, const TX* __restrict__ x, int rows_per_cta,
                  float* __restrict__ dW) {
   constexpr int V = VecN<T>::N;
   __shared__ float sh[256 * V];
@@ -981,7 +981,7 @@ smallk_dw_kernel(long long M, int N, int K, const T* __restrict__ dz, const T* _
     float g[V];
     vload(dz + (size_t)r * N + n0, g);
     float xv[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < K; ++c) xv[c] = ldf<T>(x + (size_t)r * K + c);
+    for (int c = 0; c < K; ++c) xv[c] = ldf<TX>(x + (size_t)r * K + c);
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -1013,6 +1013,28 @@ extern "C" int p2r_smallk_linear(const void* x, const float* W, const float* bia
   else
     smallk_linear_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)x, W, bias, (__nv_bfloat16*)y);
   P2R_RETURN_LAUNCH("p2r_smallk_linear");
+}
+
+// The first layer of a point MLP in throughput mode: COORDINATES stay float32 (rounding a position of ~1 m to bf16 moves it
+// by millimetres: the largest single contribution to the bf16-vs-fp32 error of the whole backbone), the output is bf16.
+extern "C" int p2r_smallk_linear_mixed(const float* x, const float* W, const float* bias, long long M, int N, int K,
+                                       void* y, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && K >= 1 && K <= 4 && N > 0, "p2r_smallk_linear_mixed");
+  P2R_CHECK_ARG(N % 8 == 0 && (256 * 8) % N == 0, "p2r_smallk_linear_mixed (N must divide 2048)");
+  if (M == 0) return 0;
+  const int grid = (int)min((long long)P2R_SM_COUNT * 16, (M * (N / 8) + 255) / 256);
+  smallk_linear_kernel<__nv_bfloat16, float><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, x, W, bias, (__nv_bfloat16*)y);
+  P2R_RETURN_LAUNCH("p2r_smallk_linear_mixed");
+}
+
+extern "C" int p2r_smallk_dw_mixed(const void* dz, const float* x, long long M, int N, int K, float* dW, void* stream) {
+  P2R_CHECK_ARG(M >= 0 && K >= 1 && K <= 4 && N > 0, "p2r_smallk_dw_mixed");
+  P2R_CHECK_ARG(N % 8 == 0 && 256 % (N / 8) == 0, "p2r_smallk_dw_mixed");
+  if (M == 0) return 0;
+  int rpc;
+  const int grid = colreduce_grid(M, &rpc);
+  smallk_dw_kernel<__nv_bfloat16, float><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)dz, x, rpc, dW);
+  P2R_RETURN_LAUNCH("p2r_smallk_dw_mixed");
 }
 
 // dW f32[N,K] must be zero-filled by the caller.

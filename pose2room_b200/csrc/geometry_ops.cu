@@ -194,13 +194,13 @@ nn_distance_kernel(int n, int m, int c, int mode, float delta, const float* __re
                    const float* __restrict__ pc2, float* __restrict__ dist1, long long* __restrict__ idx1,
                    float* __restrict__ dist2, long long* __restrict__ idx2) {
   P2R_DYN_SMEM(float, s_other);  // [tile][c]
-  const int b = blockIdx.y;
-  const bool second = blockIdx.z == 1;
+  const int b = blockIdx.x;      // the batch runs along grid.x: the vote loss calls this with B * num_seeds "batches"
+  const bool second = blockIdx.z == 1;      // (grid.y is limited to 65535, grid.x is not)
   const int nr = second ? m : n, no = second ? n : m;
   const float* rows = (second ? pc2 : pc1) + (size_t)b * nr * c;
   const float* others = (second ? pc1 : pc2) + (size_t)b * no * c;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((long long)blockIdx.x * blockDim.x >= nr) return;  // whole CTA out of range (uniform)
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if ((long long)blockIdx.y * blockDim.x >= nr) return;  // whole CTA out of range (uniform)
   float best = __int_as_float(0x7f800000);
   int besti = 0;
   bool any = false;
@@ -238,7 +238,8 @@ extern "C" int p2r_nn_distance(const float* pc1, const float* pc2, int b, int n,
   P2R_CHECK_ARG(smem <= 200 * 1024, "p2r_nn_distance (C too large for the smem tile)");
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(nn_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(p2r_ceil_div(mx, 128), b, 2);
+  P2R_CHECK_ARG(p2r_ceil_div(mx, 128) <= 65535, "p2r_nn_distance (more than 8 M points per cloud)");
+  dim3 grid(b, p2r_ceil_div(mx, 128), 2);
   P2R_LAUNCH(nn_distance_kernel, grid, 128, smem, (cudaStream_t)stream, n, m, c, mode, delta, pc1, pc2, dist1, idx1, dist2, idx2);
   P2R_RETURN_LAUNCH("p2r_nn_distance");
 }

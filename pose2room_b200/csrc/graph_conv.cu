@@ -87,9 +87,11 @@ extern "C" int p2r_gcn_build_weight(const float* conv_w, const float* conv_b, co
 // Backward of the construction above, two launches, no atomics (deterministic):
 //   gcn_dA_kernel, grid (V, V), block (w, v):
 //     dA[k,v,w] = <W_k, dW_eff block (w,v)> + sum_co conv_b[k,co] * db_eff[w,co]   where A[k,v,w] != 0, else 0
-//   gcn_dw_kernel, grid (K, 8), block (k, 8 output rows co):
+//   gcn_dw_kernel, grid (K, 64), block (k, output row co), 8 warps that split the joints v between them (warp i takes
+//   v = i, i + 8, ...: eight short chains of dependent loads instead of one long one -- round 1's version, one warp per
+//   row walking all V*V pairs, took 68 us for 10 MB), combined through shared memory in warp order:
 //     d_conv_w[k*64+co, ci] = sum over (v,w) with A[k,v,w] != 0 of A[k,v,w] * dW_eff[(w,co),(v,ci)]
-//     d_conv_b[k*64+co]     = sum_w db_eff[w,co] * sum_v A[k,v,w]                          (the slice that owns co)
+//     d_conv_b[k*64+co]     = sum_w db_eff[w,co] * sum_v A[k,v,w]
 // Entries of dA where A == 0 are written as 0: A = adjacency * importance, so the chain rule multiplies them by the
 // adjacency's zero anyway, and the structurally-zero blocks of dW_eff are never computed (tile mask of the dW GEMM).
 __global__ void __launch_bounds__(256)
@@ -140,32 +142,46 @@ gcn_dA_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff
 __global__ void __launch_bounds__(256)
 gcn_dw_kernel(const float* __restrict__ dw_eff, const float* __restrict__ db_eff, const float* __restrict__ A, int K,
               int V, float* __restrict__ d_conv_w, float* __restrict__ d_conv_b) {
-  P2R_DYN_SMEM(float, sA);                                   // A[k] : V x V
-  const int k = blockIdx.x, slice = blockIdx.y, t = threadIdx.x;
+  P2R_DYN_SMEM(float, sA);                                   // A[k] : V x V, then red[8][64]
+  float* red = sA + V * V;
+  const int k = blockIdx.x, co = blockIdx.y, t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   for (int i = t; i < V * V; i += 256) sA[i] = __ldg(A + (size_t)k * V * V + i);
   __syncthreads();
-  const int co = slice * 8 + (t >> 5);                       // 8 output rows per CTA, one warp each
-  const int ci = (t & 31) * 2;                               // two adjacent columns per lane: 256-byte rows per warp
+  const int ci = lane * 2;                                   // two adjacent columns per lane: 256-byte rows per warp
   const size_t ld = (size_t)V * GC_C;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int v = 0; v < V; ++v)
+  for (int v = warp; v < V; v += 8) {
+    const float* base = dw_eff + (size_t)co * ld + (size_t)v * GC_C + ci;
+#pragma unroll 4
     for (int w = 0; w < V; ++w) {
       const float a = sA[v * V + w];
-      if (a != 0.f) {                                        // (block-uniform)
-        const float2 q = __ldg(reinterpret_cast<const float2*>(dw_eff + ((size_t)w * GC_C + co) * ld + (size_t)v * GC_C + ci));
+      if (a != 0.f) {                                        // (warp-uniform)
+        const float2 q = __ldg(reinterpret_cast<const float2*>(base + (size_t)w * GC_C * ld));
         acc0 = fmaf(a, q.x, acc0);
         acc1 = fmaf(a, q.y, acc1);
       }
     }
-  *reinterpret_cast<float2*>(d_conv_w + ((size_t)k * GC_C + co) * GC_C + ci) = make_float2(acc0, acc1);
-  if (d_conv_b != nullptr && db_eff != nullptr && (t & 31) == 0) {
+  }
+  red[warp * GC_C + ci] = acc0;
+  red[warp * GC_C + ci + 1] = acc1;
+  __syncthreads();
+  if (t < GC_C) {
     float s = 0.f;
-    for (int w = 0; w < V; ++w) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i * GC_C + t];      // fixed order: deterministic
+    d_conv_w[((size_t)k * GC_C + co) * GC_C + t] = s;
+  }
+  if (d_conv_b != nullptr && db_eff != nullptr && warp == 1) {
+    float s = 0.f;
+    for (int w = lane; w < V; w += 32) {
       float cs = 0.f;
       for (int v = 0; v < V; ++v) cs += sA[v * V + w];
       s = fmaf(__ldg(db_eff + w * GC_C + co), cs, s);
     }
-    d_conv_b[k * GC_C + co] = s;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) d_conv_b[k * GC_C + co] = s;
   }
 }
 
@@ -173,9 +189,9 @@ extern "C" int p2r_gcn_reduce_weight_grad(const float* dw_eff, const float* db_e
                                           const float* conv_b, const float* A, int K, int V, int Co, int Ci,
                                           float* d_conv_w, float* d_conv_b, float* dA, void* stream) {
   P2R_CHECK_ARG(K > 0 && V > 0 && Co == GC_C && Ci == GC_C, "p2r_gcn_reduce_weight_grad (64 -> 64 channel blocks)");
-  P2R_CHECK_ARG((size_t)V * V * sizeof(float) <= 48 * 1024, "p2r_gcn_reduce_weight_grad (adjacency too large for shared memory)");
+  P2R_CHECK_ARG(((size_t)V * V + 8 * GC_C) * sizeof(float) <= 48 * 1024, "p2r_gcn_reduce_weight_grad (adjacency too large for shared memory)");
   P2R_LAUNCH(gcn_dA_kernel, dim3(V, V), 256, 0, (cudaStream_t)stream, dw_eff, db_eff, conv_w, conv_b, A, K, V, dA);
-  P2R_LAUNCH(gcn_dw_kernel, dim3(K, GC_C / 8), 256, (size_t)V * V * sizeof(float), (cudaStream_t)stream, dw_eff, db_eff, A,
-             K, V, d_conv_w, d_conv_b);
+  P2R_LAUNCH(gcn_dw_kernel, dim3(K, GC_C), 256, ((size_t)V * V + 8 * GC_C) * sizeof(float), (cudaStream_t)stream, dw_eff,
+             db_eff, A, K, V, d_conv_w, d_conv_b);
   P2R_RETURN_LAUNCH("p2r_gcn_reduce_weight_grad");
 }

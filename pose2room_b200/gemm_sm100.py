@@ -188,7 +188,7 @@ class _TemporalConvTC(torch.autograd.Function):
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
         x = x if x.is_contiguous() else x.contiguous()
-        w2 = weight[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci).to(torch.bfloat16).contiguous()
+        w2 = ops.bf16_weight(weight)[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci).contiguous()   # column = dt*Ci + ci
         y = torch.empty(b * t * v, co, dtype=torch.bfloat16, device=x.device)
         bias_f = bias.float().contiguous() if bias is not None else None
         sums = None
@@ -216,7 +216,7 @@ class _TemporalConvTC(torch.autograd.Function):
         dx = dw = db = None
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:
-                wt = weight[:, :, :, 0].permute(2, 0, 1).reshape(kt * co, ci).to(torch.bfloat16).contiguous()
+                wt = ops.bf16_weight(weight)[:, :, :, 0].permute(2, 0, 1).reshape(kt * co, ci).contiguous()
                 dx = torch.empty(b, t, v, ci, dtype=torch.bfloat16, device=x.device)
                 _lib.call("p2r_tconv_bf16", 1, dy.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), b, t * v, ci, co, kt, v,
                           None, 1, None, 1, _stream())

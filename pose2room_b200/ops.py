@@ -50,8 +50,46 @@ PROFILE = {"on": False, "log": []}
 # frees -- the graph behind the weight, e.g. the einsum that builds W_eff) and remember the real one as the target of
 # the deferred gradient.  Off by default: a plain forward + `loss.backward()` (what the reference's trainer does,
 # models/training.py:25-43) behaves exactly as before.
-DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": [], "ws": {}, "ws_off": {}}
+DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": [], "ws": {}, "ws_off": {},
+         "streams_by_device": {}, "device": None}
 _WS_BYTES = 8 << 20
+
+
+# ---- bf16 shadow copies of the weights (throughput mode) ---------------------------------------------------------
+# Every tensor-core layer needs its fp32 weight in bf16.  Converting layer by layer costs ~45 tiny cast kernels per step;
+# with shadows registered, ONE multi-tensor copy refreshes all of them when the step context is entered (after the
+# previous optimiser step, inside the captured graph) and the layers look their weight up by address.
+_SHADOW = {"params": [], "copies": [], "by_ptr": {}}
+
+
+def register_weight_shadows(module):
+    """Create bf16 shadows for every float32 parameter of `module` with two or more dimensions (call once, after the
+    module is on its device; harmless for modules that never run in bf16 mode)."""
+    params = [p for p in module.parameters() if p.dtype == torch.float32 and p.dim() >= 2 and p.is_cuda]
+    copies = [torch.empty_like(p, dtype=torch.bfloat16) for p in params]
+    _SHADOW["params"], _SHADOW["copies"] = params, copies
+    _SHADOW["by_ptr"] = {p.data_ptr(): c for p, c in zip(params, copies)}
+    refresh_weight_shadows()
+
+
+def clear_weight_shadows():
+    _SHADOW["params"], _SHADOW["copies"], _SHADOW["by_ptr"] = [], [], {}
+
+
+def refresh_weight_shadows():
+    if _SHADOW["params"]:
+        with torch.no_grad():
+            torch._foreach_copy_(_SHADOW["copies"], _SHADOW["params"])
+
+
+def bf16_weight(w):
+    """`w` (a parameter or a reshaped view of one) in bf16: its registered shadow if there is one, else a conversion."""
+    if w.dtype == torch.bfloat16:
+        return w
+    c = _SHADOW["by_ptr"].get(w.data_ptr()) if w.is_contiguous() else None
+    if c is not None and c.numel() == w.numel():
+        return c.view(w.shape)
+    return w.to(torch.bfloat16)
 
 
 def zeros_ws(shape, dtype, device):
@@ -73,11 +111,21 @@ def zeros_ws(shape, dtype, device):
 
 
 class overlap_weight_grads:
+    """Ordering contract (also INTEGRATION.md): parameters receive their `.grad` only when the context EXITS (or at an
+    explicit `flush()`), so `optimizer.step()`, gradient clipping and any gradient all-reduce belong AFTER the `with`
+    block; `parallel.allreduce_gradients` raises if it is called while deferred gradients are pending.  The model must
+    live on the CUDA device that is current when the context is entered (the side / branch streams and the workspace
+    are per device)."""
+
     def __enter__(self):
-        if DEFER["stream"] is None:
-            DEFER["stream"] = torch.cuda.Stream()
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+        per_dev = DEFER["streams_by_device"].setdefault(dev, {"stream": None, "branch_streams": []})
+        if per_dev["stream"] is None:
+            per_dev["stream"] = torch.cuda.Stream()
+        DEFER["stream"], DEFER["branch_streams"], DEFER["device"] = per_dev["stream"], per_dev["branch_streams"], dev
         DEFER["items"] = []
         DEFER["on"] = True
+        refresh_weight_shadows()               # (no-op unless register_weight_shadows was called)
         if torch.cuda.is_available():          # one memset for every small zero-initialised buffer of the step
             key = str(torch.device("cuda", torch.cuda.current_device()))
             if key not in DEFER["ws"]:
@@ -86,17 +134,30 @@ class overlap_weight_grads:
             DEFER["ws_off"][key] = 0
         return self
 
+    @staticmethod
+    def flush():
+        """Join the side stream and hand every deferred gradient to autograd now (parameters get their `.grad`)."""
+        items, DEFER["items"] = DEFER["items"], []
+        torch.cuda.current_stream().wait_stream(DEFER["stream"])      # join: every deferred dW / db is complete
+        if items:
+            tensors = [t for t, g, _ in items]
+            grads = [g for t, g, _ in items]
+            torch.autograd.backward(tensors, grads)                    # views / einsum backward -> leaf .grad
+
     def __exit__(self, exc_type, exc, tb):
         DEFER["on"] = False
         DEFER["keep"] = []
         _COLSUM.clear()
-        items, DEFER["items"] = DEFER["items"], []
-        torch.cuda.current_stream().wait_stream(DEFER["stream"])      # join: every deferred dW / db is complete
-        if exc_type is None and items:
-            tensors = [t for t, g, _ in items]
-            grads = [g for t, g, _ in items]
-            torch.autograd.backward(tensors, grads)                    # views / einsum backward -> leaf .grad
+        if exc_type is None:
+            self.flush()
+        else:
+            DEFER["items"] = []
+            torch.cuda.current_stream().wait_stream(DEFER["stream"])
         return False
+
+
+def deferred_gradients_pending():
+    return bool(DEFER["items"])
 
 
 def parallel_branches(fns):
@@ -131,6 +192,9 @@ def _defer(fn, targets, keep, inline=False):
     if inline:
         grads = fn()
     else:
+        if torch.cuda.current_device() != DEFER["device"]:
+            raise RuntimeError("pose2room_b200.ops.overlap_weight_grads was entered on cuda:%s but a layer runs on cuda:%s; "
+                               "enter the context with the model's device current" % (DEFER["device"], torch.cuda.current_device()))
         side = DEFER["stream"]
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -223,7 +287,7 @@ class _Linear(Function):
                     _lib.call("p2r_smallk_linear", x.data_ptr(), wf.data_ptr(), _ptr(bf), _DT[x.dtype], x.shape[0],
                               weight.shape[0], x.shape[1], y.data_ptr(), _stream())
             elif tc is not None and x.dtype == torch.bfloat16 and tc.supports(x.shape[0], weight.shape[0], x.shape[1]):
-                w_lp = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)   # once per step: reused by dx
+                w_lp = bf16_weight(weight)   # once per step (or the registered shadow): reused by dx
                 if sparsity is not None or want_stats:
                     y, sums = tc.linear_fwd_ex(x, w_lp, bias, relu, sparsity, want_stats)
                 else:
@@ -297,6 +361,66 @@ class _Linear(Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _col_sum(dz)
         return dx, dw, db, None, None, None, None
+
+
+class _SmallKMixed(Function):
+    """First layer of a point MLP in throughput mode: x [M, K <= 4] float32 COORDINATES (never rounded to bf16), bf16
+    output; dW from the float32 x.  The input carries no gradient (it is the pose data)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, targets, want_stats):
+        x = x if x.is_contiguous() else x.contiguous()
+        m, k = x.shape
+        n = weight.shape[0]
+        y = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
+        wf = weight.float().contiguous()
+        bf = bias.float().contiguous() if bias is not None else None
+        with torch.cuda.device(x.device):
+            _lib.call("p2r_smallk_linear_mixed", x.data_ptr(), wf.data_ptr(), _ptr(bf), m, n, k, y.data_ptr(), _stream())
+        ctx.save_for_backward(x)
+        ctx.targets, ctx.dims, ctx.has_bias = targets, (m, n, k), bias is not None
+        if want_stats:
+            sums = torch.empty(0, dtype=torch.float64, device=x.device)      # no fused statistics: the caller runs its pass
+            ctx.mark_non_differentiable(sums)
+            return y, sums
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, _dsums=None):
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("pose2room_b200: the float32-coordinate first layer has no input gradient")
+        (x,) = ctx.saved_tensors
+        m, n, k = ctx.dims
+        dz = dy if dy.is_contiguous() else dy.contiguous()
+        dz = dz if dz.dtype == torch.bfloat16 else dz.to(torch.bfloat16)
+
+        def weight_grads(need_w=True, need_b=ctx.has_bias):
+            gw = gb = None
+            if need_w:
+                gw = torch.zeros(n, k, dtype=torch.float32, device=x.device)
+                with torch.cuda.device(x.device):
+                    _lib.call("p2r_smallk_dw_mixed", dz.data_ptr(), x.data_ptr(), m, n, k, gw.data_ptr(), _stream())
+            if need_b:
+                gb = _col_sum(dz)
+            return [gw, gb]
+        if ctx.targets is not None:
+            tw, tb = ctx.targets
+            need_w = tw is not None and tw.requires_grad
+            need_b = tb is not None and tb.requires_grad
+            _defer(lambda: weight_grads(need_w, need_b), [tw if need_w else None, tb if need_b else None], (dz, x))
+            return None, None, None, None, None
+        gw, gb = weight_grads(ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2])
+        return None, gw, gb, None, None
+
+
+def smallk_mixed_ok(x, n, k):
+    return x.is_cuda and x.dtype == torch.float32 and k <= 4 and n % 8 == 0 and 2048 % n == 0 and 256 % (n // 8) == 0
+
+
+def linear_coords(x, weight, bias=None, want_stats=False):
+    """y bf16 [M, N] = x f32 [M, K <= 4] @ weight^T (+ bias): see _SmallKMixed.  Never deferred: the input carries no
+    gradient, so with a detached weight the node would drop out of the autograd graph (same rule as linear())."""
+    return _SmallKMixed.apply(x, weight, bias, None, want_stats)
 
 
 def linear(x, weight, bias=None, relu=False, sparsity=None, want_stats=False):
@@ -429,10 +553,11 @@ class _BatchNormAct(Function):
                           stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), _stream())
             else:
                 rstd = torch.rsqrt(running_var + eps)
+                g_ = gamma if gamma is not None else torch.ones_like(rstd)        # affine=False
                 stats[0] = running_mean
                 stats[1] = rstd
-                stats[2] = gamma * rstd
-                stats[3] = beta - running_mean * gamma * rstd
+                stats[2] = g_ * rstd
+                stats[3] = (beta if beta is not None else 0.0) - running_mean * g_ * rstd
             y = torch.empty_like(x)
             if residual is not None:
                 residual = residual if residual.is_contiguous() else residual.contiguous()
@@ -486,10 +611,17 @@ def batchnorm_act(x, bn, relu=False, residual=None, sums=None, colsum_period=0):
     sums: per-channel [copies, 2, C] float64 sum / sum of squares of x already produced by the GEMM that wrote x.
     colsum_period: the backward also leaves sum_rows dx per (row % period, channel) for the layer that produced x (the
     graph convolution's bias gradient: rows cycle through the joints) -- streaming kernels, multi-stream step only."""
+    c = x.shape[1]
+    if not (256 % c == 0 or c % 256 == 0):
+        raise RuntimeError("pose2room_b200.ops.batchnorm_act: %d channels -- the column-statistics kernels take widths that "
+                           "divide 256 or are multiples of 256 (every BatchNorm of the P2RNet path does)" % c)
     training = bn.training or not bn.track_running_stats
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
-    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if bn.momentum is None:      # nn.BatchNorm: cumulative moving average (a host read; no module of the path uses it)
+        momentum = 1.0 / float(bn.num_batches_tracked) if (training and bn.track_running_stats) else 0.0
+    else:
+        momentum = bn.momentum
     return _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training,
                                momentum, bn.eps, relu, sums, colsum_period)
 
@@ -587,6 +719,96 @@ class _MaxPoolRows(Function):
 def maxpool_rows(x):
     """x [R,S,C] -> max over S -> [R,C] (F.max_pool2d over nsample, pointnet2_modules.py:243-247)."""
     return _MaxPoolRows.apply(x)
+
+
+class _SAFused(Function):
+    """group -> Conv2d 1x1 + ReLU -> Conv2d 1x1 + ReLU -> max over nsample of the set-abstraction layer as one kernel
+    (csrc/sa_fused.cu; ref: pointnet2_modules.py:220-256).  Training keeps the first activation (written by the same
+    kernel) and the arg-max; the backward pass re-gathers the grouped rows instead of having kept them."""
+
+    @staticmethod
+    def forward(ctx, feats, idx, w1, b1, w2, b2, targets):
+        b, n, c = feats.shape
+        _, p, s = idx.shape
+        dev = feats.device
+        feats = feats if feats.is_contiguous() else feats.contiguous()
+        w1b, w2b = bf16_weight(w1).contiguous(), bf16_weight(w2).contiguous()
+        b1f = b1.float().contiguous() if b1 is not None else None
+        b2f = b2.float().contiguous() if b2 is not None else None
+        need_grad = targets is not None or any(ctx.needs_input_grad)   # (grad mode is always off inside forward)
+        out = torch.empty(b * p, c, dtype=torch.bfloat16, device=dev)
+        arg = torch.empty(b * p, c, dtype=torch.uint8, device=dev) if need_grad else None
+        h1 = torch.empty(b * p * s, c, dtype=torch.bfloat16, device=dev) if need_grad else None
+        with torch.cuda.device(dev), _Timed("sa_fused", b * p * s, c, c):
+            _lib.call("p2r_sa_fused", feats.data_ptr(), idx.data_ptr(), w1b.data_ptr(), _ptr(b1f), w2b.data_ptr(), _ptr(b2f),
+                      b, n, p, s, c, out.data_ptr(), 1, _ptr(arg), _ptr(h1), _stream())
+        ctx.save_for_backward(feats, idx, w1b, w2b, h1, arg, out)
+        ctx.targets = targets
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, idx, w1b, w2b, h1, arg, out = ctx.saved_tensors
+        b, n, c = feats.shape
+        _, p, s = idx.shape
+        dev = feats.device
+        tc = _TC_GEMM["fn"]
+        g = g if g.is_contiguous() else g.contiguous()
+        g = g if g.dtype == torch.bfloat16 else g.to(torch.bfloat16)
+        rows = b * p * s
+        with torch.cuda.device(dev):
+            gz = torch.empty_like(g)                    # ReLU of layer 2 at the pooled position: out > 0
+            _lib.call("p2r_relu_bwd", g.data_ptr(), out.data_ptr(), _DT[g.dtype], g.numel(), gz.data_ptr(), _stream())
+            dz2 = torch.empty(rows, c, dtype=torch.bfloat16, device=dev)
+            _lib.call("p2r_maxpool_rows_grad", gz.data_ptr(), _DT[gz.dtype], arg.data_ptr(), b * p, s, c, dz2.data_ptr(),
+                      _stream())
+            dh1 = tc.linear_dx(dz2, w2b)
+            dz1 = torch.empty_like(dh1)
+            _lib.call("p2r_relu_bwd", dh1.data_ptr(), h1.data_ptr(), _DT[dh1.dtype], dh1.numel(), dz1.data_ptr(), _stream())
+            dfeats = None
+            if ctx.needs_input_grad[0]:
+                dxg = tc.linear_dx(dz1, w1b)
+                d = torch.zeros(b, n, c, dtype=torch.float32, device=dev)
+                _lib.call("p2r_group_rows_grad", dxg.data_ptr(), _DT[dxg.dtype], idx.data_ptr(), b, n, c, p, s, d.data_ptr(),
+                          _stream())
+                dfeats = d.to(feats.dtype)
+        has_b1, has_b2 = ctx.has_bias
+
+        def weight_grads():
+            xg = torch.empty(rows, c, dtype=feats.dtype, device=dev)       # re-gather (33 MB) instead of having kept it
+            with torch.cuda.device(dev):
+                _lib.call("p2r_group_rows", feats.data_ptr(), _DT[feats.dtype], idx.data_ptr(), b, n, c, p, s, xg.data_ptr(),
+                          _stream())
+            return [tc.linear_dw(dz1, xg), _col_sum(dz1) if has_b1 else None,
+                    tc.linear_dw(dz2, h1), _col_sum(dz2) if has_b2 else None]
+
+        if ctx.targets is not None:
+            _defer(weight_grads, [t if (t is not None and t.requires_grad) else None for t in ctx.targets],
+                   (dz1, dz2, h1, feats))
+            return dfeats, None, None, None, None, None, None
+        gw1, gb1, gw2, gb2 = weight_grads()
+        return dfeats, None, gw1, gb1, gw2, gb2, None
+
+
+def sa_fused_available(feats, idx, convs):
+    """The one-kernel set-abstraction path: tensor-core (bf16) mode, two 256 -> 256 layers, nsample a power of two <= 128."""
+    tc = _TC_GEMM["fn"]
+    s = idx.shape[2]
+    return (tc is not None and feats.is_cuda and feats.dtype == torch.bfloat16 and len(convs) == 2 and feats.shape[2] == 256
+            and all(cv.in_channels == 256 and cv.out_channels == 256 for cv in convs) and 0 < s <= 128 and (s & (s - 1)) == 0
+            and os.environ.get("P2R_FUSED_SA", "1") != "0")
+
+
+def sa_fused(feats, idx, conv1, conv2):
+    """feats [B,N,256] bf16 rows, idx [B,P,S] int32, two nn.Conv2d(256, 256, 1) -> [B*P, 256] bf16 (see _SAFused)."""
+    w1, b1 = conv1.weight.reshape(conv1.out_channels, conv1.in_channels), conv1.bias
+    w2, b2 = conv2.weight.reshape(conv2.out_channels, conv2.in_channels), conv2.bias
+    idx = idx.contiguous()
+    if DEFER["on"] and not PROFILE["on"] and torch.is_grad_enabled() and feats.requires_grad:
+        det = lambda t: t.detach() if t is not None else None
+        return _SAFused.apply(feats, idx, det(w1), det(b1), det(w2), det(b2), (w1, b1, w2, b2))
+    return _SAFused.apply(feats, idx, w1, b1, w2, b2, None)
 
 
 class _EmbedSum(Function):

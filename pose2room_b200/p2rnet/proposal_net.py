@@ -133,9 +133,13 @@ class ProposalNet(nn.Module):
         idx = pointnet2_utils.ball_query(sa.radius, sa.nsample, xyz, new_xyz)          # (B,P,S) i32
         assert not sa.use_xyz and sa.pooling == "max"
         act = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        grouped = ops.group_rows(feats_rows.to(act), idx)                              # (B,P,S,C)
-        h = grouped.reshape(b * sa.npoint * sa.nsample, c)
         convs = [m for m in sa.mlp_module if isinstance(m, nn.Conv2d)]
+        rows = feats_rows.to(act)
+        if ops.sa_fused_available(rows, idx, convs):      # gather -> MLP -> max as ONE tcgen05 kernel (csrc/sa_fused.cu)
+            pooled = ops.sa_fused(rows, idx, convs[0], convs[1])
+            return new_xyz, pooled.float().reshape(b, sa.npoint, -1), inds
+        grouped = ops.group_rows(rows, idx)                                            # (B,P,S,C)
+        h = grouped.reshape(b * sa.npoint * sa.nsample, c)
         for conv in convs:                                                             # Conv2d 1x1 + bias + ReLU
             h = ops.linear(h, conv.weight.reshape(conv.out_channels, conv.in_channels), conv.bias, relu=True)
         pooled = ops.maxpool_rows(h.reshape(b * sa.npoint, sa.nsample, h.shape[1]))    # (B*P, C')

@@ -175,8 +175,9 @@ class STGCN(nn.Module):
         if self._permuted:
             x0 = x0.index_select(2, self._perm_idx)                          # internal joint order (see __init__)
         rel = hip[:, self._window_idx(t, hip.device)] - hip[:, :, None]      # (B,T,20,3): stgcn.py:109-117
-        pos = run_rows(self.pos_embed, rel.reshape(b * t * self.knn, 3).to(act))   # (B*T*20, 64)
-        sk = run_rows(self.sk_feat, x0.reshape(b * t * j, 3).to(act))              # (B*T*J, 64)
+        # (coordinates enter the first layer as float32 in both modes: bf16 would move a 1 m position by millimetres)
+        pos = run_rows(self.pos_embed, rel.reshape(b * t * self.knn, 3), act)      # (B*T*20, 64)
+        sk = run_rows(self.sk_feat, x0.reshape(b * t * j, 3), act)                 # (B*T*J, 64)
         # x = sk + mean_k(pos) broadcast over the joints of the frame (stgcn.py:121,129), one fused kernel
         x = ops.embed_sum(sk.reshape(b * t, j, 64), pos.reshape(b * t, self.knn, 64)).reshape(b, t, j, 64)
 

@@ -2,6 +2,7 @@
 (/root/reference/models/p2rnet/modules/sub_modules.py:88-113; submodules 'conv', 'batchnorm', 'ReLU' in the
 order given by `order`, conv bias only when no norm layer is present), executed on channel-last rows by the
 B200 kernels.  Only the orders the hot path uses are built: 'cbr' and 'c' with kernel_size 1."""
+import torch
 import torch.nn as nn
 
 from .. import ops
@@ -21,9 +22,17 @@ class SingleConv(nn.Sequential):
         if "r" in order:
             self.add_module("ReLU", nn.ReLU(inplace=True))
 
-    def forward_rows(self, x):
-        """x [M, Cin] channel-last rows -> [M, Cout]."""
+    def forward_rows(self, x, act=None):
+        """x [M, Cin] channel-last rows -> [M, Cout].  act: activation dtype of the layer's output when it differs from
+        x's (throughput mode feeds float32 point coordinates into the first layer of an MLP and gets bf16 out)."""
         w = self.conv.weight.reshape(self.conv.out_channels, self.conv.in_channels)
+        if act is not None and act != x.dtype:
+            if act == torch.bfloat16 and ops.smallk_mixed_ok(x, self.conv.out_channels, self.conv.in_channels):
+                y, sums = ops.linear_coords(x, w, self.conv.bias, want_stats=True)
+                if "b" in self.order:
+                    return ops.batchnorm_act(y, self.batchnorm, relu="r" in self.order, sums=sums)
+                return y
+            x = x.to(act)
         if "b" in self.order and self.conv.out_channels == 64 and self.batchnorm.training:
             # 64-channel layers (pos_embed / sk_feat over all T*J points): the BatchNorm statistics come out of the GEMM
             # epilogue (an empty tensor when the kernel in use has no fused statistics: batchnorm_act then runs its pass)
@@ -35,7 +44,8 @@ class SingleConv(nn.Sequential):
         return y
 
 
-def run_rows(seq, x):
-    for m in seq:
-        x = m.forward_rows(x)
+def run_rows(seq, x, act=None):
+    """act: activation dtype of the stack (see SingleConv.forward_rows); None = x's own."""
+    for i, m in enumerate(seq):
+        x = m.forward_rows(x, act) if (i == 0 and act is not None) else m.forward_rows(x)
     return x

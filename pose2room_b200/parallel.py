@@ -17,6 +17,10 @@ def allreduce_gradients(params):
     """Average the gradients of `params` over all ranks with ONE flat all-reduce (the whole model is 1.44 M parameters
     = 5.8 MB: a single bucket; message-latency bound on NVLink).  Parameters without a gradient are skipped
     consistently on every rank (same model, same graph)."""
+    from . import ops
+    if ops.deferred_gradients_pending():
+        raise RuntimeError("allreduce_gradients inside ops.overlap_weight_grads(): the weight gradients of this step are "
+                           "still deferred (parameters get their .grad when the context exits); call it after the block")
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]

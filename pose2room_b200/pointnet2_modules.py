@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import pointnet2_utils
+from . import ops, pointnet2_utils
 
 
 def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
@@ -25,6 +25,48 @@ def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
             layers.append(nn.BatchNorm2d(mlp_spec[i]))
         layers.append(nn.ReLU(True))
     return nn.Sequential(*layers)
+
+
+def _bn_rows_supported(c):
+    return 256 % c == 0 or c % 256 == 0           # channel counts the column-statistics kernels take (csrc/dense_ops.cu)
+
+
+def run_shared_mlp(mlp_module, x, pool_max=False):
+    """A build_shared_mlp stack applied to x (B, C, P, S) on this library's kernels: every 1x1 Conv2d is a row-major GEMM
+    (ops.linear: tcgen05 for bf16 rows, the fixed-order SIMT kernel for fp32), BatchNorm2d a column statistic
+    (ops.batchnorm_act), ReLU fused into whichever comes last; pool_max also takes the max over S (ops.maxpool_rows).
+    Returns (B, C', P, S), or (B, C', P, 1) with pool_max.  Falls back to the nn modules (cuDNN) only for inputs that are
+    not on a GPU-supported shape (BatchNorm widths the statistics kernels do not take)."""
+    mods = list(mlp_module)
+    convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+    ok = x.is_cuda and x.dtype == torch.float32 and all(
+        isinstance(m, (nn.Conv2d, nn.BatchNorm2d, nn.ReLU)) for m in mods) and all(
+        m.kernel_size == (1, 1) for m in convs) and all(
+        _bn_rows_supported(m.num_features) for m in mods if isinstance(m, nn.BatchNorm2d))
+    if not ok:
+        y = mlp_module(x)
+        return F.max_pool2d(y, kernel_size=[1, y.size(3)]) if pool_max else y
+    b, c, p, s = x.shape
+    rows = x.permute(0, 2, 3, 1).reshape(b * p * s, c)
+    i = 0
+    while i < len(mods):
+        conv = mods[i]
+        i += 1
+        bn = relu = None
+        if i < len(mods) and isinstance(mods[i], nn.BatchNorm2d):
+            bn = mods[i]
+            i += 1
+        if i < len(mods) and isinstance(mods[i], nn.ReLU):
+            relu = True
+            i += 1
+        w = conv.weight.reshape(conv.out_channels, conv.in_channels)
+        if bn is None:
+            rows = ops.linear(rows, w, conv.bias, relu=bool(relu))
+        else:
+            rows = ops.batchnorm_act(ops.linear(rows, w, conv.bias), bn, relu=bool(relu))
+    if pool_max:
+        return ops.maxpool_rows(rows.reshape(b * p, s, rows.shape[1])).reshape(b, p, 1, -1).permute(0, 3, 1, 2)
+    return rows.reshape(b, p, s, -1).permute(0, 3, 1, 2)
 
 
 class PointnetSAModuleVotes(nn.Module):
@@ -67,9 +109,12 @@ class PointnetSAModuleVotes(nn.Module):
             grouped_features, grouped_xyz, unique_cnt = self.grouper(xyz, new_xyz, features)
         else:
             grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
-        new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
+        if self.pooling == "max":    # shared MLP + max over nsample on this library's GEMM / pooling kernels
+            new_features = run_shared_mlp(self.mlp_module, grouped_features, pool_max=True)
+        else:
+            new_features = run_shared_mlp(self.mlp_module, grouped_features)  # (B, mlp[-1], npoint, nsample)
         if self.pooling == "max":
-            new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+            pass
         elif self.pooling == "avg":
             new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
         elif self.pooling == "rbf":
@@ -97,4 +142,4 @@ class PointnetFPModule(nn.Module):
         else:
             interpolated = known_feats.expand(*(list(known_feats.size()[0:2]) + [unknown.size(1)]))
         new_features = torch.cat([interpolated, unknow_feats], dim=1) if unknow_feats is not None else interpolated
-        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+        return run_shared_mlp(self.mlp, new_features.unsqueeze(-1)).squeeze(-1)

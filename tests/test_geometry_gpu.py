@@ -58,7 +58,8 @@ def test_nn_distance_live_shapes_and_grad(cuda):
     from pose2room_b200 import geometry
     gen = torch.Generator().manual_seed(0)
     # the three live call sites of models/loss.py:64,105,128 at BASELINE shapes
-    for (B, N, M) in [(32, 128, 10), (32 * 512, 3, 25), (1, 128, 7)]:
+    # (+ a per-GPU batch of 160: B * num_seeds = 81 920 clouds, beyond the 65 535 limit of grid.y the batch used to ride on)
+    for (B, N, M) in [(32, 128, 10), (32 * 512, 3, 25), (1, 128, 7), (160 * 512, 3, 25)]:
         a = torch.randn(B, N, 3, generator=gen)
         b = torch.randn(B, M, 3, generator=gen)
         want = G.nn_distance(a.numpy(), b.numpy())

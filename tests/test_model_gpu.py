@@ -198,6 +198,39 @@ def test_overlapped_weight_gradients_match_plain_backward(cuda, golden):
         gemm_sm100.uninstall()
 
 
+def test_weight_shadows_change_nothing(cuda, golden):
+    """ops.register_weight_shadows (one multi-tensor fp32 -> bf16 copy per step instead of a cast per layer): same loss and
+    the same gradients, bit for bit, as converting layer by layer -- also after the weights have moved."""
+    from pose2room_b200 import gemm_sm100, ops, synthetic
+    gemm_sm100.install()
+    try:
+        out = []
+        for use_shadows in (False, True):
+            net = H.make_product("small", "train", golden, precision="bf16").to(cuda).train()
+            if use_shadows:
+                ops.register_weight_shadows(net)
+            opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=1e-2)
+            data = H.make_data("small", cuda)
+            rec = []
+            for _ in range(2):
+                opt.zero_grad(set_to_none=True)
+                with ops.overlap_weight_grads():
+                    loss = net.loss(net(data), data)["total"]
+                    loss.backward()
+                rec.append((loss.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}))
+                opt.step()
+            out.append(rec)
+            ops.clear_weight_shadows()
+        for (la, ga), (lb, gb) in zip(*out):
+            assert torch.equal(la, lb)
+            assert set(ga) == set(gb)
+            for k in ga:
+                assert torch.equal(ga[k], gb[k]), k
+    finally:
+        ops.clear_weight_shadows()
+        gemm_sm100.uninstall()
+
+
 def _fused_vs_chain_on_random_predictions(dev):
     """Fused loss kernel vs the chain of torch kernels on predictions that hit every branch (near / far / in-between
     proposals, both sides of the huber knee, masked seeds): ten numbers and the six input gradients."""

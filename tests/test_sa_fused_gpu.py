@@ -1,0 +1,128 @@
+"""GPU: the one-kernel set-abstraction path (csrc/sa_fused.cu: gather rows by ball-query index -> two 256 x 256 tcgen05
+GEMMs with the intermediate in shared memory / TMEM -> max over nsample in the epilogue) against
+
+  * an fp64 torch reference of the reference's formulation (grouping_operation -> Conv2d 1x1 + ReLU -> Conv2d 1x1 + ReLU ->
+    max_pool2d; pointnet2_modules.py:220-256) on the same bf16-rounded inputs and weights, forward and every gradient;
+  * the four-launch path it replaces (group_rows -> linear -> linear -> maxpool_rows), same kernels' arithmetic: outputs
+    equal to bf16 rounding, identical arg-max decisions wherever the maximum is not a near-tie.
+Shapes: the live ProposalNet layer (512 votes -> 128 proposals x 16 samples), a ragged last tile, nsample 8 / 32 / 128."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(cuda, B, N, P, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, N, 256, generator=g)
+    feats = (feats / feats.norm(dim=2, keepdim=True)).to(cuda)
+    idx = torch.randint(0, N, (B, P, S), generator=g, dtype=torch.int32).to(cuda)
+    idx[:, :, S // 2:] = idx[:, :, :1]            # ball query pads with the first hit: exact ties inside a group
+    conv1, conv2 = nn.Conv2d(256, 256, 1).to(cuda), nn.Conv2d(256, 256, 1).to(cuda)
+    with torch.no_grad():
+        for cv in (conv1, conv2):
+            cv.weight.copy_(cv.weight.bfloat16().float())         # bf16-representable weights: every path sees the same values
+            cv.bias.normal_(0, 0.05, generator=None)
+    return feats, idx, conv1, conv2
+
+
+def _reference(feats16, idx, conv1, conv2, go):
+    """fp64, the reference's layout: (B, C, P, S) grouped tensor -> 1x1 convs -> max over S."""
+    B, N, C = feats16.shape
+    _, P, S = idx.shape
+    x = feats16.double().detach().requires_grad_(True)
+    ws = [t.detach().double().requires_grad_(True) for t in (conv1.weight, conv1.bias, conv2.weight, conv2.bias)]
+    grouped = torch.gather(x[:, None].expand(B, P, N, C), 2, idx.long()[..., None].expand(B, P, S, C))    # (B,P,S,C)
+    g = grouped.permute(0, 3, 1, 2)                                                                     # (B,C,P,S)
+    h = F.relu(F.conv2d(g, ws[0], ws[1]))
+    h = h + (h.bfloat16().double() - h).detach()         # the kernel rounds the first activation to bf16 (straight-through)
+    h = F.relu(F.conv2d(h, ws[2], ws[3]))
+    out = F.max_pool2d(h, kernel_size=[1, S]).squeeze(-1).permute(0, 2, 1).reshape(B * P, C)
+    grads = torch.autograd.grad(out, [x] + ws, go.double())
+    return out.detach(), grads
+
+
+@pytest.mark.parametrize("B,N,P,S", [(4, 512, 128, 16), (1, 64, 5, 16), (2, 100, 24, 8), (2, 300, 12, 32), (3, 200, 3, 128)])
+def test_sa_fused_vs_reference_formulation_and_unfused_path(cuda, B, N, P, S):
+    from pose2room_b200 import gemm_sm100, ops
+    gemm_sm100.install()
+    try:
+        feats, idx, conv1, conv2 = _case(cuda, B, N, P, S, seed=B * 1000 + S)
+        rows16 = feats.bfloat16()
+        go = torch.randn(B * P, 256, device=cuda).bfloat16()
+        assert ops.sa_fused_available(rows16, idx, [conv1, conv2])
+        # fused
+        x = rows16.detach().clone().requires_grad_(True)
+        out = ops.sa_fused(x, idx, conv1, conv2)
+        assert out.dtype == torch.bfloat16 and out.shape == (B * P, 256)
+        gf = torch.autograd.grad(out, [x, conv1.weight, conv1.bias, conv2.weight, conv2.bias], go)
+        # the path it replaces
+        x2 = rows16.detach().clone().requires_grad_(True)
+        h = ops.group_rows(x2, idx).reshape(B * P * S, 256)
+        for cv in (conv1, conv2):
+            h = ops.linear(h, cv.weight.reshape(256, 256), cv.bias, relu=True)
+        out2 = ops.maxpool_rows(h.reshape(B * P, S, 256))
+        gu = torch.autograd.grad(out2, [x2, conv1.weight, conv1.bias, conv2.weight, conv2.bias], go)
+        # fp64 reference of the reference's formulation
+        ref, gr = _reference(rows16, idx, conv1, conv2, go.float())
+        scale = float(ref.abs().max())
+        assert float((out.double() - ref).abs().max()) <= 1e-2 * scale, "forward vs fp64 reference"
+        assert float((out.double() - out2.double()).abs().max()) <= 8e-3 * scale, "forward vs unfused kernels"
+        assert float((out.double() - out2.double()).abs().mean()) <= 2e-4 * scale
+        for name, a, u, r in zip(("dfeats", "dW1", "db1", "dW2", "db2"), gf, gu, gr):
+            s = float(r.abs().max()) + 1e-12
+            r = r.reshape(a.shape)
+            # relative L2 against fp64 (isolated arg-max / ReLU flips at near-ties move single entries, not the norm)
+            assert float((a.double() - r).norm() / r.norm()) <= 3e-2, (name, "vs fp64")
+            assert float((a.double() - u.double()).norm() / (u.double().norm() + 1e-12)) <= 3e-2, (name, "vs unfused")
+            assert float((a.double() - r).abs().max()) <= 0.25 * s, name
+    finally:
+        gemm_sm100.uninstall()
+
+
+def test_sa_fused_eval_mode_writes_nothing_extra_and_is_deterministic(cuda):
+    from pose2room_b200 import gemm_sm100, ops
+    gemm_sm100.install()
+    try:
+        feats, idx, conv1, conv2 = _case(cuda, 32, 512, 128, 16, seed=7)
+        rows16 = feats.bfloat16()
+        with torch.no_grad():
+            a = ops.sa_fused(rows16, idx, conv1, conv2)
+            b = ops.sa_fused(rows16, idx, conv1, conv2)
+        assert torch.equal(a, b) and torch.isfinite(a.float()).all() and float(a.float().min()) >= 0.0
+        x = rows16.detach().clone().requires_grad_(True)
+        c = ops.sa_fused(x, idx, conv1, conv2)             # training variant (also stores the first activation)
+        assert torch.equal(a, c)
+    finally:
+        gemm_sm100.uninstall()
+
+
+def test_proposal_net_takes_the_fused_path_in_bf16_mode(cuda):
+    """ProposalNet._aggregate (the live caller) with and without the fused kernel: same proposals, same pooled features to
+    bf16 rounding; the fp32 parity mode keeps the SIMT path."""
+    import os
+    from pose2room_b200 import _lib, gemm_sm100, synthetic
+    from pose2room_b200.config import P2RConfig
+    from pose2room_b200.p2rnet.proposal_net import ProposalNet
+    gemm_sm100.install()
+    try:
+        torch.manual_seed(0)
+        det = ProposalNet(P2RConfig(mode="train", joint_num=25, precision="bf16")).to(cuda)
+        xyz = torch.from_numpy(synthetic.make_cloud(4, 512, seed=2)).to(cuda)
+        feats = torch.randn(4, 512, 256, device=cuda)
+        feats = feats / feats.norm(dim=2, keepdim=True)
+        res = {}
+        for flag in ("1", "0"):
+            os.environ["P2R_FUSED_SA"] = flag
+            n0 = _lib.LAUNCHES["count"]
+            with torch.no_grad():
+                res[flag] = det._aggregate(xyz, feats) + (_lib.LAUNCHES["count"] - n0,)
+        os.environ.pop("P2R_FUSED_SA")
+        assert torch.equal(res["1"][2], res["0"][2]) and torch.equal(res["1"][0], res["0"][0])
+        assert res["0"][3] - res["1"][3] == 3                                   # 4 launches became 1
+        scale = float(res["0"][1].abs().max())
+        assert float((res["1"][1] - res["0"][1]).abs().max()) <= 8e-3 * scale
+    finally:
+        gemm_sm100.uninstall()
