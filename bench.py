@@ -213,6 +213,14 @@ def start_watchdog():
             if time.time() - _HEARTBEAT["t"] > _HEARTBEAT.get("limit", limit):
                 sys.stderr.write("bench.py: no progress for %.0f s in phase '%s' -- aborting\n" % (limit, _HEARTBEAT["phase"]))
                 sys.stderr.flush()
+                if os.environ.get("P2R_BENCH_GDB"):      # diagnostic: which kernels are resident on the GPU right now
+                    try:
+                        r = subprocess.run(["cuda-gdb", "-p", str(os.getpid()), "-batch", "-ex", "info cuda kernels"],
+                                           capture_output=True, text=True, timeout=90)
+                        sys.stderr.write("cuda-gdb:\n" + r.stdout[-6000:] + r.stderr[-1500:] + "\n")
+                    except Exception as e:
+                        sys.stderr.write("cuda-gdb attach failed: %r\n" % (e,))
+                    sys.stderr.flush()
                 os._exit(17)
     threading.Thread(target=run, daemon=True).start()
 

@@ -509,6 +509,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                   int relu, int tiles_n, int num_tiles, const GemmExtra ex) {
   using S = PairSmem<BN>;
   const bool dbg_nostore = (relu & 256) != 0, dbg_nomma = (relu & 512) != 0, dbg_nobias = (relu & 1024) != 0;
+  // accumulate: C += A.B^T instead of C = A.B^T -- the epilogue's bulk-tensor stores become bulk-tensor REDUCE-ADD stores
+  // (the bf16 addition happens in L2; same rounding as a separate elementwise add of two bf16 tensors).  The backward
+  // pass uses it to add the graph convolution's input gradient onto the residual branch's gradient in place.
+  const bool accumulate = (relu & 2) != 0;
   relu &= 1;
   if (dbg_nobias) bias = nullptr;
   extern __shared__ uint8_t smem_raw[];
@@ -678,7 +682,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
         p2r_fence_proxy_async();      // generic-proxy writes of the staging tile -> visible to the bulk-copy engine
         __syncwarp();
-        if (lane == 0 && !dbg_nostore) tma_store_2d(&tma_c, stg, n0 + g0, row0);   // rows >= M / columns >= N are clipped
+        if (lane == 0 && !dbg_nostore) {                                             // rows >= M / columns >= N are clipped
+          if (accumulate) tma_reduce_add_2d(&tma_c, stg, n0 + g0, row0);
+          else tma_store_2d(&tma_c, stg, n0 + g0, row0);
+        }
         if (STATS) {
           // column sums straight from the staged bf16 tile: lane l owns columns 2l, 2l+1 of this 64-column group
           // (= channels 2l, 2l+1: n0 + g0 is a multiple of 64); one conflict-free 4-byte read per row

@@ -64,35 +64,58 @@ gmm_mix_fwd_kernel(const LogitT* __restrict__ logits, const MuT* __restrict__ mu
   }
 }
 
+#define P2RG_ROW_GROUPS 4
 template <typename MuT, typename LogitT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gmm_mix_bwd_kernel(const LogitT* __restrict__ logits, const MuT* __restrict__ mu, const float* __restrict__ log_sigma,
                    const MuT* __restrict__ eps, const MuT* __restrict__ dout, long long rows, int G, int D,
                    int rows_per_block, LogitT* __restrict__ dlogits, double* __restrict__ partials,
                    unsigned int* __restrict__ counter, MuT* __restrict__ dmu, float* __restrict__ dls) {
-  P2R_DYN_SMEM(double, s_par);                          // mu[G*D] | sigma[G*D] | dout[rows_per_block*D]
+  // Round 2: P2RG_ROW_GROUPS x as many threads per block (thread = (component g, row group q); a row group walks
+  // rows_per_block / P2RG_ROW_GROUPS rows), the groups' partial sums combined through shared memory in a fixed order --
+  // the one-thread-per-component version walked 32 rows per thread with 128 mostly idle blocks: ~200 us inside a step.
+  P2R_DYN_SMEM(double, s_par);                // mu[G*D] | sigma[G*D] | dout[rows_per_block*D] | acc[ROW_GROUPS][G][2*D]
   double* s_mu = s_par;
   double* s_sig = s_par + G * D;
   double* s_dout = s_sig + G * D;
+  double* s_acc = s_dout + rows_per_block * D;
   __shared__ bool s_last;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const int nr = (int)((rows - r0) < rows_per_block ? (rows - r0) : rows_per_block);
   for (int i = threadIdx.x; i < nr * D; i += blockDim.x) s_dout[i] = (double)dout[r0 * D + i];
   p2rg_stage_params(mu, log_sigma, G * D, s_mu, s_sig);       // ends with __syncthreads
-  const int g = threadIdx.x;
+  const int gpad = blockDim.x / P2RG_ROW_GROUPS;
+  const int g = threadIdx.x % gpad, q = threadIdx.x / gpad;
+  const int per_q = rows_per_block / P2RG_ROW_GROUPS;
   if (g < G) {
     double am[P2RG_MAX_D] = {0.0, 0.0, 0.0, 0.0}, al[P2RG_MAX_D] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = 0; i < nr; ++i) {
+    const int i1 = (q + 1) * per_q < nr ? (q + 1) * per_q : nr;
+#pragma unroll 4
+    for (int i = q * per_q; i < i1; ++i) {
       const long long r = r0 + i;
       const double pi = p2rg_sigmoid(p2rg_load_logit(logits + r * G + g));
       double e[P2RG_MAX_D];
       for (int c = 0; c < D; ++c) e[c] = (double)eps[(r * G + g) * D + c];
       p2rg_store_logit(dlogits + r * G + g, p2rg_backward(pi, s_mu + g * D, s_sig + g * D, e, s_dout + i * D, D, am, al));
     }
+    double* pa = s_acc + ((size_t)q * G + g) * 2 * D;
+    for (int c = 0; c < D; ++c) {
+      pa[c] = am[c];
+      pa[D + c] = al[c];
+    }
+  }
+  __syncthreads();
+  if (q == 0 && g < G) {
     double* pm = partials + (size_t)blockIdx.x * 2 * G * D;
     for (int c = 0; c < D; ++c) {
-      pm[g * D + c] = am[c];
-      pm[G * D + g * D + c] = al[c];
+      double tm = 0.0, tl = 0.0;
+#pragma unroll
+      for (int qq = 0; qq < P2RG_ROW_GROUPS; ++qq) {           // fixed order: deterministic
+        tm += s_acc[((size_t)qq * G + g) * 2 * D + c];
+        tl += s_acc[((size_t)qq * G + g) * 2 * D + D + c];
+      }
+      pm[g * D + c] = tm;
+      pm[G * D + g * D + c] = tl;
     }
     __threadfence();
   }
@@ -101,11 +124,20 @@ gmm_mix_bwd_kernel(const LogitT* __restrict__ logits, const MuT* __restrict__ mu
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // deterministic tail: eight independent partial sums per output (eight L2 loads in flight instead of a chain of
+  // gridDim.x dependent ones: this loop was ~80 of the kernel's 100 us), combined in a fixed order
+  const size_t pstride = (size_t)2 * G * D;
   for (int i = threadIdx.x; i < 2 * G * D; i += blockDim.x) {
-    double t = 0.0;
-    for (unsigned blk = 0; blk < gridDim.x; ++blk) t += __ldcg(partials + (size_t)blk * 2 * G * D + i);
-    if (i < G * D) dmu[i] = (MuT)t;
-    else dls[i - G * D] = (float)t;
+    double t[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    unsigned blk = 0;
+    for (; blk + 8 <= gridDim.x; blk += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] += __ldcg(partials + (size_t)(blk + u) * pstride + i);
+    }
+    for (; blk < gridDim.x; ++blk) t[0] += __ldcg(partials + (size_t)blk * pstride + i);
+    const double tot = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+    if (i < G * D) dmu[i] = (MuT)tot;
+    else dls[i - G * D] = (float)tot;
   }
 }
 
@@ -151,14 +183,15 @@ extern "C" int p2r_gmm_mix_grad(const void* logits, int logits_bf16, const void*
   P2R_CHECK_ARG(rows > 0, "p2r_gmm_mix_grad");
   P2R_CHECK_ARG(workspace_doubles >= p2r_gmm_mix_workspace(rows, g, d), "p2r_gmm_mix_grad (workspace too small)");
   const int grid = p2r_ceil_div(rows, P2RG_ROWS_PER_BLOCK);
-  const int threads = (g + 31) / 32 * 32;
-  const size_t smem = (size_t)(2 * g * d + P2RG_ROWS_PER_BLOCK * d) * sizeof(double);
+  const int threads = P2RG_ROW_GROUPS * ((g + 31) / 32 * 32);        // <= 4 * 256 = 1024
+  const size_t smem = (size_t)(2 * g * d + P2RG_ROWS_PER_BLOCK * d + P2RG_ROW_GROUPS * g * 2 * d) * sizeof(double);
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);     // first 8 bytes; zero on entry
   double* partials = workspace + 1;
   cudaStream_t st = (cudaStream_t)stream;
 #define P2RG_BWD(MuT, LogitT)                                                                                       \
   do {                                                                                                              \
     auto kern = gmm_mix_bwd_kernel<MuT, LogitT>;                                                                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
     P2R_LAUNCH(kern, grid, threads, smem, st, (const LogitT*)logits, (const MuT*)mu, log_sigma, (const MuT*)eps,    \
                (const MuT*)dout, rows, g, d, P2RG_ROWS_PER_BLOCK, (LogitT*)dlogits, partials, counter, (MuT*)dmu,   \
                dls);                                                                                                \

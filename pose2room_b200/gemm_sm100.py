@@ -133,13 +133,19 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bf
     return c
 
 
-def gemm_pair(a, b, bias=None, relu=False, block_n=256, kb_list=None, stats=None, _debug_flags=0):
-    """C[M,N] bf16 = a[M,K] @ b[N,K]^T on CTA pairs (p2r_gemm_bf16_pair): K-major bf16 operands, 256 x block_n tiles."""
+def gemm_pair(a, b, bias=None, relu=False, block_n=256, kb_list=None, stats=None, _debug_flags=0, accumulate_into=None):
+    """C[M,N] bf16 = a[M,K] @ b[N,K]^T on CTA pairs (p2r_gemm_bf16_pair): K-major bf16 operands, 256 x block_n tiles.
+    accumulate_into: a contiguous bf16 [M,N] tensor the product is ADDED to in place (reduce-add stores) and returned."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
     assert a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]
     m, k = a.shape
     n = b.shape[0]
-    c = torch.empty(m, n, dtype=torch.bfloat16, device=a.device)
+    if accumulate_into is not None:
+        c = accumulate_into
+        assert c.dtype == torch.bfloat16 and c.is_contiguous() and tuple(c.shape) == (m, n) and bias is None and not relu
+        _debug_flags |= 2
+    else:
+        c = torch.empty(m, n, dtype=torch.bfloat16, device=a.device)
     if bias is not None:
         bias = bias.float().contiguous()
     if kb_list is not None:
@@ -328,12 +334,15 @@ class _Backend:
         return gemm(dz, w, False, True, out_dtype=torch.bfloat16)
 
     @staticmethod
-    def linear_dx_pretransposed(dz, w_t, sparsity=None):
-        """dx = dz . W with W^T [K, N] already materialised in bf16 (the graph-conv weight builder writes both)."""
+    def linear_dx_pretransposed(dz, w_t, sparsity=None, accumulate_into=None):
+        """dx = dz . W with W^T [K, N] already materialised in bf16 (the graph-conv weight builder writes both).
+        accumulate_into: add dx onto this tensor in place (CTA-pair kernel only) and return it."""
         sp = sparsity if USE_SPARSITY else None
         if USE_PAIR and dz.shape[0] >= 4096 and w_t.shape[0] >= 512:
             kbl = sp.kb_list(PAIR_BLOCK_N, True, dz.device) if sp is not None else None
-            return gemm_pair(dz, w_t, block_n=PAIR_BLOCK_N, kb_list=kbl)
+            return gemm_pair(dz, w_t, block_n=PAIR_BLOCK_N, kb_list=kbl, accumulate_into=accumulate_into)
+        if accumulate_into is not None:
+            return accumulate_into.add_(_Backend.linear_dx_pretransposed(dz, w_t, sparsity))
         bn = GCN_BLOCK_N if (w_t.shape[0] % 160 == 0 or GCN_BLOCK_N != 160) else 128
         kbl = sp.kb_list(bn, True, dz.device) if sp is not None else None
         return gemm(dz, w_t, False, False, out_dtype=torch.bfloat16, block_n=bn, kb_list=kbl)

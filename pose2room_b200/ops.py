@@ -450,7 +450,7 @@ class _GraphConv(Function):
     one kernel.  ref: ConvTemporalGraphical.forward, stgcn_layers.py:58-67."""
 
     @staticmethod
-    def forward(ctx, x, conv_w, conv_b, a_eff, targets, sparsity, want_stats):
+    def forward(ctx, x, conv_w, conv_b, a_eff, targets, sparsity, want_stats, with_alias=False):
         tc = _TC_GEMM["fn"]
         k, v = a_eff.shape[0], a_eff.shape[1]
         co, ci = conv_w.shape[0] // k, conv_w.shape[1]
@@ -473,10 +473,15 @@ class _GraphConv(Function):
         if sums is None:
             sums = torch.empty(0, dtype=torch.float64, device=dev)
         ctx.mark_non_differentiable(sums)
+        if with_alias:
+            # third output: x itself (autograd hands it out as an alias) for the block's residual branch.  Its gradient
+            # then arrives HERE, next to dy, and the input-gradient GEMM adds its product onto it in place (reduce-add
+            # stores) -- instead of autograd summing the two 105 MB gradients of x with a separate elementwise kernel.
+            return y, sums, x
         return y, sums
 
     @staticmethod
-    def backward(ctx, dy, _dsums=None):
+    def backward(ctx, dy, _dsums=None, d_alias=None):
         x, cw, cb, ae, w_eff_t = ctx.saved_tensors
         k, v, co, ci = ctx.dims
         sp = ctx.sparsity
@@ -487,8 +492,16 @@ class _GraphConv(Function):
             fused_cs = None
         dx = None
         if ctx.needs_input_grad[0]:
+            acc = None
+            if d_alias is not None:
+                if d_alias.dtype == torch.bfloat16 and d_alias.is_contiguous() and d_alias.shape == x.shape:
+                    acc = d_alias          # fresh tensor written by the BatchNorm backward of the block: ours to add onto
             with _Timed("dx", dy.shape[0], v * co, v * ci):
-                dx = tc.linear_dx_pretransposed(dy, w_eff_t, sp)
+                dx = tc.linear_dx_pretransposed(dy, w_eff_t, sp, accumulate_into=acc)
+            if d_alias is not None and acc is None:
+                dx = dx + d_alias.to(dx.dtype)
+        elif d_alias is not None:
+            dx = d_alias
 
         def weight_grads():
             with _Timed("gcn_dw", dy.shape[0], v * co, v * ci):
@@ -507,19 +520,29 @@ class _GraphConv(Function):
         if ctx.targets is not None:
             _defer(weight_grads, [t if (t is not None and t.requires_grad) else None for t in ctx.targets], (dy, x),
                    inline=getattr(tc, "DW_INLINE", False))
-            return dx, None, None, None, None, None, None
+            return dx, None, None, None, None, None, None, None
         gw, gb, ga = weight_grads()
-        return dx, gw, gb, ga, None, None, None
+        return dx, gw, gb, ga, None, None, None, None
 
 
-def graph_conv(x, conv_weight, conv_bias, a_eff, sparsity=None, want_stats=True):
+_FUSED_RESADD = os.environ.get("P2R_FUSED_RESADD", "1") != "0"
+
+
+def graph_conv(x, conv_weight, conv_bias, a_eff, sparsity=None, want_stats=True, residual_alias=False):
     """x [M, V*Ci] frames (channel-last joints) -> (y [M, V*Co], sums): the st_gcn graph convolution with conv weight
     (K*Co, Ci, 1, 1), conv bias (K*Co,), A_eff (K, V, V).  Tensor-core (bf16) path only -- callers check
-    `graph_conv_available(x)` and use the generic linear() otherwise."""
+    `graph_conv_available(x)` and use the generic linear() otherwise.
+    residual_alias: also return x (as an autograd alias) for the block's residual branch -> (y, sums, x_alias); the
+    gradient of the alias is then folded into the input-gradient GEMM (see _GraphConv.forward)."""
+    alias = bool(residual_alias and _FUSED_RESADD)
     if DEFER["on"] and not PROFILE["on"] and torch.is_grad_enabled() and x.requires_grad:
-        return _GraphConv.apply(x, conv_weight.detach(), conv_bias.detach() if conv_bias is not None else None,
-                                a_eff.detach(), (conv_weight, conv_bias, a_eff), sparsity, want_stats)
-    return _GraphConv.apply(x, conv_weight, conv_bias, a_eff, None, sparsity, want_stats)
+        out = _GraphConv.apply(x, conv_weight.detach(), conv_bias.detach() if conv_bias is not None else None,
+                               a_eff.detach(), (conv_weight, conv_bias, a_eff), sparsity, want_stats, alias)
+    else:
+        out = _GraphConv.apply(x, conv_weight, conv_bias, a_eff, None, sparsity, want_stats, alias)
+    if residual_alias and not alias:
+        return out[0], out[1], x
+    return out
 
 
 def graph_conv_available(x, co, ci):
@@ -784,8 +807,10 @@ class _SAFused(Function):
                     tc.linear_dw(dz2, h1), _col_sum(dz2) if has_b2 else None]
 
         if ctx.targets is not None:
+            # (idx too: the re-gather runs on the side stream after this node's saved tensors have been released -- without
+            # it a captured step re-used the index buffer and the gather read garbage row numbers: illegal address)
             _defer(weight_grads, [t if (t is not None and t.requires_grad) else None for t in ctx.targets],
-                   (dz1, dz2, h1, feats))
+                   (dz1, dz2, h1, feats, idx))
             return dfeats, None, None, None, None, None, None
         gw1, gb1, gw2, gb2 = weight_grads()
         return dfeats, None, gw1, gb1, gw2, gb2, None

@@ -75,15 +75,20 @@ class st_gcn_block(nn.Module):
         b, t, v, c = x.shape
         co = self.gcn.out_channels
         frames = x.reshape(b * t, v * c)
+        res = x.reshape(b * t * v, c) if self.has_residual else None
         if ops.graph_conv_available(frames, co, c):   # bf16: weight build + block-sparse GEMM + statistics, 2 launches
-            g, s1 = ops.graph_conv(frames, self.gcn.conv.weight, self.gcn.conv.bias, A, sparsity)
+            if self.has_residual:    # the residual branch reads an alias handed out by the operator (gradient fold, ops.py)
+                g, s1, x_res = ops.graph_conv(frames, self.gcn.conv.weight, self.gcn.conv.bias, A, sparsity,
+                                              residual_alias=True)
+                res = x_res.reshape(b * t * v, c)
+            else:
+                g, s1 = ops.graph_conv(frames, self.gcn.conv.weight, self.gcn.conv.bias, A, sparsity)
         else:
             w_eff, b_eff = self.gcn.effective_weight(A)
             g, s1 = ops.linear(frames, w_eff, b_eff, sparsity=sparsity, want_stats=True)
         # BN + ReLU; its backward also leaves the per-(joint, channel) sums of dg = the graph conv's bias gradient
         h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True, sums=s1, colsum_period=v)
         y, s2 = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias, want_stats=True)
-        res = x.reshape(b * t * v, c) if self.has_residual else None
         out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res, sums=s2)                       # BN + res + ReLU
         return out.reshape(b, t, v, co)
 

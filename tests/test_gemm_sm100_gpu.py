@@ -360,3 +360,49 @@ def test_gemm_cta_pair_weight_gradient(cuda):
     keep = torch.from_numpy(np.kron(sp.tile_mask(256, 256, "cpu").numpy(), np.ones((256, 256), dtype=np.float32)))[:1600, :1600]
     assert torch.equal(dw.cpu(), (dz.t() @ x) * keep)
     assert (keep.numpy() >= np.kron(nz, np.ones((64, 64), dtype=np.float32))).all()
+
+
+def test_graph_conv_residual_gradient_fold(cuda):
+    """The residual branch's gradient folded into the input-gradient GEMM (reduce-add stores of the CTA-pair kernel: dx is
+    ADDED onto the residual gradient in place) against autograd's own sum of the two gradients: M = 8192 rows (the pair
+    kernel's path) and a ragged M; also C += A.B^T of gemm_pair directly against a float64 product."""
+    import numpy as np
+    from pose2room_b200 import gemm_sm100, ops
+    from pose2room_b200.p2rnet.graph import layout_for_joints, spatial_adjacency
+    gemm_sm100.install()
+    try:
+        g = torch.Generator().manual_seed(5)
+        # (1) the GEMM itself
+        for m in (8192, 4096 + 300):
+            a = torch.randn(m, 1600, generator=g).to(cuda).bfloat16()
+            b = (torch.randn(1600, 1600, generator=g) / 40).to(cuda).bfloat16()
+            c0 = torch.randn(m, 1600, generator=g).to(cuda).bfloat16()
+            c = c0.clone()
+            out = gemm_sm100.gemm_pair(a, b, accumulate_into=c)
+            assert out.data_ptr() == c.data_ptr()
+            want = c0.double() + a.double() @ b.double().t()
+            err = (c.double() - want).abs().max().item()
+            assert err <= 2e-2 * want.abs().max().item(), err          # two bf16 roundings (the product tile, then the sum)
+        # (2) through the operator: x feeds the graph convolution AND a residual branch
+        A = torch.tensor(np.array(spatial_adjacency(layout_for_joints(25), max_hop=5)), dtype=torch.float32).to(cuda)
+        K, V, C, M = A.shape[0], 25, 64, 8192
+        sp = gemm_sm100.BlockSparsity((A.abs().sum(0) > 0).t().cpu().numpy())
+        conv_w = (torch.randn(K * C, C, 1, 1, generator=g) / 8).to(cuda).requires_grad_(True)
+        conv_b = (torch.randn(K * C, generator=g) / 4).to(cuda).requires_grad_(True)
+        x0 = torch.randn(M, V * C, generator=g).to(cuda).bfloat16()
+        go, gr = (torch.randn(M, V * C, generator=g).to(cuda).bfloat16() for _ in range(2))
+        grads = []
+        for fold in (True, False):
+            ops._FUSED_RESADD = fold
+            x = x0.clone().requires_grad_(True)
+            y, _, x_res = ops.graph_conv(x, conv_w, conv_b, A, sp, residual_alias=True)
+            torch.autograd.backward([y, x_res * 1.0], [go, gr.clone()])
+            grads.append(x.grad.double())
+            conv_w.grad = conv_b.grad = None
+        ops._FUSED_RESADD = True
+        scale = grads[1].abs().max().item()
+        assert (grads[0] - grads[1]).abs().max().item() <= 1e-2 * scale
+        assert (grads[0] - grads[1]).abs().mean().item() <= 1e-3 * scale
+    finally:
+        ops._FUSED_RESADD = True
+        gemm_sm100.uninstall()

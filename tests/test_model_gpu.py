@@ -199,9 +199,12 @@ def test_overlapped_weight_gradients_match_plain_backward(cuda, golden):
 
 
 def test_weight_shadows_change_nothing(cuda, golden):
-    """ops.register_weight_shadows (one multi-tensor fp32 -> bf16 copy per step instead of a cast per layer): same loss and
-    the same gradients, bit for bit, as converting layer by layer -- also after the weights have moved."""
-    from pose2room_b200 import gemm_sm100, ops, synthetic
+    """ops.register_weight_shadows (one multi-tensor fp32 -> bf16 copy per step instead of a cast per layer): the first
+    step's loss bit for bit and its gradients to atomics noise; after an optimiser step the shadows must hold the NEW
+    weights: seed features and votes of the second step agree with the layer-by-layer conversion (and differ clearly from
+    the first step's: the weights did move).  The total loss of step 2 is not compared -- the fixture's sharp logits turn
+    one flipped FPS pick (atomics noise of 1e-7 in a weight is enough) into a jump of the cross-entropy terms."""
+    from pose2room_b200 import gemm_sm100, ops
     gemm_sm100.install()
     try:
         out = []
@@ -209,23 +212,31 @@ def test_weight_shadows_change_nothing(cuda, golden):
             net = H.make_product("small", "train", golden, precision="bf16").to(cuda).train()
             if use_shadows:
                 ops.register_weight_shadows(net)
-            opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=1e-2)
+            opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=1e-3)
             data = H.make_data("small", cuda)
             rec = []
             for _ in range(2):
                 opt.zero_grad(set_to_none=True)
                 with ops.overlap_weight_grads():
-                    loss = net.loss(net(data), data)["total"]
+                    ep = net(data)
+                    loss = net.loss(ep, data)["total"]
                     loss.backward()
-                rec.append((loss.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}))
+                rec.append((loss.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None},
+                            ep["seed_features"].detach().double().clone(), ep["vote_xyz"].detach().double().clone()))
                 opt.step()
             out.append(rec)
             ops.clear_weight_shadows()
-        for (la, ga), (lb, gb) in zip(*out):
-            assert torch.equal(la, lb)
-            assert set(ga) == set(gb)
-            for k in ga:
-                assert torch.equal(ga[k], gb[k]), k
+        (la, ga, sfa, va), (lb, gb, sfb, vb) = out[0][0], out[1][0]
+        assert torch.equal(la, lb)                     # the forward pass is deterministic: bit-identical first loss
+        assert set(ga) == set(gb)
+        for k in ga:    # (weight gradients that end in fp32 atomics -- K = 3 first layers, split-K -- differ in the last bits)
+            scale = float(ga[k].abs().max()) + 1e-12
+            assert float((ga[k].double() - gb[k].double()).abs().max()) <= 1e-4 * scale, k
+        (_, _, sfa2, va2), (_, _, sfb2, vb2) = out[0][1], out[1][1]
+        rel = lambda x, y: float((x - y).norm() / y.norm())
+        moved = rel(sfa2, sfa)
+        assert moved > 1e-3, moved                     # the optimiser step changed the features ...
+        assert rel(sfb2, sfa2) <= 0.05 * moved and rel(vb2, va2) <= 0.05 * max(rel(va2, va), 1e-4), (rel(sfb2, sfa2), moved)
     finally:
         ops.clear_weight_shadows()
         gemm_sm100.uninstall()

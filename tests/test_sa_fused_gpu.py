@@ -3,8 +3,8 @@ GEMMs with the intermediate in shared memory / TMEM -> max over nsample in the e
 
   * an fp64 torch reference of the reference's formulation (grouping_operation -> Conv2d 1x1 + ReLU -> Conv2d 1x1 + ReLU ->
     max_pool2d; pointnet2_modules.py:220-256) on the same bf16-rounded inputs and weights, forward and every gradient;
-  * the four-launch path it replaces (group_rows -> linear -> linear -> maxpool_rows), same kernels' arithmetic: outputs
-    equal to bf16 rounding, identical arg-max decisions wherever the maximum is not a near-tie.
+  * the four-launch path it replaces (group_rows -> linear -> linear -> maxpool_rows): outputs equal to bf16 rounding;
+    gradients of both paths against fp64 (the fused path must be at least as accurate).
 Shapes: the live ProposalNet layer (512 votes -> 128 proposals x 16 samples), a ragged last tile, nsample 8 / 32 / 128."""
 import pytest
 import torch
@@ -71,13 +71,21 @@ def test_sa_fused_vs_reference_formulation_and_unfused_path(cuda, B, N, P, S):
         assert float((out.double() - ref).abs().max()) <= 1e-2 * scale, "forward vs fp64 reference"
         assert float((out.double() - out2.double()).abs().max()) <= 8e-3 * scale, "forward vs unfused kernels"
         assert float((out.double() - out2.double()).abs().mean()) <= 2e-4 * scale
+        # Gradients: both paths against fp64.  The fused kernel takes the max over the fp32 accumulators; the path it replaces
+        # takes it over bf16-ROUNDED activations, where the two largest of 16 values collide in ~10 % of the (proposal,
+        # channel) pairs and the gradient then goes to the first of them instead of the larger one -- so the fused path is
+        # the more accurate one (measured: 12-24 % relative L2 between the two paths' dfeats, fused within 3 % of fp64).
+        report = {}
         for name, a, u, r in zip(("dfeats", "dW1", "db1", "dW2", "db2"), gf, gu, gr):
             s = float(r.abs().max()) + 1e-12
             r = r.reshape(a.shape)
-            # relative L2 against fp64 (isolated arg-max / ReLU flips at near-ties move single entries, not the norm)
-            assert float((a.double() - r).norm() / r.norm()) <= 3e-2, (name, "vs fp64")
-            assert float((a.double() - u.double()).norm() / (u.double().norm() + 1e-12)) <= 3e-2, (name, "vs unfused")
+            ef = float((a.double() - r).norm() / r.norm())
+            eu = float((u.double() - r).norm() / r.norm())
+            report[name] = (round(ef, 4), round(eu, 4))
+            assert ef <= 3e-2, (name, "fused vs fp64", ef)
+            assert ef <= eu + 5e-3, (name, "the fused path must not be less accurate than the one it replaces", ef, eu)
             assert float((a.double() - r).abs().max()) <= 0.25 * s, name
+        print("sa_fused gradients, relative L2 vs fp64 (fused, unfused):", report)
     finally:
         gemm_sm100.uninstall()
 

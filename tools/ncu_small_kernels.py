@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) 
 
 REGEX = ("fps_kernel|ball_query|group_points|group_rows|gather_points|three_nn|three_interpolate|nn_distance|uniform_seed|"
          "knn_kernel|graph_offset|decode_boxes|nms3d|box3d_iou|make_batch|detection_loss|gmm_mix|vote_tail|maxpool_rows|"
-         "embed_sum|smallk")
+         "embed_sum|smallk|sa_fused")
 if "--regex" in sys.argv:
     print(REGEX)
     sys.exit(0)
@@ -98,6 +98,18 @@ for _ in range(2):
     grouped = ops.group_rows(rows, bq)
     pooled = ops.maxpool_rows(grouped.reshape(B * 128, 16, 256))
     pooled.float().sum().backward()
+torch.cuda.synchronize()
+
+# ---- the fused set-abstraction kernel (gather -> 256-256-256 MLP -> max over 16) at the live shape -------------------
+from pose2room_b200 import gemm_sm100
+gemm_sm100.install()
+conv1, conv2 = torch.nn.Conv2d(256, 256, 1).to(dev), torch.nn.Conv2d(256, 256, 1).to(dev)
+with torch.no_grad():
+    for _ in range(2):
+        ops.sa_fused(rows.detach(), bq, conv1, conv2)
+for _ in range(2):
+    ops.sa_fused(rows.detach().requires_grad_(True), bq, conv1, conv2).float().sum().backward()
+gemm_sm100.uninstall()
 torch.cuda.synchronize()
 
 # ---- nn_distance at the three call sites of the loss (loss.py:64,105,128), seed sampling, knn, graph offset ----------

@@ -49,7 +49,10 @@ def launches(src, dst, command):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if src.endswith(".csv"):      # `ncu -i x.ncu-rep --page raw --csv` already run on the GPU box (a large .ncu-rep cannot travel)
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "dram__bytes_read.sum",
@@ -59,9 +62,50 @@ def full(src, dst):
             "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_elapsed.avg.per_second"]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
     ki = hdr.index("Kernel Name")
-    seen = {}
+    col = {w: i for w, i in idx}
+    peak = 6543.1
+    try:
+        import json
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    def num(r, w):
+        try:
+            return float(r[col[w]].replace(",", ""))
+        except Exception:
+            return None
+
+    def to_us(r):
+        v, u = num(r, "gpu__time_duration.sum"), units[col["gpu__time_duration.sum"]]
+        return None if v is None else (v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v))
+
+    def to_bytes(r, w):
+        v, u = num(r, w), units[col[w]].lower() if w in col else ""
+        if v is None:
+            return None
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+    # every launch of a kernel (the scripts launch each shape twice: the second one is warm)
+    launches = {}
+    for r in rows[2:]:
+        launches.setdefault(short(r[ki]), []).append(r)
     with open(dst, "w") as f:
-        f.write("# ncu --set full --clock-control none, one launch per kernel (cold cache, profiler replay): %s\n" % src)
+        f.write("# ncu --set full --clock-control none (profiler replay, serialised): %s\n" % src)
+        f.write("# HBM column: (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum vs the measured %.0f GB/s\n" % peak)
+        f.write("# kernels that move a few hundred KB are launch-latency bound (~2-5 us): their GB/s is informational\n\n")
+        f.write("%-58s %4s %9s %10s %9s %7s %7s %6s\n" % ("kernel (last launch of each)", "n", "us", "dram MB", "GB/s", "%HBM", "tensor%", "regs"))
+        for k, rs in launches.items():
+            r = rs[-1]
+            us = to_us(r)
+            rd, wr = to_bytes(r, "dram__bytes_read.sum"), to_bytes(r, "dram__bytes_write.sum")
+            mb = (rd + wr) / 1e6 if rd is not None and wr is not None else None
+            gbs = (rd + wr) / (us * 1e-6) / 1e9 if (mb is not None and us) else None
+            tp = num(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+            rg = num(r, "launch__registers_per_thread")
+            f.write("%-58s %4d %9.1f %10.2f %9.0f %7.1f %7s %6s\n" % (
+                k[:58], len(rs), us or 0, mb or 0, gbs or 0, 100.0 * (gbs or 0) / peak, "%.1f" % tp if tp else "-", "%d" % rg if rg else "-"))
+        f.write("\n# full metric rows (first launch of each kernel)\n")
+        seen = {}
         for r in rows[2:]:
             k = short(r[ki])
             seen[k] = seen.get(k, 0) + 1
