@@ -25,10 +25,11 @@ import torch  # noqa: E402
 
 B_PER_GPU, T_FRAMES, JOINTS = 32, 1024, 25
 # DRAM bytes of ONE launch of the dominant kernel (graph-conv forward GEMM, block-sparse, fused statistics) from the
-# ncu --set full capture of this round: dram__bytes_read.sum 109.0 MB + dram__bytes_write.sum 67.5 MB
-# (profiles/r01_ncu_kernels_summary.txt; algorithmic bytes: X 104.9 MB + W_eff 5.1 MB + Y 104.9 MB -- part of Y is still
-# in the 126 MB L2 when the kernel ends)
-GCN_FWD_DRAM_BYTES_NCU = 109.048e6 + 67.502e6
+# ncu --set full capture of round 2: dram__bytes_read.sum 109.07 MB + dram__bytes_write.sum 66.73 MB
+# (profiles/r02_ncu_hot_kernels_summary.txt; algorithmic bytes: X 104.9 MB + W_eff 5.1 MB + Y 104.9 MB -- part of Y is still
+# in the 126 MB L2 when the kernel ends); the weight-gradient GEMM: 214.4 MB (its operands once: 209.7 MB + dW 10 MB)
+GCN_FWD_DRAM_BYTES_NCU = 109.065e6 + 66.726e6
+GCN_DW_DRAM_BYTES_NCU = 214.43e6
 # algorithmic (conv 64->704 + einsum, the reference's formulation) forward FLOPs of ONE graph convolution for ONE
 # sequence at T=1024, J=25: (13.84 + 5.41) GFLOP / 6 blocks  (SURVEY.md section 8d / BASELINE.md section 3)
 GCN_ALGO_GFLOP_PER_SEQ = (13.84 + 5.41) / 6.0
@@ -191,12 +192,12 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ supervision
-# Twice in ~60 runs of this round an experimental multi-stream configuration of the step stopped making progress during
-# the warm-up steps (cause not established; never seen with the shipped defaults).  A bench that
-# hangs helps nobody, so: (1) every measuring process carries a watchdog that exits with an error when no phase
-# boundary has been crossed for P2R_BENCH_STALL_S seconds; (2) the single-GPU run is a child process of a small
-# supervisor that, if the child stalls, kills it and measures once more with the single-stream step
-# (P2R_OVERLAP_DW=0) and says so in `config.fallback`.  Multi-rank runs (torchrun) only have the watchdog.
+# A bench that hangs helps nobody, so: (1) every measuring process carries a watchdog that exits with an error when no
+# phase boundary has been crossed for P2R_BENCH_STALL_S seconds; (2) the single-GPU run is a child process of a small
+# supervisor that, if the child stalls, kills it and measures ONCE more -- the SAME configuration (round 1 fell back to a
+# single-stream step here; round 2 removed that: the experimental multi-stream configurations that stalled in round 1 ran
+# 100 eager steps + 100 replays each without a stall, tools/stress_multistream.py, and a different configuration must
+# never stand in for the benched one) -- and says so in `config.retry`.  Multi-rank runs (torchrun) only have the watchdog.
 _HEARTBEAT = {"t": time.time(), "phase": "start"}
 
 
@@ -211,6 +212,10 @@ def start_watchdog():
         while True:
             time.sleep(2.0)
             if time.time() - _HEARTBEAT["t"] > _HEARTBEAT.get("limit", limit):
+                if _HEARTBEAT.get("exit_code", 17) == 0:     # the line is out, only the teardown is stuck: leave cleanly
+                    sys.stderr.write("bench.py: process-group teardown did not return in %.0f s -- exiting\n" % _HEARTBEAT["limit"])
+                    sys.stderr.flush()
+                    os._exit(0)
                 sys.stderr.write("bench.py: no progress for %.0f s in phase '%s' -- aborting\n" % (limit, _HEARTBEAT["phase"]))
                 sys.stderr.flush()
                 if os.environ.get("P2R_BENCH_GDB"):      # diagnostic: which kernels are resident on the GPU right now
@@ -221,7 +226,7 @@ def start_watchdog():
                     except Exception as e:
                         sys.stderr.write("cuda-gdb attach failed: %r\n" % (e,))
                     sys.stderr.flush()
-                os._exit(17)
+                os._exit(_HEARTBEAT.get("exit_code", 17))
     threading.Thread(target=run, daemon=True).start()
 
 
@@ -320,7 +325,7 @@ def _leg(script, name, timeout_s):
 def supervise(script=None):
     import signal
     script = script or os.path.abspath(__file__)
-    attempts = [({}, None), ({"P2R_OVERLAP_DW": "0"}, "single-stream step: the multi-stream attempt stalled and was killed")]
+    attempts = [({}, None), ({}, "second attempt of the same configuration: the first one stalled and was killed")]
     for extra, label in attempts:
         env = dict(os.environ, P2R_BENCH_CHILD="1", **extra)
         p = subprocess.Popen([sys.executable, script] + sys.argv[1:], env=env, stdout=subprocess.PIPE,
@@ -340,7 +345,7 @@ def supervise(script=None):
             if p.returncode != 0:
                 d["census"] = {"error": "the census leg ended the measuring process (exit code %s)" % p.returncode}
             if label is not None:
-                d["config"]["fallback"] = label
+                d["config"]["retry"] = label
             if isinstance(d.get("data_path"), dict) and "error" not in d["data_path"]:
                 d["data_path"]["variants"] = _variants_subprocess(script)
             if label is None and isinstance(d.get("roofline"), dict) and d.get("n_gpus") == 1:
@@ -820,7 +825,7 @@ def main():
         peak = peaks["tf_sustained"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": GCN_FWD_DRAM_BYTES_NCU if (precision == "bf16" and B == B_PER_GPU) else None,
-                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_kernels_summary.txt)",
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_ncu_hot_kernels_summary.txt)",
                     "kernel": "graph-conv GEMM fwd (M=%d,N=K=%d) %s, CTA-pair tcgen05, block-sparse K, fused BN statistics" % (gcn[0][1], vj, precision),
                     "avg_launch_ms": t_ms, "launches_timed": len(gcn), "executed_tflops": exec_flops / (t_ms * 1e-3) / 1e12,
                     "executed_over_dense": live_fraction("fwd"),
@@ -835,7 +840,10 @@ def main():
               "unit": "TFLOP/s", "kernel": "graph-conv weight gradient dW_eff[%d,%d] = dG^T.X over %d rows, %s" % (vj, vj, gdw[0][1], precision),
               "avg_launch_ms": t_dw, "launches_timed": len(gdw), "executed_over_dense": live_fraction("dw"),
               "executed_tflops": 2.0 * gdw[0][1] * vj * vj * live_fraction("dw") / (t_dw * 1e-3) / 1e12,
-              "share_of_step": t_dw * 6 / (ms / args.steps), "traffic": None}
+              "share_of_step": t_dw * 6 / (ms / args.steps),
+              "traffic": GCN_DW_DRAM_BYTES_NCU if (precision == "bf16" and B == B_PER_GPU) else None,
+              "l2_to_sm_bytes": 1.83e9 if (precision == "bf16" and B == B_PER_GPU) else None,
+              "note": "L2 -> SM bound: l1tex__m_xbar2l1tex_read_bytes 1.83 GB per launch for 0.21 GB of DRAM traffic (128 x 128 tiles)"}
         dw["frac"] = dw["achieved"] / dw["peak"]
         roofline["other_kernels"] = [dw]
     ops.PROFILE["log"] = []
@@ -968,6 +976,19 @@ def main():
                 line["census"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown: NCCL will not destroy a communicator while a captured graph still holds its kernels (round 2: with the
+        # all-reduce inside the graph, destroy_process_group() sat there until the watchdog fired and torchrun reported a
+        # failed rank although the line had been printed).  So: release the graphs first, and bound the teardown -- the
+        # measurement is complete and printed, a stuck teardown must not turn the run into a failure.
+        sys.stdout.flush()
+        beat("shutdown")
+        _HEARTBEAT["limit"], _HEARTBEAT["exit_code"] = 20.0, 0
+        torch.cuda.synchronize()
+        dist.barrier()
+        for gr in (graph, opt_graph):
+            if gr is not None:
+                gr.reset()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

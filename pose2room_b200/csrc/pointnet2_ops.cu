@@ -44,11 +44,16 @@ __device__ __forceinline__ int fps_unrank(unsigned rank, int bs_ref, int log2bs,
   return (int)(q * (unsigned)bs_ref + t);
 }
 
+// `staged`: the cloud is also kept in (dynamic) shared memory so that the coordinates of each round's pick are read
+// from there -- the m - 1 rounds are a dependent chain, and the global load of the pick (L2 latency, ~0.3 us) was the
+// longest link of it (round 2: 63 -> see DESIGN.md section 5).  Same values, same order, same result.
 template <int PPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restrict__ xyz, int* __restrict__ idxs) {
+fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restrict__ xyz, int* __restrict__ idxs,
+           int staged) {
   constexpr int NW = THREADS / 32;
   __shared__ unsigned long long s_key[2][NW];
+  P2R_DYN_SMEM(float, s_pts);    // [n * 3] when staged
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* pts = xyz + (size_t)blockIdx.x * n * 3;
   int* out = idxs + (size_t)blockIdx.x * m;
@@ -65,6 +70,11 @@ fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restric
       px[i] = __ldg(pts + 3 * k + 0);
       py[i] = __ldg(pts + 3 * k + 1);
       pz[i] = __ldg(pts + 3 * k + 2);
+      if (staged) {
+        s_pts[3 * k + 0] = px[i];
+        s_pts[3 * k + 1] = py[i];
+        s_pts[3 * k + 2] = pz[i];
+      }
       const float mag = p2r_sqnorm3(px[i], py[i], pz[i]);
       if (!((double)mag <= 1e-3)) {  // sampling_gpu.cu:100-101 (float promoted against a double literal)
         nrank[i] = ~fps_rank(k, bs_ref, log2bs, cpt);
@@ -73,6 +83,8 @@ fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restric
   }
   if (tid == 0) out[0] = 0;
   float x1 = __ldg(pts + 0), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
+  const float* cpts = staged ? s_pts : pts;
+  if (staged) __syncthreads();
 
   for (int j = 1; j < m; ++j) {
     unsigned long long best = 0ull;
@@ -105,9 +117,9 @@ fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restric
       old = fps_unrank(~(unsigned)(v & 0xffffffffull), bs_ref, log2bs, cpt);
     }
     if (tid == 0) out[j] = old;
-    x1 = __ldg(pts + 3 * old + 0);
-    y1 = __ldg(pts + 3 * old + 1);
-    z1 = __ldg(pts + 3 * old + 2);
+    x1 = cpts[3 * old + 0];
+    y1 = cpts[3 * old + 1];
+    z1 = cpts[3 * old + 2];
   }
 }
 
@@ -161,7 +173,8 @@ static void launch_fps(int b, int n, int m, int bs_ref, int cpt, const float* xy
   int log2bs = 0;
   while ((1 << log2bs) < bs_ref) ++log2bs;
   auto kern = fps_kernel<PPT, THREADS>;
-  P2R_LAUNCH(kern, b, THREADS, 0, st, n, m, bs_ref, log2bs, cpt, xyz, idxs);
+  const int staged = (size_t)n * 12 <= 48 * 1024 ? 1 : 0;      // clouds of up to 4096 points ride in shared memory
+  P2R_LAUNCH(kern, b, THREADS, staged ? (size_t)n * 12 : 0, st, n, m, bs_ref, log2bs, cpt, xyz, idxs, staged);
 }
 
 extern "C" int p2r_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idxs, float* scratch,

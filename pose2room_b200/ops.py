@@ -184,6 +184,31 @@ def parallel_branches(fns):
     return outs
 
 
+class fork_branch:
+    """Run fn() on a forked stream NOW and hand its result over at `.join()`: for a kernel whose result is needed much
+    later than its inputs are ready (the arc-length seed sampling: inputs = the raw joints, consumer = the gather at the
+    end of the backbone; 40 us of a dependent chain otherwise).  Outside the multi-stream step it simply runs in line."""
+
+    def __init__(self, fn):
+        self.stream = None
+        if not DEFER["on"] or PROFILE["on"]:
+            self.out = fn()
+            return
+        per_dev = DEFER["streams_by_device"][DEFER["device"]]
+        if per_dev.get("fork_stream") is None:
+            per_dev["fork_stream"] = torch.cuda.Stream()
+        self.stream = per_dev["fork_stream"]
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.out = fn()
+        DEFER["keep"].append(self.out)      # allocated on the forked stream: alive until the step context exits
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        return self.out
+
+
 def _defer(fn, targets, keep, inline=False):
     """Run fn() -> list of gradients on the side stream; `targets` are the autograd-connected tensors they belong to;
     `keep` are the operands the side-stream kernels read (kept alive until the join so the caching allocator cannot

@@ -173,7 +173,7 @@ class STGCN(nn.Module):
         input_joints = input_joints.contiguous()
         b, t, j, d = input_joints.shape
         act = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        seed_inds = self._seed_inds(input_joints)
+        seed_job = ops.fork_branch(lambda: self._seed_inds(input_joints))   # needed only after the six blocks
 
         hip = input_joints[:, :, self.origin_joint_id]                       # (B,T,3)
         x0 = input_joints - hip[:, :, None]                                  # joints relative to the hip
@@ -193,6 +193,7 @@ class STGCN(nn.Module):
             x = blk.forward_rows(x, a_eff, self._w_sparsity)
 
         # conv_joint on the seed frames only; reference channel order is c*J + v (stgcn.py:136-139)
+        seed_inds = seed_job.join()
         frames = x.reshape(b, t, j * 64)
         sel = torch.gather(frames, 1, seed_inds[:, :, None].expand(b, self.n_seeds, j * 64))
         wj = self.conv_joint.weight.reshape(256, 64, j).permute(0, 2, 1)     # (256, joint, 64)

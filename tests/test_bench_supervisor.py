@@ -1,5 +1,5 @@
-"""CPU: bench.py's supervisor -- a measuring child that stalls is killed and the measurement is repeated once with the
-single-stream step, flagged in config.fallback; a child that fails for another reason is not retried."""
+"""CPU: bench.py's supervisor -- a measuring child that stalls is killed and the SAME configuration is measured once more,
+flagged in config.retry; a child that fails for another reason is not retried."""
 import json
 import os
 import sys
@@ -19,30 +19,36 @@ def _run(tmp_path, body, monkeypatch, capsys, timeout="3"):
     return rc, capsys.readouterr()
 
 
-def test_stalled_child_falls_back_to_single_stream(tmp_path, monkeypatch, capsys):
+def test_stalled_child_is_retried_once_with_the_same_configuration(tmp_path, monkeypatch, capsys):
+    marker = tmp_path / "first_attempt_seen"
+    monkeypatch.setenv("FAKE_MARKER", str(marker))
     rc, io = _run(tmp_path, '''
         import json, os, time
-        assert os.environ["P2R_BENCH_CHILD"] == "1"
-        if os.environ.get("P2R_OVERLAP_DW") != "0":
-            time.sleep(60)                       # the multi-stream attempt never finishes
+        assert os.environ["P2R_BENCH_CHILD"] == "1" and os.environ.get("P2R_OVERLAP_DW") is None
+        if not os.path.exists(os.environ["FAKE_MARKER"]):
+            open(os.environ["FAKE_MARKER"], "w").close()
+            time.sleep(60)                       # the first attempt never finishes
         print(json.dumps({"value": 1.0, "config": {"workload": "w"}}))
     ''', monkeypatch, capsys)
     assert rc == 0
     lines = [l for l in io.out.splitlines() if l.startswith("{")]
     assert len(lines) == 1                                         # exactly ONE json line
     d = json.loads(lines[0])
-    assert d["value"] == 1.0 and "single-stream" in d["config"]["fallback"]
+    assert d["value"] == 1.0 and "same configuration" in d["config"]["retry"]
     assert "timed out" in io.err
 
 
 def test_watchdog_exit_is_retried_and_real_failures_are_not(tmp_path, monkeypatch, capsys):
+    marker = tmp_path / "watchdog_fired_once"
+    monkeypatch.setenv("FAKE_MARKER", str(marker))
     rc, io = _run(tmp_path, '''
         import json, os, sys
-        if os.environ.get("P2R_OVERLAP_DW") != "0":
+        if not os.path.exists(os.environ["FAKE_MARKER"]):
+            open(os.environ["FAKE_MARKER"], "w").close()
             sys.exit(17)                         # what the in-process watchdog does on a stall
         print(json.dumps({"value": 2.0, "config": {}}))
     ''', monkeypatch, capsys, timeout="30")
-    assert rc == 0 and json.loads(io.out.strip().splitlines()[-1])["config"]["fallback"]
+    assert rc == 0 and json.loads(io.out.strip().splitlines()[-1])["config"]["retry"]
     rc, io = _run(tmp_path, '''
         import sys
         print("bench.py: no CUDA device")
@@ -181,4 +187,4 @@ def test_child_that_hangs_in_the_census_leg_keeps_its_line(tmp_path, monkeypatch
     ''', monkeypatch, capsys, timeout="3")
     lines = [l for l in io.out.splitlines() if l.startswith("{")]
     d = json.loads(lines[0])
-    assert rc == 0 and len(lines) == 1 and d["value"] == 7.0 and "error" in d["census"] and "fallback" not in d["config"]
+    assert rc == 0 and len(lines) == 1 and d["value"] == 7.0 and "error" in d["census"] and "retry" not in d["config"]

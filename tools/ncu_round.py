@@ -24,6 +24,7 @@ for _ in range(2):
     st = torch.zeros(16, 2, 64, dtype=torch.float64, device=dev)
     y = gemm_sm100.gemm_pair(x, w, bias=bias, block_n=256, kb_list=sp.kb_list(256, False, dev), stats=st)   # graph conv fwd
     dx = gemm_sm100.gemm_pair(dy, w, block_n=256, kb_list=sp.kb_list(256, True, dev))                        # input gradient
+    dx = gemm_sm100.gemm_pair(dy, w, block_n=256, kb_list=sp.kb_list(256, True, dev), accumulate_into=dx)    # ... added onto the residual gradient
     dw = gemm_sm100.gemm(dy, x, True, True, out_dtype=torch.float32, block_n=128, tile_mask=sp.tile_mask(128, 128, dev))
 rows = torch.randn(M * V, C, device=dev).bfloat16().requires_grad_(True)
 res = torch.randn(M * V, C, device=dev).bfloat16()
