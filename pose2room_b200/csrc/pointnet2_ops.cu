@@ -47,6 +47,16 @@ __device__ __forceinline__ int fps_unrank(unsigned rank, int bs_ref, int log2bs,
 // `staged`: the cloud is also kept in (dynamic) shared memory so that the coordinates of each round's pick are read
 // from there -- the m - 1 rounds are a dependent chain, and the global load of the pick (L2 latency, ~0.3 us) was the
 // longest link of it (round 2: 63 -> see DESIGN.md section 5).  Same values, same order, same result.
+// Warp-wide maximum of a 64-bit key with two redux.sync (REDUX.MAX.U32) instead of five shuffle stages of two SHFLs each:
+// first the high words (the distance bits: monotone as unsigned for d2 >= 0), then the low words (~rank) among the lanes
+// that hold the winning high word.  The rounds of FPS are one dependent chain, so every cycle here is paid m - 1 times.
+__device__ __forceinline__ unsigned long long fps_warp_max(unsigned long long key) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+
 template <int PPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restrict__ xyz, int* __restrict__ idxs,
@@ -98,23 +108,29 @@ fps_kernel(int n, int m, int bs_ref, int log2bs, int cpt, const float* __restric
         best = key > best ? key : best;
       }
     }
+    best = fps_warp_max(best);
+    unsigned long long v;
+    if (NW == 1) {
+      v = best;
+    } else {
+      if (lane == 0) s_key[j & 1][warp] = best;
+      __syncthreads();
+      if (NW <= 8) {               // every thread folds the few per-warp maxima itself: no second shuffle stage
+        v = s_key[j & 1][0];
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-      best = o > best ? o : best;
+        for (int w8 = 1; w8 < NW; ++w8) {
+          const unsigned long long o = s_key[j & 1][w8];
+          v = o > v ? o : v;
+        }
+      } else {
+        v = fps_warp_max(lane < NW ? s_key[j & 1][lane] : 0ull);
+      }
     }
-    if (lane == 0) s_key[j & 1][warp] = best;
-    __syncthreads();
-    unsigned long long v = lane < NW ? s_key[j & 1][lane] : 0ull;
-#pragma unroll
-    for (int off = (NW > 16 ? 16 : NW / 2); off >= 1; off >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
-      v = o > v ? o : v;
-    }
-    v = __shfl_sync(0xffffffffu, v, 0);
     int old = 0;
     if (v != 0ull) {
-      old = fps_unrank(~(unsigned)(v & 0xffffffffull), bs_ref, log2bs, cpt);
+      const unsigned rank = ~(unsigned)(v & 0xffffffffull);
+      // (cpt == 1 whenever n is at most the reference's block size: rank = bit-reversed index, no division)
+      old = cpt == 1 ? (int)(log2bs == 0 ? 0u : (__brev(rank) >> (32 - log2bs))) : fps_unrank(rank, bs_ref, log2bs, cpt);
     }
     if (tid == 0) out[j] = old;
     x1 = cpts[3 * old + 0];

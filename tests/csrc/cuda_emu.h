@@ -131,6 +131,17 @@ static inline int __any_sync(unsigned, int pred) {
   return any;
 }
 
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {      // redux.sync.max.u32
+  EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  memcpy(w.slot[lane], &v, sizeof(unsigned));
+  w.bar.wait();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) { unsigned q; memcpy(&q, w.slot[l], sizeof(unsigned)); m = q > m ? q : m; }
+  w.bar.wait();
+  return m;
+}
+
 static inline unsigned __ballot_sync(unsigned, int pred) {
   EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31, p = pred != 0;
