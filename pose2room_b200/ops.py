@@ -51,7 +51,7 @@ PROFILE = {"on": False, "log": []}
 # the deferred gradient.  Off by default: a plain forward + `loss.backward()` (what the reference's trainer does,
 # models/training.py:25-43) behaves exactly as before.
 DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": [], "ws": {}, "ws_off": {},
-         "streams_by_device": {}, "device": None}
+         "streams_by_device": {}, "device": None, "bn_counted": set()}
 _WS_BYTES = 8 << 20
 
 
@@ -59,7 +59,7 @@ _WS_BYTES = 8 << 20
 # Every tensor-core layer needs its fp32 weight in bf16.  Converting layer by layer costs ~45 tiny cast kernels per step;
 # with shadows registered, ONE multi-tensor copy refreshes all of them when the step context is entered (after the
 # previous optimiser step, inside the captured graph) and the layers look their weight up by address.
-_SHADOW = {"params": [], "copies": [], "by_ptr": {}}
+_SHADOW = {"params": [], "copies": [], "by_ptr": {}, "bn": []}
 
 
 def register_weight_shadows(module):
@@ -69,11 +69,16 @@ def register_weight_shadows(module):
     copies = [torch.empty_like(p, dtype=torch.bfloat16) for p in params]
     _SHADOW["params"], _SHADOW["copies"] = params, copies
     _SHADOW["by_ptr"] = {p.data_ptr(): c for p, c in zip(params, copies)}
+    # the BatchNorm layers' `num_batches_tracked += 1` (29 one-element kernels per step) become one multi-tensor add when
+    # the step context is entered; batchnorm_act skips its own increment for these modules while the context is open
+    _SHADOW["bn"] = [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)
+                     and m.track_running_stats and m.num_batches_tracked is not None and m.num_batches_tracked.is_cuda]
     refresh_weight_shadows()
 
 
 def clear_weight_shadows():
-    _SHADOW["params"], _SHADOW["copies"], _SHADOW["by_ptr"] = [], [], {}
+    _SHADOW["params"], _SHADOW["copies"], _SHADOW["by_ptr"], _SHADOW["bn"] = [], [], {}, []
+    DEFER["bn_counted"] = set()
 
 
 def refresh_weight_shadows():
@@ -126,6 +131,10 @@ class overlap_weight_grads:
         DEFER["items"] = []
         DEFER["on"] = True
         refresh_weight_shadows()               # (no-op unless register_weight_shadows was called)
+        counted = [m for m in _SHADOW["bn"] if m.training]
+        DEFER["bn_counted"] = set(id(m) for m in counted)
+        if counted:
+            torch._foreach_add_([m.num_batches_tracked for m in counted], 1)
         if torch.cuda.is_available():          # one memset for every small zero-initialised buffer of the step
             key = str(torch.device("cuda", torch.cuda.current_device()))
             if key not in DEFER["ws"]:
@@ -147,6 +156,7 @@ class overlap_weight_grads:
     def __exit__(self, exc_type, exc, tb):
         DEFER["on"] = False
         DEFER["keep"] = []
+        DEFER["bn_counted"] = set()
         _COLSUM.clear()
         if exc_type is None:
             self.flush()
@@ -664,7 +674,8 @@ def batchnorm_act(x, bn, relu=False, residual=None, sums=None, colsum_period=0):
         raise RuntimeError("pose2room_b200.ops.batchnorm_act: %d channels -- the column-statistics kernels take widths that "
                            "divide 256 or are multiples of 256 (every BatchNorm of the P2RNet path does)" % c)
     training = bn.training or not bn.track_running_stats
-    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None and \
+            id(bn) not in DEFER.get("bn_counted", ()):
         bn.num_batches_tracked += 1
     if bn.momentum is None:      # nn.BatchNorm: cumulative moving average (a host read; no module of the path uses it)
         momentum = 1.0 / float(bn.num_batches_tracked) if (training and bn.track_running_stats) else 0.0

@@ -207,7 +207,7 @@ def test_weight_shadows_change_nothing(cuda, golden):
     from pose2room_b200 import gemm_sm100, ops
     gemm_sm100.install()
     try:
-        out = []
+        out, counters = [], []
         for use_shadows in (False, True):
             net = H.make_product("small", "train", golden, precision="bf16").to(cuda).train()
             if use_shadows:
@@ -226,6 +226,8 @@ def test_weight_shadows_change_nothing(cuda, golden):
                 opt.step()
             out.append(rec)
             ops.clear_weight_shadows()
+            counters.append(sorted((k, int(v)) for k, v in net.state_dict().items() if k.endswith("num_batches_tracked")))
+        assert counters[0] == counters[1] and all(v == 2 for _, v in counters[0])    # one increment per BatchNorm per step
         (la, ga, sfa, va), (lb, gb, sfb, vb) = out[0][0], out[1][0]
         assert torch.equal(la, lb)                     # the forward pass is deterministic: bit-identical first loss
         assert set(ga) == set(gb)

@@ -1,4 +1,8 @@
 #!/bin/bash
+# One GPU call that regenerates the evidence kept under profiles/ (gpurun --timeout 1700 -- "bash tools/gpu_round_evidence.sh"):
+# the full GPU suite, the bench line, the multi-stream stress runs, an ncu --set full pass over the GEMMs / streaming BatchNorm
+# kernels (CSV made on the box: a large .ncu-rep cannot travel) and the ncu launch list of an eager window of the bench.
+# (tools/ncu_small_kernels.py + tools/summarize_ncu.py do the same for every other kernel.)
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -rA --tb=short -s > gpurun_out/r02h_gputests.log 2>&1
 grep -E "passed|failed" gpurun_out/r02h_gputests.log | tail -2
