@@ -186,6 +186,28 @@ int p2r_smallk_linear_mixed(const float* x, const float* W, const float* bias, l
                             void* stream);
 int p2r_smallk_dw_mixed(const void* dz, const float* x, long long M, int N, int K, float* dW, void* stream);
 
+/* First layer of a point MLP (Conv1d K<=4 -> N, BatchNorm, ReLU; ref: stgcn.py:45-50, sub_modules.py:88-113) without its
+ * pre-activation ever being stored (csrc/embed_ops.cu): z = W x is linear in the coordinates, so the BatchNorm statistics
+ * follow from the moments of x, and forward / backward recompute z from 12 bytes instead of moving [M, N] tensors.
+ *   p2r_coord_moments      s f64[K + K*K] (zero-filled) += (sum x_k, sum x_i x_j)
+ *   p2r_embed_l1_finalize  moments -> mean / rstd / scale / shift f32[N] (+ running statistics, like p2r_bn_finalize)
+ *   p2r_embed_l1_fwd       y bf16[M,N] = relu(scale (W x) + shift)
+ *   p2r_embed_l1_bwd_stats s1 f64[N] += sum g, s2 += sum g xhat   (g = dy masked by the ReLU; dy bf16[M,N])
+ *   p2r_embed_l1_bwd_dw    dW f32[N,K] (zero-filled) += sum_m dz_m x_m^T, dz = scale (g - s1/M - xhat s2/M) (s1 = NULL: eval)
+ * x f32[M,K], W f32[N,K]; N a multiple of 8 that divides 2048.                                                          */
+int p2r_coord_moments(const float* x, long long M, int K, double* s, void* stream);
+int p2r_embed_l1_finalize(const double* s, long long M, int K, const float* W, int N, const float* gamma, const float* beta,
+                          float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                          float* scale, float* shift, void* stream);
+int p2r_embed_l1_fwd(const float* x, const float* W, const float* scale, const float* shift, long long M, int N, int K,
+                     void* y, void* stream);
+int p2r_embed_l1_bwd_stats(const void* dy, const float* x, const float* W, const float* mean, const float* rstd,
+                           const float* scale, const float* shift, long long M, int N, int K, double* s1, double* s2,
+                           void* stream);
+int p2r_embed_l1_bwd_dw(const void* dy, const float* x, const float* W, const float* mean, const float* rstd,
+                        const float* scale, const float* shift, const double* s1, const double* s2, long long M, int N,
+                        int K, float* dW, void* stream);
+
 /* bf16 tensor-core GEMM (tcgen05 + TMA + TMEM), the throughput-mode backend of every dense layer, above all the
  * fused graph-convolution GEMM that replaces conv 64->704 + einsum (ref: stgcn_layers.py:58-67).
  * C[M,N] (+)= op(A).op(B)^T, fp32 accumulate.  a_mn = 0: A is [M,K] row-major, 1: [K,M]; b_mn = 0: B is [N,K]

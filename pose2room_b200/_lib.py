@@ -55,6 +55,11 @@ SIGNATURES = {
     "p2r_smallk_dw": [_vp, _vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_linear_mixed": [_vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_smallk_dw_mixed": [_vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
+    "p2r_coord_moments": [_vp, _c_ll, _c_int, _vp, _vp],
+    "p2r_embed_l1_finalize": [_vp, _c_ll, _c_int, _vp, _c_int, _vp, _vp, _c_float, _c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "p2r_embed_l1_fwd": [_vp, _vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
+    "p2r_embed_l1_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp, _vp],
+    "p2r_embed_l1_bwd_dw": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_col_sum_wide": [_vp, _c_int, _c_ll, _c_int, _vp, _vp],
     "p2r_col_stats": [_vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp],
     "p2r_col_bwd_stats": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],

@@ -1094,6 +1094,10 @@ extern "C" int p2r_col_sum_wide(const void* dy, int dtype, long long M, int C, d
   const int V = dtype == 0 ? 4 : 8;
   P2R_CHECK_ARG(M >= 0 && C > 0 && C % V == 0, "p2r_col_sum_wide");
   if (M == 0) return 0;
+  // [M, V * 64] bf16 (the graph convolution's output gradient): rows of 64 channels that cycle through V joints -> the
+  // bulk-TMA ring with register-resident sums (stream_bn.cu)
+  if (C % 64 == 0 && C / 64 >= 2 && C / 64 <= 32 && p2r_stream_bn_ok(dtype, M * (C / 64), 64, dy))
+    return p2r_stream_colsum_period(dy, M * (C / 64), C / 64, s1, (cudaStream_t)stream);
   const int col_tiles = p2r_ceil_div(C, 32 * V);
   int row_tiles = (P2R_SM_COUNT * 8 + col_tiles - 1) / col_tiles;
   long long rpc = (M + row_tiles - 1) / row_tiles;

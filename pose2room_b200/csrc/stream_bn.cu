@@ -268,6 +268,86 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
   }
 }
 
+// Column sums of a matrix whose rows cycle through `period` classes (the graph convolution's bias gradient: dG viewed as
+// [M * V, 64], a row's class = its joint): out[row % period][channel] += x.  Same producer / consumer ring, but a tile is
+// a whole number of periods (`tile_rows` = period * floor(64 / period) rows), so the class of a thread's rows never
+// changes and the sums live in registers; the generic colsum_wide_kernel (per-thread loads) ran at 1.7 TB/s.
+__global__ void __launch_bounds__(SB_THREADS, 2)
+stream_colsum_period_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int period, int tile_rows,
+                            double* __restrict__ out) {
+  P2R_DYN_SMEM_ALIGNED(uint8_t, sb_smem, 128);
+  constexpr int STAGES = 8;
+  const int tile_bytes = tile_rows * (SB_C * 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb_smem + STAGES * SB_TILE_BYTES);
+  uint64_t* empty = full + STAGES;
+  __shared__ float cs_tab[32 * SB_C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ntiles = (rows + tile_rows - 1) / tile_rows;
+  for (int i = tid; i < 32 * SB_C; i += SB_THREADS) cs_tab[i] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      p2r_mbar_init(full + s, 1);
+      p2r_mbar_init(empty + s, SB_CONSUMERS / 32);
+    }
+    p2r_fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == SB_CONSUMERS / 32) {
+    if (lane == 0) {
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        p2r_mbar_wait(empty + s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+        const long long r0 = tile * tile_rows;
+        const uint32_t bytes = (uint32_t)min((long long)tile_rows, rows - r0) * (SB_C * 2);
+        p2r_mbar_expect_tx(full + s, bytes);
+        p2r_bulk_g2s(sb_smem + s * SB_TILE_BYTES, x + r0 * SB_C, bytes, full + s);
+      }
+    }
+    return;
+  }
+  const int cv = tid & 7, rl = tid >> 3, c0 = cv * 8;
+  float acc[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[h][i] = 0.f;
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it % STAGES;
+    p2r_mbar_wait(full + s, (uint32_t)(it / STAGES) & 1u);
+    const int rows_here = (int)min((long long)tile_rows, rows - tile * tile_rows);
+    const uint8_t* st = sb_smem + s * SB_TILE_BYTES;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = rl + 32 * h;
+      if (r < rows_here) {
+        float p[8];
+        unpack8(*reinterpret_cast<const uint4*>(st + r * (SB_C * 2) + cv * 16), p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[h][i] += p[i];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) p2r_mbar_arrive(empty + s);
+  }
+  (void)tile_bytes;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = rl + 32 * h;
+    if (r < tile_rows) {
+      float* row = cs_tab + (r % period) * SB_C + c0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(row + i, acc[h][i]);
+    }
+  }
+  P2R_NAMED_BARRIER_SYNC_1_256();
+  for (int i = tid; i < period * SB_C; i += SB_CONSUMERS) {
+    const float v = cs_tab[i];
+    if (v != 0.f) atomicAdd(out + i, (double)v);
+  }
+}
+
 int stream_ctas_per_sm() {
   static int v = 0;
   if (v == 0) {
@@ -314,6 +394,19 @@ bool p2r_stream_bn_ok(int dtype, long long M, int C, const void* p0, const void*
                       const void* p4) {
   return p2r_stream_bn_enabled() && dtype == 1 && C == SB_C && M >= 4096 && aligned16(p0) && aligned16(p1) &&
          aligned16(p2) && aligned16(p3) && aligned16(p4);
+}
+
+// out: double[period * 64], zero-filled by the caller.  rows must be a multiple of period, 2 <= period <= 32.
+int p2r_stream_colsum_period(const void* x, long long rows, int period, double* out, cudaStream_t st) {
+  const int tile_rows = period * (SB_ROWS / period);
+  constexpr int SMEM = 8 * SB_TILE_BYTES + 2 * 8 * 8;
+  const long long ntiles = (rows + tile_rows - 1) / tile_rows;
+  const int grid = (int)min(ntiles, (long long)P2R_SM_COUNT * stream_ctas_per_sm());
+  cudaFuncSetAttribute(stream_colsum_period_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  P2R_LAUNCH(stream_colsum_period_kernel, grid, SB_THREADS, SMEM, st, (const __nv_bfloat16*)x, rows, period, tile_rows, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) p2r_set_last_error("p2r_col_sum_wide", (int)e);
+  return (int)e;
 }
 
 int p2r_stream_col_stats(const void* x, long long M, double* s1, double* s2, cudaStream_t st) {

@@ -6,6 +6,7 @@
 bool p2r_stream_bn_ok(int dtype, long long M, int C, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr,
                       const void* p3 = nullptr, const void* p4 = nullptr);
 int p2r_stream_col_stats(const void* x, long long M, double* s1, double* s2, cudaStream_t st);
+int p2r_stream_colsum_period(const void* x, long long rows, int period, double* out, cudaStream_t st);
 int p2r_stream_col_bwd_stats(const void* dy, const void* x, const void* y, long long M, const float* mean,
                              const float* rstd, int relu, double* s1, double* s2, const float* scale,
                              const float* shift, cudaStream_t st);

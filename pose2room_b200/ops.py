@@ -448,6 +448,85 @@ class _SmallKMixed(Function):
         return None, gw, gb, None, None
 
 
+class _EmbedL1(Function):
+    """Conv (K <= 4 -> N) + BatchNorm + ReLU on float32 coordinates -> bf16, the pre-activation never stored
+    (csrc/embed_ops.cu): statistics from the moments of x, z recomputed in the backward, dW accumulated in the pass that
+    computes dz.  The input carries no gradient (it is the pose data)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, training, momentum, eps):
+        x = x if x.is_contiguous() else x.contiguous()
+        m, k = x.shape
+        n = weight.shape[0]
+        dev = x.device
+        wf = weight.float().contiguous()
+        stats = torch.empty(4, n, dtype=torch.float32, device=dev)       # mean, rstd, scale, shift
+        y = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            if training:
+                mom = zeros_ws(k + k * k, torch.float64, dev)
+                _lib.call("p2r_coord_moments", x.data_ptr(), m, k, mom.data_ptr(), _stream())
+                _lib.call("p2r_embed_l1_finalize", mom.data_ptr(), m, k, wf.data_ptr(), n, _ptr(gamma), _ptr(beta), float(eps),
+                          float(momentum), _ptr(running_mean), _ptr(running_var), stats[0].data_ptr(), stats[1].data_ptr(),
+                          stats[2].data_ptr(), stats[3].data_ptr(), _stream())
+            else:
+                rstd = torch.rsqrt(running_var + eps)
+                g_ = gamma if gamma is not None else torch.ones_like(rstd)
+                stats[0] = running_mean
+                stats[1] = rstd
+                stats[2] = g_ * rstd
+                stats[3] = (beta if beta is not None else 0.0) - running_mean * g_ * rstd
+            _lib.call("p2r_embed_l1_fwd", x.data_ptr(), wf.data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), m, n, k,
+                      y.data_ptr(), _stream())
+        ctx.save_for_backward(x, wf, stats)
+        ctx.training, ctx.w_shape = training, weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("pose2room_b200: the float32-coordinate first layer has no input gradient")
+        x, wf, stats = ctx.saved_tensors
+        m, k = x.shape
+        n = wf.shape[0]
+        dev = x.device
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        dy = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        sums = zeros_ws((2, n), torch.float64, dev)
+        dw = torch.zeros(n, k, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("p2r_embed_l1_bwd_stats", dy.data_ptr(), x.data_ptr(), wf.data_ptr(), stats[0].data_ptr(),
+                      stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), m, n, k, sums[0].data_ptr(),
+                      sums[1].data_ptr(), _stream())
+            _lib.call("p2r_embed_l1_bwd_dw", dy.data_ptr(), x.data_ptr(), wf.data_ptr(), stats[0].data_ptr(),
+                      stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+                      sums[0].data_ptr() if ctx.training else None, sums[1].data_ptr() if ctx.training else None, m, n, k,
+                      dw.data_ptr(), _stream())
+        sums_f = sums.float()
+        return (None, dw.reshape(ctx.w_shape) if ctx.needs_input_grad[1] else None,
+                sums_f[1] if ctx.needs_input_grad[2] else None, sums_f[0] if ctx.needs_input_grad[3] else None,
+                None, None, None, None, None)
+
+
+def embed_l1_ok(x, n, k):
+    return (x.is_cuda and x.dtype == torch.float32 and k <= 4 and n % 8 == 0 and 2048 % n == 0 and 256 % (n // 8) == 0
+            and os.environ.get("P2R_FUSED_EMBED_L1", "1") != "0")
+
+
+def embed_l1(x, weight, bn):
+    """relu(bn(x @ weight^T)) for float32 coordinates x [M, K <= 4] -> bf16 [M, N] (see _EmbedL1); `bn` an nn.BatchNorm
+    module (its mode, parameters, running statistics, momentum and eps are honoured like in batchnorm_act)."""
+    training = bn.training or not bn.track_running_stats
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None and \
+            id(bn) not in DEFER.get("bn_counted", ()):
+        bn.num_batches_tracked += 1
+    if bn.momentum is None:
+        momentum = 1.0 / float(bn.num_batches_tracked) if (training and bn.track_running_stats) else 0.0
+    else:
+        momentum = bn.momentum
+    return _EmbedL1.apply(x, weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, momentum, bn.eps)
+
+
 def smallk_mixed_ok(x, n, k):
     return x.is_cuda and x.dtype == torch.float32 and k <= 4 and n % 8 == 0 and 2048 % n == 0 and 256 % (n // 8) == 0
 

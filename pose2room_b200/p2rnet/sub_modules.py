@@ -27,6 +27,9 @@ class SingleConv(nn.Sequential):
         x's (throughput mode feeds float32 point coordinates into the first layer of an MLP and gets bf16 out)."""
         w = self.conv.weight.reshape(self.conv.out_channels, self.conv.in_channels)
         if act is not None and act != x.dtype:
+            if act == torch.bfloat16 and self.order == "cbr" and self.conv.bias is None and \
+                    ops.embed_l1_ok(x, self.conv.out_channels, self.conv.in_channels):
+                return ops.embed_l1(x, w, self.batchnorm)       # conv + BN + ReLU, the pre-activation never stored
             if act == torch.bfloat16 and ops.smallk_mixed_ok(x, self.conv.out_channels, self.conv.in_channels):
                 y, sums = ops.linear_coords(x, w, self.conv.bias, want_stats=True)
                 if "b" in self.order:

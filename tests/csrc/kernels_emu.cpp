@@ -40,4 +40,8 @@ extern "C" int emu_stream_bn_bwd_apply(const void* dy, const void* x, const void
   return p2r_stream_bn_bwd_apply(dy, x, y, M, mean, rstd, scale, s1, s2, relu, dx, dres, shift, colsum, period, nullptr);
 }
 
+extern "C" int emu_stream_colsum_period(const void* x, long long rows, int period, double* out) {
+  return p2r_stream_colsum_period(x, rows, period, out, nullptr);
+}
+
 extern "C" unsigned long long emu_launch_count() { return emu_launches; }

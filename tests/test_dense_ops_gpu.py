@@ -276,3 +276,41 @@ def test_bn_backward_fused_periodic_column_sums(cuda):
               colsum.data_ptr(), P, cs_stream)
     want = dx.double().reshape(M // P, P, C).sum(0)
     assert torch.allclose(colsum, want, rtol=1e-4, atol=1e-2), (colsum - want).abs().max()
+
+
+@pytest.mark.parametrize("M,K", [(70017, 3), (4096, 3), (1000, 4), (70020, 3), (8196, 4)])      # the last three take the bulk-TMA ring
+@pytest.mark.parametrize("training", [True, False])
+def test_embed_first_layer_without_stored_preactivation(cuda, M, K, training):
+    """ops.embed_l1 (conv K -> 64 + BatchNorm + ReLU on float32 coordinates; statistics from the moments of the input, z
+    recomputed in the backward, dW accumulated in the pass that computes dz: csrc/embed_ops.cu) against an fp64 torch
+    run of the same three modules: output, running statistics, gradients of the conv weight and of gamma / beta."""
+    from pose2room_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    x = (torch.randn(M, K, generator=g) * torch.tensor([0.3, 1.0, 2.0, 0.5][:K]) + torch.tensor([0.1, -0.9, 0.4, 2.0][:K])).to(cuda)
+    w = (torch.randn(64, K, generator=g) / K ** 0.5).to(cuda).requires_grad_(True)
+    bn = nn.BatchNorm1d(64).to(cuda)
+    with torch.no_grad():
+        bn.weight.normal_(1, 0.2)
+        bn.bias.normal_(0, 0.2)
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 1.5)
+    bn_ref = nn.BatchNorm1d(64).to(cuda).double()
+    bn_ref.load_state_dict(bn.state_dict())
+    bn.train(training)
+    bn_ref.train(training)
+    assert ops.embed_l1_ok(x, 64, K)
+    y = ops.embed_l1(x, w, bn)
+    assert y.dtype == torch.bfloat16 and y.shape == (M, 64)
+    wr = w.detach().double().requires_grad_(True)
+    ref = F.relu(bn_ref(x.double() @ wr.t()))
+    assert float((y.double() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())            # bf16 output
+    assert float((y.double() - ref).norm() / ref.norm()) <= 3e-3
+    _close(bn.running_mean, bn_ref.running_mean, rtol=1e-4, atol=1e-5)
+    _close(bn.running_var, bn_ref.running_var, rtol=1e-4, atol=1e-5)
+    assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+    go = torch.randn(M, 64, generator=g).to(cuda).bfloat16()
+    gw, gg, gb = torch.autograd.grad(y, [w, bn.weight, bn.bias], go)
+    # the reference masks with ITS ReLU; entries within bf16 rounding of zero may differ: compare norms
+    rw, rg, rb = torch.autograd.grad(ref, [wr, bn_ref.weight, bn_ref.bias], go.double())
+    for name, a, r in (("dW", gw, rw), ("dgamma", gg, rg), ("dbeta", gb, rb)):
+        assert float((a.double() - r).norm() / (r.norm() + 1e-12)) <= 2e-3, (name, float((a.double() - r).norm() / r.norm()))

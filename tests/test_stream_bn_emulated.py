@@ -33,6 +33,7 @@ def bind(path):
     lib.emu_stream_col_bwd_stats.argtypes = [vp, vp, vp, ll, vp, vp, ci, vp, vp, vp, vp]
     lib.emu_stream_affine_act.argtypes = [vp, ll, vp, vp, vp, ci, vp, vp]
     lib.emu_stream_bn_bwd_apply.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci]
+    lib.emu_stream_colsum_period.argtypes = [vp, ll, ci, vp]
     return lib
 
 
@@ -117,6 +118,22 @@ def test_streaming_batchnorm_kernels_under_emulation(emu):
     w = run_all(emu)
     assert w["fwd_stats"] < 1e-6 and w["bwd_stats"] < 1e-6 and w["colsum"] < 1e-6 and w["dres"] == 0.0
     assert w["affine"] < 8e-3 and w["dx"] < 8e-3                     # outputs are rounded to bf16
+
+
+@pytest.mark.parametrize("period,frames", [(25, 41), (25, 200), (32, 33), (2, 257), (13, 64)])
+def test_periodic_column_sums_under_emulation(emu, period, frames):
+    """stream_colsum_period_kernel (the graph convolution's bias gradient: rows of 64 channels cycling through `period`
+    joints, tiles of whole periods, register-resident sums): equal to a float64 sum per (joint, channel), ring wrapping,
+    ragged last tile, canary behind the output intact."""
+    rng = np.random.default_rng(period * 1000 + frames)
+    rows = period * frames
+    x = to_bf16(rng.normal(0.0, 1.0, size=(rows, 64)).astype(np.float32))
+    out = np.zeros(period * 64 + 8, np.float64)
+    out[-8:] = 123.0
+    assert emu.emu_stream_colsum_period(_p(x), rows, period, _p(out)) == 0
+    want = from_bf16(x).astype(np.float64).reshape(frames, period, 64).sum(0).reshape(-1)
+    assert np.all(out[-8:] == 123.0)
+    assert np.abs(out[:-8] - want).max() <= 2e-4 * max(1.0, np.abs(want).max())       # fp32 partial sums per thread
 
 
 if __name__ == "__main__":      # sanitizer driver: python tests/test_stream_bn_emulated.py <instrumented .so>
