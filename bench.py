@@ -548,10 +548,30 @@ def kernel_census(replay):
     glue = [k for k in by if k.startswith("at::") or k.startswith("at_cuda") or "cub::" in k or k.startswith("nccl")]
     t0 = min(e["ts"] for e in ker)
     t1 = max(e["ts"] + e["dur"] for e in ker)
+    streams = {}          # per stream: launches, busy time, first start and last end relative to the step's first kernel
+    for e in ker:
+        st = streams.setdefault(str((e.get("args") or {}).get("stream")), [0, 0.0, 1e30, 0.0])
+        st[0] += 1
+        st[1] += float(e["dur"])
+        st[2] = min(st[2], e["ts"] - t0)
+        st[3] = max(st[3], e["ts"] + e["dur"] - t0)
+    # time with no kernel resident at all (launch / dependency bubbles) and with more than one (the overlap)
+    edges = sorted([(e["ts"], 1) for e in ker] + [(e["ts"] + e["dur"], -1) for e in ker])
+    depth, last, idle, multi = 0, t0, 0.0, 0.0
+    for ts, d in edges:
+        if depth == 0:
+            idle += ts - last
+        elif depth > 1:
+            multi += ts - last
+        depth += d
+        last = ts
     top = sorted(by.items(), key=lambda kv: -kv[1][1])[:14]
     return {"kernels": len(ker), "kernel_time_us": sum(v[1] for v in by.values()), "span_us": t1 - t0,
             "torch_glue_kernels": sum(by[k][0] for k in glue), "torch_glue_time_us": sum(by[k][1] for k in glue),
             "memcpy_memset": sum(1 for e in events if e.get("cat") in ("gpu_memcpy", "gpu_memset")),
+            "idle_us": round(idle, 1), "overlapped_us": round(multi, 1),
+            "streams": [{"stream": k, "launches": v[0], "busy_us": round(v[1], 1), "first_us": round(v[2], 1),
+                         "last_us": round(v[3], 1)} for k, v in sorted(streams.items(), key=lambda kv: -kv[1][1])],
             "top_by_time": [{"kernel": k, "launches": v[0], "us": round(v[1], 1)} for k, v in top],
             "glue_by_count": [{"kernel": k[:60], "launches": by[k][0], "us": round(by[k][1], 1)}
                               for k in sorted(glue, key=lambda k: -by[k][0])[:16]]}

@@ -146,6 +146,12 @@ int p2r_stream_bn_supported(int dtype, long long M, int C);
 int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
                      const float* rstd, const float* scale, const double* s1, const double* s2, int relu, void* dx,
                      void* dres, const float* shift, double* colsum, int period, void* stream);
+/* The same launch; sums64 / sums32 (both or neither): the finished [2][C] double sums of p2r_col_bwd_stats (d beta,
+ * d gamma) are also stored as float32 [2][C] -- the parameters' gradient dtype without a conversion launch.          */
+int p2r_bn_bwd_apply_ex(const void* dy, const void* x, const void* y, int dtype, long long M, int C, const float* mean,
+                        const float* rstd, const float* scale, const double* s1, const double* s2, int relu, void* dx,
+                        void* dres, const float* shift, double* colsum, int period, const double* sums64, float* sums32,
+                        void* stream);
 /* dz = dy * (y > 0)                                                                                */
 int p2r_relu_bwd(const void* dy, const void* y, int dtype, long long total, void* dz, void* stream);
 /* (KT x 1) temporal conv as GEMM: x[B,T,V,C] -> col[B*T*V, KT*C] (zero padded), and its adjoint    */
@@ -156,6 +162,11 @@ int p2r_group_rows(const void* feats, int dtype, const int* idx, int B, int N, i
                    void* stream);
 int p2r_group_rows_grad(const void* grad, int dtype, const int* idx, int B, int N, int C, int P, int S, float* dfeats,
                         void* stream);
+/* Adjoint of out[b][p][:] = feats[b][idx[b][p]][:] (p2r_group_rows with S = 1: the seed-frame pick before conv_joint,
+ * ref: models/p2rnet/modules/stgcn.py:136-139) written destination-major into dfeats[B,N,C] of the gradient's dtype:
+ * every row is stored (zeros where no slot picked it, the sum where several did), no zero-fill, no atomics.          */
+int p2r_select_rows_grad(const void* grad, int dtype, const int* idx, int B, int N, int C, int P, void* dfeats,
+                         void* stream);
 int p2r_maxpool_rows(const void* x, int dtype, long long R, int S, int C, void* out, unsigned char* arg, void* stream);
 int p2r_maxpool_rows_grad(const void* dout, int dtype, const unsigned char* arg, long long R, int S, int C, void* dx,
                           void* stream);

@@ -68,11 +68,14 @@ SIGNATURES = {
     "p2r_stream_bn_supported": [_c_int, _c_ll, _c_int],
     "p2r_bn_bwd_apply": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp,
                          _c_int, _vp],
+    "p2r_bn_bwd_apply_ex": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp,
+                            _c_int, _vp, _vp, _vp],
     "p2r_relu_bwd": [_vp, _vp, _c_int, _c_ll, _vp, _vp],
     "p2r_temporal_unfold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_temporal_fold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_group_rows": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_group_rows_grad": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "p2r_select_rows_grad": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_maxpool_rows": [_vp, _c_int, _c_ll, _c_int, _c_int, _vp, _vp, _vp],
     "p2r_maxpool_rows_grad": [_vp, _c_int, _vp, _c_ll, _c_int, _c_int, _vp, _vp],
     "p2r_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp],

@@ -364,12 +364,45 @@ extern "C" int p2r_col_stats(const void* x, int dtype, long long M, int C, doubl
   P2R_RETURN_LAUNCH("p2r_col_stats");
 }
 
+// column sums of dz = relu ? dy * (y > 0) : dy for ANY width (the 259-column vote head, 100 mixture weights, 24 box
+// parameters): a block takes a run of rows, adds into a shared float table, one double atomic per column and block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_any_kernel(long long M, int C, int rows_per_block, const T* __restrict__ dy, const T* __restrict__ y,
+                  double* __restrict__ s1) {
+  P2R_DYN_SMEM(float, ca_tab);  // [C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) ca_tab[c] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long n = min((long long)rows_per_block, M - r0) * C;
+  const T* g = dy + r0 * C;
+  const T* yy = y != nullptr ? y + r0 * C : nullptr;
+  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+    float v = ldf<T>(g + e);
+    if (yy != nullptr && !(ldf<T>(yy + e) > 0.f)) v = 0.f;
+    atomicAdd(ca_tab + (int)(e % C), v);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(s1 + c, (double)ca_tab[c]);
+}
+
 // backward column sums: s1 = sum dz, s2 = sum dz*xhat (s2/x/mean/rstd may be NULL -> only s1, e.g. a bias grad)
 extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
                                  const float* mean, const float* rstd, int relu, double* s1, double* s2,
                                  const float* scale, const float* shift, void* stream) {
-  P2R_CHECK_ARG(M >= 0 && C > 0 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "p2r_col_bwd_stats");
+  const bool any_width = x == nullptr && s2 == nullptr && (relu == 0 || relu == 1) && C <= 8192;   // a bias gradient
+  P2R_CHECK_ARG(M >= 0 && C > 0 && (any_width || (C <= 256 ? 256 % C == 0 : C % 256 == 0)), "p2r_col_bwd_stats");
   P2R_CHECK_ARG(!(relu == 1 && y == nullptr), "p2r_col_bwd_stats (relu = 1 needs y)");
+  if (M > 0 && any_width && !(C <= 256 ? 256 % C == 0 : C % 256 == 0)) {
+    const int rpb = (int)max(16LL, min(1024LL, (M + P2R_SM_COUNT * 2 - 1) / (P2R_SM_COUNT * 2)));
+    const int grid = (int)((M + rpb - 1) / rpb);
+    const size_t smem = (size_t)C * sizeof(float);
+    if (dtype == 0)
+      colsum_any_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(M, C, rpb, (const float*)dy, relu ? (const float*)y : nullptr, s1);
+    else
+      colsum_any_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(M, C, rpb, (const __nv_bfloat16*)dy, relu ? (const __nv_bfloat16*)y : nullptr, s1);
+    P2R_RETURN_LAUNCH("p2r_col_bwd_stats");
+  }
   P2R_CHECK_ARG(!(relu == 2 && (x == nullptr || scale == nullptr || shift == nullptr)), "p2r_col_bwd_stats (relu = 2 needs x, scale, shift)");
   if (M == 0) return 0;
   if ((x != nullptr || relu == 0) && (s2 == nullptr || x != nullptr) && p2r_stream_bn_ok(dtype, M, C, dy, x, relu == 3 ? nullptr : y))
@@ -574,17 +607,28 @@ bn_bwd_apply_vec_kernel(long long nvec, int C, double inv_m, const T* __restrict
 // colsum / period (optional, streaming kernels with period <= 32 only): also accumulate sum over rows of dx per
 // (row % period, channel) into colsum[period][C] (double, zero-filled by the caller) -- the bias gradient of a layer whose
 // output rows cycle through `period` joints, without another pass over dx.
-extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
-                                const float* mean, const float* rstd, const float* scale, const double* s1,
-                                const double* s2, int relu, void* dx, void* dres, const float* shift, double* colsum,
-                                int period, void* stream) {
+__global__ void sums_to_float_kernel(int n, const double* __restrict__ src, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
+// sums64 / sums32 (optional): the finished [2][C] double sums of p2r_col_bwd_stats (d beta, d gamma) are also written as
+// float32 by this launch (streaming kernels) -- the parameter-dtype gradients without a conversion launch of their own.
+extern "C" int p2r_bn_bwd_apply_ex(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
+                                   const float* mean, const float* rstd, const float* scale, const double* s1,
+                                   const double* s2, int relu, void* dx, void* dres, const float* shift, double* colsum,
+                                   int period, const double* sums64, float* sums32, void* stream) {
   P2R_CHECK_ARG(M >= 0 && C > 0, "p2r_bn_bwd_apply");
   const long long total = M * C;
-  if (total == 0) return 0;
+  if (total == 0) {
+    if (sums64 != nullptr && sums32 != nullptr)
+      sums_to_float_kernel<<<p2r_ceil_div(2 * C, 256), 256, 0, (cudaStream_t)stream>>>(2 * C, sums64, sums32);
+    return 0;
+  }
   if (x != nullptr && ((relu != 1 && relu != 3) || y != nullptr) && (relu != 2 || shift != nullptr) &&
       p2r_stream_bn_ok(dtype, M, C, dy, x, relu == 3 ? nullptr : y, dx, dres))
     return p2r_stream_bn_bwd_apply(dy, x, (relu == 1 || relu == 3) ? y : nullptr, M, mean, rstd, scale, s1, s2, relu, dx, dres,
-                                   shift, colsum, period, (cudaStream_t)stream);
+                                   shift, colsum, period, (cudaStream_t)stream, sums64, sums32);
   P2R_CHECK_ARG(relu != 3, "p2r_bn_bwd_apply (relu = 3, the bit mask, needs p2r_stream_bn_supported(dtype, M, C))");
   P2R_CHECK_ARG(colsum == nullptr, "p2r_bn_bwd_apply (fused column sums need p2r_stream_bn_supported(dtype, M, C))");
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
@@ -596,7 +640,17 @@ extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, in
     bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);
   else
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, shift);
+  if (sums64 != nullptr && sums32 != nullptr)
+    sums_to_float_kernel<<<p2r_ceil_div(2 * C, 256), 256, 0, (cudaStream_t)stream>>>(2 * C, sums64, sums32);
   P2R_RETURN_LAUNCH("p2r_bn_bwd_apply");
+}
+
+extern "C" int p2r_bn_bwd_apply(const void* dy, const void* x, const void* y, int dtype, long long M, int C,
+                                const float* mean, const float* rstd, const float* scale, const double* s1,
+                                const double* s2, int relu, void* dx, void* dres, const float* shift, double* colsum,
+                                int period, void* stream) {
+  return p2r_bn_bwd_apply_ex(dy, x, y, dtype, M, C, mean, rstd, scale, s1, s2, relu, dx, dres, shift, colsum, period, nullptr,
+                             nullptr, stream);
 }
 
 // dz = dy * (y > 0)   (backward of a ReLU fused into a GEMM epilogue)
@@ -754,6 +808,75 @@ extern "C" int p2r_group_rows_grad(const void* grad, int dtype, const int* idx, 
   else
     group_rows_grad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, rows, P * S, (const __nv_bfloat16*)grad, idx, dfeats);
   P2R_RETURN_LAUNCH("p2r_group_rows_grad");
+}
+
+// Adjoint of out[b][p] = feats[b][idx[b][p]] (one picked row per slot: group_rows with S = 1) written destination-major:
+// one warp per row of dfeats scans the P picks of its batch, sums the matching gradient rows (a frame picked twice
+// gets both) and stores the row -- zeros included, so the caller does not zero-fill and nothing is atomic.
+template <typename T>
+__global__ void __launch_bounds__(256)
+select_rows_grad_kernel(int N, int C, int P, long long dst_rows, const T* __restrict__ grad,
+                        const int* __restrict__ idx, T* __restrict__ dfeats) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= dst_rows) return;
+  const long long b = w / N;
+  const int row = (int)(w - b * N);
+  const int* picks = idx + b * P;
+  constexpr int VEC = 16 / sizeof(T);
+  T* d = dfeats + (size_t)w * C;
+  __shared__ int s_match[8][32];                 // the first 32 slots that picked this row, per warp
+  int* match = s_match[threadIdx.x >> 5];
+  int count = 0;
+  for (int p0 = 0; p0 < P; p0 += 32) {
+    const int p = p0 + lane;
+    const bool hit = p < P && __ldg(picks + p) == row;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int slot = count + __popc(m & ((1u << lane) - 1u));
+      if (slot < 32) match[slot] = p;
+    }
+    count += __popc(m);
+  }
+  __syncwarp();
+  if (count == 0) {
+    if (C % VEC == 0) {
+      uint4* d4 = reinterpret_cast<uint4*>(d);
+      for (int i = lane; i < C / VEC; i += 32) d4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int i = lane; i < C; i += 32) stf<T>(d + i, 0.f);
+    }
+  } else if (count == 1 && C % VEC == 0) {
+    const uint4* g4 = reinterpret_cast<const uint4*>(grad + ((size_t)b * P + match[0]) * C);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    for (int i = lane; i < C / VEC; i += 32) d4[i] = __ldg(g4 + i);
+  } else if (count <= 32) {
+    for (int i = lane; i < C; i += 32) {
+      float t = 0.f;
+      for (int q = 0; q < count; ++q) t += ldf<T>(grad + ((size_t)b * P + match[q]) * C + i);   // slot order: deterministic
+      stf<T>(d + i, t);
+    }
+  } else {                                       // a frame picked more than 32 times: scan again per element
+    for (int i = lane; i < C; i += 32) {
+      float t = 0.f;
+      for (int p = match[0]; p < P; ++p)
+        if (__ldg(picks + p) == row) t += ldf<T>(grad + ((size_t)b * P + p) * C + i);
+      stf<T>(d + i, t);
+    }
+  }
+}
+
+extern "C" int p2r_select_rows_grad(const void* grad, int dtype, const int* idx, int B, int N, int C, int P, void* dfeats,
+                                    void* stream) {
+  P2R_CHECK_ARG(B >= 0 && N > 0 && C > 0 && P >= 0 && (dtype == 0 || dtype == 1), "p2r_select_rows_grad");
+  const long long rows = (long long)B * N;
+  if (rows == 0) return 0;
+  const int grid = p2r_ceil_div(rows * 32, 256);
+  if (dtype == 0)
+    select_rows_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, P, rows, (const float*)grad, idx, (float*)dfeats);
+  else
+    select_rows_grad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(N, C, P, rows, (const __nv_bfloat16*)grad, idx, (__nv_bfloat16*)dfeats);
+  P2R_RETURN_LAUNCH("p2r_select_rows_grad");
 }
 
 template <typename T, bool GRAD>

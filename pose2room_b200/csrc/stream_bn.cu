@@ -49,6 +49,8 @@ struct StreamArgs {
   int period;           //            atomically accumulated (the bias gradient of the layer that produced x: rows = joints)
   unsigned char* mask_out;        // AFFINE: optional ReLU bit mask of the output, [M, 8] bytes (bit i of byte cv = channel 8 cv + i)
   const unsigned char* mask_in;   // STATS_BWD / BWD_APPLY with relu == 3: that mask instead of re-reading y
+  const double* sums64;           // BWD_APPLY: optional [2][64] doubles (the finished STATS_BWD sums) that block 0 also
+  float* sums32;                  //            writes as float32 [2][64]: d beta / d gamma in the parameter's dtype
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
     p2r_fence_mbar_init();
   }
   __syncthreads();
+  if (MODE == BWD_APPLY && a.sums32 != nullptr && blockIdx.x == 0 && tid < 2 * SB_C) a.sums32[tid] = (float)a.sums64[tid];
 
   if (warp == SB_CONSUMERS / 32) {
     // ===================== producer: one lane streams tiles through the ring =====================
@@ -456,8 +459,11 @@ int p2r_stream_affine_act(const void* x, long long M, const float* scale, const 
 
 int p2r_stream_bn_bwd_apply(const void* dy, const void* x, const void* y, long long M, const float* mean,
                             const float* rstd, const float* scale, const double* s1, const double* s2, int relu,
-                            void* dx, void* dres, const float* shift, double* colsum, int period, cudaStream_t st) {
+                            void* dx, void* dres, const float* shift, double* colsum, int period, cudaStream_t st,
+                            const double* sums64, float* sums32) {
   StreamArgs a = {};
+  a.sums64 = sums64;
+  a.sums32 = sums64 != nullptr ? sums32 : nullptr;
   a.colsum = (colsum != nullptr && period >= 1 && period <= 32) ? colsum : nullptr;
   a.period = period;
   a.in[0] = (const __nv_bfloat16*)dy;

@@ -14,4 +14,5 @@ int p2r_stream_affine_act(const void* x, long long M, const float* scale, const 
                           int relu, void* y, unsigned char* relu_mask, cudaStream_t st);
 int p2r_stream_bn_bwd_apply(const void* dy, const void* x, const void* y, long long M, const float* mean,
                             const float* rstd, const float* scale, const double* s1, const double* s2, int relu,
-                            void* dx, void* dres, const float* shift, double* colsum, int period, cudaStream_t st);
+                            void* dx, void* dres, const float* shift, double* colsum, int period, cudaStream_t st,
+                            const double* sums64 = nullptr, float* sums32 = nullptr);

@@ -3,6 +3,7 @@ csrc/gemm_sm100.cu (C ABI `p2r_gemm_bf16`).  `install()` hooks it into pose2room
 forward (x.W^T), input gradient (dy.W) and weight gradient (dy^T.x) of every layer with bf16 activations run on
 the tensor cores; layers the kernel cannot take (K or N not a multiple of 8, tiny K) stay on the SIMT kernel."""
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -92,10 +93,11 @@ def available():
 
 
 def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bfloat16, splits=1, block_n=0,
-         kb_list=None, tile_mask=None, stats=None):
+         kb_list=None, tile_mask=None, stats=None, zero_skipped=True):
     """C[M,N] = op(a) @ op(b)^T.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); bf16, contiguous rows.
     kb_list / tile_mask / stats: the extras of p2r_gemm_bf16_ex (block-sparse reduction, skipped output tiles --
-    those stay zero --, fused per-channel output statistics [copies, 2, 64] float64, zero-filled here by the caller)."""
+    those stay zero, or unwritten with zero_skipped=False for a consumer that never reads them --, fused per-channel
+    output statistics [copies, 2, 64] float64, zero-filled here by the caller)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
     assert a.stride(1) == 1 and b.stride(1) == 1
     k, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
@@ -103,7 +105,7 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, out_dtype=torch.bf
     assert k == kb, (a.shape, b.shape, a_mn, b_mn)
     if splits > 1:
         c = torch.zeros(m, n, dtype=torch.float32, device=a.device)
-    elif tile_mask is not None:
+    elif tile_mask is not None and zero_skipped:
         c = torch.zeros(m, n, dtype=out_dtype, device=a.device)
     else:
         c = torch.empty(m, n, dtype=out_dtype, device=a.device)
@@ -261,15 +263,31 @@ def _pad8(n):
 
 
 def _pad_rows(t, rows):
-    """[n, k] -> [rows, k] with zero rows appended (odd output widths: 259-channel vote head, 100 mixture weights)."""
+    """[n, k] -> [rows, k] with zero rows appended (odd output widths: 259-channel vote head, 100 mixture weights).
+    A registered bf16 weight shadow already lives in a zero-padded buffer (ops.register_weight_shadows): no copy."""
+    parent = ops.padded_shadow(t, rows)
+    if parent is not None:
+        return parent
     out = torch.zeros(rows, t.shape[1], dtype=t.dtype, device=t.device)
     out[:t.shape[0]] = t
     return out
 
 
+_PAD_MEMO = {"key": None, "value": None, "src": None}
+
+
 def _pad_cols(t, cols):
+    """[m, n] -> [m, cols] with zero columns appended.  The input gradient and the weight gradient of an odd-width layer
+    both pad the same dz, one right after the other: the last result is kept and reused while its source is alive and
+    unchanged (same storage, same version counter)."""
+    key = (t.data_ptr(), tuple(t.shape), cols, t._version, t.dtype)
+    if _PAD_MEMO["key"] == key and _PAD_MEMO["src"]() is t:
+        return _PAD_MEMO["value"]
     out = torch.zeros(t.shape[0], cols, dtype=t.dtype, device=t.device)
     out[:, :t.shape[1]] = t
+    _PAD_MEMO["key"], _PAD_MEMO["value"], _PAD_MEMO["src"] = key, out, weakref.ref(t)
+    if ops.DEFER["on"]:
+        ops.DEFER["keep"].append(out)      # the deferred weight gradient reads it on the side stream: alive until the join
     return out
 
 
@@ -348,7 +366,7 @@ class _Backend:
         return gemm(dz, w_t, False, False, out_dtype=torch.bfloat16, block_n=bn, kb_list=kbl)
 
     @staticmethod
-    def linear_dw(dz, x, sparsity=None):
+    def linear_dw(dz, x, sparsity=None, zero_skipped=True):
         # dW[N,K] = dz^T[N,M] . x[M,K]: both operands MN-major (reduction over the row index m)
         if dz.shape[1] % 8:     # odd layer width: pad the columns of dz, drop the extra rows of dW
             n_true = dz.shape[1]
@@ -361,7 +379,8 @@ class _Backend:
             return gemm_pair_dw(dz, x, tl)
         if tiles >= 148:  # graph-conv: 13 x 13 = 169 tiles of 128x128 fill the chip without split-K / atomics
             mask = sparsity.tile_mask(128, 128, dz.device) if (sparsity is not None and USE_SPARSITY) else None
-            return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128, tile_mask=mask)
+            return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128, tile_mask=mask,
+                        zero_skipped=zero_skipped)
         splits = max(1, min((296 + tiles - 1) // tiles, (m + 4095) // 4096))
         return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits)
 

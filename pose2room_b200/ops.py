@@ -59,16 +59,21 @@ _WS_BYTES = 8 << 20
 # Every tensor-core layer needs its fp32 weight in bf16.  Converting layer by layer costs ~45 tiny cast kernels per step;
 # with shadows registered, ONE multi-tensor copy refreshes all of them when the step context is entered (after the
 # previous optimiser step, inside the captured graph) and the layers look their weight up by address.
-_SHADOW = {"params": [], "copies": [], "by_ptr": {}, "bn": []}
+_SHADOW = {"params": [], "copies": [], "by_ptr": {}, "bn": [], "parents": {}}
 
 
 def register_weight_shadows(module):
     """Create bf16 shadows for every float32 parameter of `module` with two or more dimensions (call once, after the
     module is on its device; harmless for modules that never run in bf16 mode)."""
     params = [p for p in module.parameters() if p.dtype == torch.float32 and p.dim() >= 2 and p.is_cuda]
-    copies = [torch.empty_like(p, dtype=torch.bfloat16) for p in params]
+    # a weight whose row count is not a multiple of 8 (TMA row pitch of the transposed roles: the 259-row vote head, the
+    # 100 mixture weights) gets its shadow inside a zero-padded parent, so the GEMM wrappers need no per-step padding copy
+    parents = [torch.zeros((-(-p.shape[0] // 8) * 8,) + tuple(p.shape[1:]), dtype=torch.bfloat16, device=p.device)
+               for p in params]
+    copies = [q[:p.shape[0]] for p, q in zip(params, parents)]
     _SHADOW["params"], _SHADOW["copies"] = params, copies
     _SHADOW["by_ptr"] = {p.data_ptr(): c for p, c in zip(params, copies)}
+    _SHADOW["parents"] = {c.data_ptr(): q for c, q in zip(copies, parents) if q.shape[0] != c.shape[0]}
     # the BatchNorm layers' `num_batches_tracked += 1` (29 one-element kernels per step) become one multi-tensor add when
     # the step context is entered; batchnorm_act skips its own increment for these modules while the context is open
     _SHADOW["bn"] = [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)
@@ -77,7 +82,7 @@ def register_weight_shadows(module):
 
 
 def clear_weight_shadows():
-    _SHADOW["params"], _SHADOW["copies"], _SHADOW["by_ptr"], _SHADOW["bn"] = [], [], {}, []
+    _SHADOW["params"], _SHADOW["copies"], _SHADOW["by_ptr"], _SHADOW["bn"], _SHADOW["parents"] = [], [], {}, [], {}
     DEFER["bn_counted"] = set()
 
 
@@ -95,6 +100,16 @@ def bf16_weight(w):
     if c is not None and c.numel() == w.numel():
         return c.view(w.shape)
     return w.to(torch.bfloat16)
+
+
+def padded_shadow(w, rows):
+    """The zero-padded [rows, k] parent of the registered bf16 shadow `w` ([n, k], n <= rows), or None."""
+    if w.dtype != torch.bfloat16 or w.dim() != 2 or not w.is_contiguous():
+        return None
+    q = _SHADOW["parents"].get(w.data_ptr())
+    if q is None or q.shape[0] != rows or q[0].numel() != w.shape[1] or w.shape[0] > rows:
+        return None
+    return q.view(rows, w.shape[1])
 
 
 def zeros_ws(shape, dtype, device):
@@ -290,8 +305,8 @@ def _col_sum(dy, y=None, relu=False):
         with torch.cuda.device(dy.device):
             _lib.call("p2r_col_sum_wide", dy.data_ptr(), _DT[dy.dtype], m, c, s1.data_ptr(), _stream())
         return s1.float()
-    if c > 256 and c % 256 or c <= 256 and 256 % c:
-        return (dy.float() if not relu else dy.float() * (y > 0)).sum(0)  # odd channel counts (259, 100, 24): tiny tensors
+    if (c > 256 and c % 256 or c <= 256 and 256 % c) and (c > 8192 or dy.dtype not in _DT or not dy.is_contiguous()):
+        return (dy.float() if not relu else dy.float() * (y > 0)).sum(0)
     s1 = zeros_ws(c, torch.float64, dy.device)
     with torch.cuda.device(dy.device):
         _lib.call("p2r_col_bwd_stats", dy.data_ptr(), None, _ptr(y), _DT[dy.dtype], m, c, None, None, int(relu),
@@ -619,7 +634,9 @@ class _GraphConv(Function):
 
         def weight_grads():
             with _Timed("gcn_dw", dy.shape[0], v * co, v * ci):
-                dw_eff = tc.linear_dw(dy, x, sp)                 # fp32 [V*Co, V*Ci], structurally-zero tiles stay 0
+                # fp32 [V*Co, V*Ci]; the structurally-zero tiles are neither computed nor zero-filled: the two reducers below
+                # only read blocks (w, v) with A[k, v, w] != 0 for some k (csrc/graph_conv.cu)
+                dw_eff = tc.linear_dw(dy, x, sp, zero_skipped=False)
             db_eff = None
             if cb is not None:
                 db_eff = fused_cs.reshape(-1).float() if fused_cs is not None else _col_sum(dy)
@@ -730,13 +747,15 @@ class _BatchNormAct(Function):
             _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
                       stats[1].data_ptr(), ctx.relu_mode, sums[0].data_ptr(), sums[1].data_ptr(), stats[2].data_ptr(),
                       stats[3].data_ptr(), _stream())
-            _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
+            want_f = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+            sums_f = torch.empty(2, c, dtype=torch.float32, device=dev) if want_f else None     # written by the same launch
+            _lib.call("p2r_bn_bwd_apply_ex", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),
                       stats[1].data_ptr(), stats[2].data_ptr(), sums[0].data_ptr() if ctx.training else None,
                       sums[1].data_ptr() if ctx.training else None, ctx.relu_mode, dx.data_ptr(), _ptr(dres),
-                      stats[3].data_ptr(), _ptr(cs), int(period if cs is not None else 0), _stream())
+                      stats[3].data_ptr(), _ptr(cs), int(period if cs is not None else 0),
+                      sums.data_ptr() if want_f else None, _ptr(sums_f), _stream())
         if cs is not None:
             _COLSUM[dx.data_ptr()] = cs
-        sums_f = sums.float() if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None   # one conversion
         dgamma = sums_f[1] if ctx.needs_input_grad[1] else None
         dbeta = sums_f[0] if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
@@ -828,6 +847,41 @@ class _GroupRows(Function):
 def group_rows(feats, idx):
     """feats [B,N,C], idx [B,P,S] int32 -> [B,P,S,C]: channel-last twin of grouping_operation."""
     return _GroupRows.apply(feats, idx.contiguous())
+
+
+class _SelectRows(Function):
+    """out[b][p] = feats[b][idx[b][p]] (the seed-frame pick before conv_joint, stgcn.py:136-139).  The adjoint is written
+    destination-major by one launch (csrc/dense_ops.cu select_rows_grad_kernel): no zero-fill of [B,N,C], no atomics."""
+
+    @staticmethod
+    def forward(ctx, feats, idx):
+        b, n, c = feats.shape
+        p = idx.shape[1]
+        feats = feats if feats.is_contiguous() else feats.contiguous()
+        idx32 = idx.to(torch.int32).contiguous()
+        out = torch.empty(b, p, c, dtype=feats.dtype, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _lib.call("p2r_group_rows", feats.data_ptr(), _DT[feats.dtype], idx32.data_ptr(), b, n, c, p, 1,
+                      out.data_ptr(), _stream())
+        ctx.save_for_backward(idx32)
+        ctx.shape = (b, n, c, p)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx32,) = ctx.saved_tensors
+        b, n, c, p = ctx.shape
+        g = g if g.is_contiguous() else g.contiguous()
+        d = torch.empty(b, n, c, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.call("p2r_select_rows_grad", g.data_ptr(), _DT[g.dtype], idx32.data_ptr(), b, n, c, p, d.data_ptr(),
+                      _stream())
+        return d, None
+
+
+def select_rows(feats, idx):
+    """feats [B,N,C] (float32 / bfloat16), idx [B,P] integer -> [B,P,C]; torch.gather along dim 1 with whole rows."""
+    return _SelectRows.apply(feats, idx)
 
 
 class _MaxPoolRows(Function):

@@ -195,7 +195,7 @@ class STGCN(nn.Module):
         # conv_joint on the seed frames only; reference channel order is c*J + v (stgcn.py:136-139)
         seed_inds = seed_job.join()
         frames = x.reshape(b, t, j * 64)
-        sel = torch.gather(frames, 1, seed_inds[:, :, None].expand(b, self.n_seeds, j * 64))
+        sel = ops.select_rows(frames, seed_inds)                             # (B, n_seeds, J*64)
         wj = self.conv_joint.weight.reshape(256, 64, j).permute(0, 2, 1)     # (256, joint, 64)
         if self._permuted:
             wj = wj.index_select(1, self._perm_idx)

@@ -314,3 +314,64 @@ def test_embed_first_layer_without_stored_preactivation(cuda, M, K, training):
     rw, rg, rb = torch.autograd.grad(ref, [wr, bn_ref.weight, bn_ref.bias], go.double())
     for name, a, r in (("dW", gw, rw), ("dgamma", gg, rg), ("dbeta", gb, rb)):
         assert float((a.double() - r).norm() / (r.norm() + 1e-12)) <= 2e-3, (name, float((a.double() - r).norm() / r.norm()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,C,P", [(3, 50, 1600, 16), (2, 33, 25, 40), (1, 8, 64, 1), (2, 3, 40, 150)])
+def test_select_rows_and_its_destination_major_adjoint(cuda, dtype, B, N, C, P):
+    """ops.select_rows (seed-frame pick before conv_joint, stgcn.py:136-139) against torch.gather, forward and backward,
+    with frames picked twice (P > N in the second case) and never: the adjoint stores every row and sums duplicates."""
+    from pose2room_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    feats = torch.randn(B, N, C, generator=g).to(cuda).to(dtype).requires_grad_(True)
+    idx = torch.randint(0, N, (B, P), generator=g).to(cuda)
+    out = ops.select_rows(feats, idx)
+    want = torch.gather(feats, 1, idx[:, :, None].expand(B, P, C))
+    assert torch.equal(out, want)
+    go = torch.randn(B, P, C, generator=g).to(cuda).to(dtype)
+    (got,) = torch.autograd.grad(out, feats, go)
+    ref = torch.zeros(B, N, C, dtype=torch.float64, device=cuda)
+    ref.scatter_add_(1, idx[:, :, None].expand(B, P, C), go.double())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert got.dtype == dtype and torch.allclose(got.double(), ref, rtol=tol, atol=tol)
+    untouched = torch.ones(B, N, dtype=torch.bool, device=cuda)
+    untouched.scatter_(1, idx, False)
+    assert float(got[untouched].abs().max()) == 0.0 if bool(untouched.any()) else True
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,C", [(8192, 259), (8192, 100), (1000, 24), (37, 7), (300, 1000)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_bias_gradient_column_sums_of_any_width(cuda, dtype, M, C, relu):
+    """ops._col_sum on widths the thread-per-column kernels do not take (the 259-column vote head, the 100 mixture
+    weights, the 24 box parameters: proposal_module.py / vote_center.py heads) against a float64 sum."""
+    from pose2room_b200 import ops
+    g = torch.Generator().manual_seed(M + C)
+    dy = torch.randn(M, C, generator=g).to(cuda).to(dtype)
+    y = torch.randn(M, C, generator=g).to(cuda).to(dtype) if relu else None
+    got = ops._col_sum(dy, y, relu)
+    want = (dy.double() * (y > 0) if relu else dy.double()).sum(0)
+    assert got.dtype == torch.float32 and got.shape == (C,)
+    assert torch.allclose(got.double(), want, rtol=1e-4, atol=1e-3 * M ** 0.5)
+
+
+def test_bn_backward_writes_float_sums_in_the_apply_launch(cuda):
+    """p2r_bn_bwd_apply_ex: sums32 = float(sums64), dx identical to p2r_bn_bwd_apply (streaming and fallback widths)."""
+    from pose2room_b200 import _lib
+    for M, C, dt in ((4096, 64, torch.bfloat16), (513, 32, torch.float32)):
+        g = torch.Generator().manual_seed(C)
+        x = torch.randn(M, C, generator=g).to(cuda).to(dt)
+        dy = torch.randn(M, C, generator=g).to(cuda).to(dt)
+        st = torch.rand(4, C, generator=g).to(cuda) + 0.5
+        sums = (torch.randn(2, C, generator=g) * 100).double().to(cuda)
+        code = {torch.float32: 0, torch.bfloat16: 1}[dt]
+        cs = torch.cuda.current_stream().cuda_stream
+        dx0, dx1 = torch.empty_like(x), torch.empty_like(x)
+        s32 = torch.full((2, C), float("nan"), device=cuda)
+        _lib.call("p2r_bn_bwd_apply", dy.data_ptr(), x.data_ptr(), None, code, M, C, st[0].data_ptr(), st[1].data_ptr(),
+                  st[2].data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), 2, dx0.data_ptr(), None, st[3].data_ptr(), None, 0, cs)
+        _lib.call("p2r_bn_bwd_apply_ex", dy.data_ptr(), x.data_ptr(), None, code, M, C, st[0].data_ptr(), st[1].data_ptr(),
+                  st[2].data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), 2, dx1.data_ptr(), None, st[3].data_ptr(), None, 0,
+                  sums.data_ptr(), s32.data_ptr(), cs)
+        assert torch.equal(dx0, dx1)
+        assert torch.equal(s32, sums.float())
