@@ -381,7 +381,9 @@ class _Backend:
             mask = sparsity.tile_mask(128, 128, dz.device) if (sparsity is not None and USE_SPARSITY) else None
             return gemm(dz, x, True, True, out_dtype=torch.float32, splits=1, block_n=128, tile_mask=mask,
                         zero_skipped=zero_skipped)
-        splits = max(1, min((296 + tiles - 1) // tiles, (m + 4095) // 4096))
+        # split-K over about one CTA per SM (measured, tools/dw_splits_bench.py: 819200 x 64 x 64 56 us at 148 splits, 62 at
+        # 200, 69 at 296; 16384 x 256 x 256 24 us at 16, 33 at 4; below 8192 rows the zero-fill + atomics cost more than they buy)
+        splits = 1 if m < 8192 else max(1, min((148 + tiles - 1) // tiles, m // 1024, 148 if tiles == 1 else 32))
         return gemm(dz, x, True, True, out_dtype=torch.float32, splits=splits)
 
     @staticmethod

@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--gemms", action="store_true", help="instead: every GEMM of the step timed alone (ops.PROFILE), by shape")
     args = ap.parse_args()
     from pose2room_b200 import gemm_sm100, ops, synthetic
     from pose2room_b200.config import P2RConfig
@@ -51,6 +52,23 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+
+    if args.gemms:
+        ops.PROFILE["log"], ops.PROFILE["on"] = [], True
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ops.PROFILE["on"] = False
+        tab = collections.defaultdict(list)
+        for r in ops.PROFILE["log"]:
+            tab[r[:4]].append(r[4].elapsed_time(r[5]) * 1e3)
+        print("%-10s %9s %6s %6s %5s %9s %9s %9s" % ("tag", "M", "N", "K", "n/step", "us", "TFLOP/s", "GB/s(min)"))
+        for (tag, m, n, k), us in sorted(tab.items(), key=lambda kv: -sum(kv[1])):
+            t = sum(us) / len(us)
+            flops = 2.0 * m * n * k
+            byts = 2.0 * (m * k + m * n) + 4.0 * n * k      # the two tall operands in bf16 + the small one
+            print("%-10s %9d %6d %6d %5d %9.1f %9.1f %9.1f" % (tag, m, n, k, len(us) // 3, t, flops / t / 1e6, byts / t / 1e3))
+        return
 
     # (a) who calls them: a dispatch mode sees every aten op of the step (forward, and the Python backward functions on
     # the autograd thread) with the Python stack that issued it; bytes written stand in for time.
