@@ -212,11 +212,14 @@ class _TemporalConvTC(torch.autograd.Function):
             if sums is None:
                 sums = torch.empty(0, dtype=torch.float64, device=x.device)
             ctx.mark_non_differentiable(sums)
+            ctx.set_materialize_grads(False)
             return y, sums
         return y
 
     @staticmethod
     def backward(ctx, dy, _dsums=None):
+        if dy is None:
+            return (None,) * 5
         x, weight = ctx.saved_tensors
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
@@ -242,7 +245,7 @@ class _TemporalConvTC(torch.autograd.Function):
                                   kt, v, None, max(1, min(148, m // 4096)), None, 1, _stream())
                         gw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
                     if need_b:
-                        gb = ops._col_sum(dy)
+                        gb = ops._col_sum(dy, at_join=True)
                     return [gw, gb]
                 ops._defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dy, x))
                 return dx, None, None, None, None

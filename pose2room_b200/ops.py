@@ -51,8 +51,9 @@ PROFILE = {"on": False, "log": []}
 # the deferred gradient.  Off by default: a plain forward + `loss.backward()` (what the reference's trainer does,
 # models/training.py:25-43) behaves exactly as before.
 DEFER = {"on": False, "stream": None, "items": [], "branch_streams": [], "keep": [], "ws": {}, "ws_off": {},
-         "streams_by_device": {}, "device": None, "bn_counted": set()}
+         "streams_by_device": {}, "device": None, "bn_counted": set(), "lazy_casts": [], "in_deferred_fn": False}
 _WS_BYTES = 8 << 20
+_DIRECT_LEAF_GRADS = os.environ.get("P2R_DIRECT_LEAF_GRADS", "1") != "0"
 
 
 # ---- bf16 shadow copies of the weights (throughput mode) ---------------------------------------------------------
@@ -163,9 +164,28 @@ class overlap_weight_grads:
         """Join the side stream and hand every deferred gradient to autograd now (parameters get their `.grad`)."""
         items, DEFER["items"] = DEFER["items"], []
         torch.cuda.current_stream().wait_stream(DEFER["stream"])      # join: every deferred dW / db is complete
-        if items:
-            tensors = [t for t, g, _ in items]
-            grads = [g for t, g, _ in items]
+        lazy, DEFER["lazy_casts"] = DEFER["lazy_casts"], []
+        if lazy:
+            with torch.no_grad():
+                torch._foreach_copy_([d for d, _ in lazy], [s for _, s in lazy])     # float64 sums -> float32 gradients
+        tensors, grads = [], []
+        for t, g, _ in items:
+            # A parameter that is itself the target takes its gradient directly: through autograd, AccumulateGrad would
+            # COPY it (the Python list here holds a second reference, so the engine may not steal the tensor) -- one small
+            # copy kernel per parameter and step.  Tensor hooks are honoured by taking the autograd route; hooks on the
+            # accumulator node (DistributedDataParallel) are not visible from here: P2R_DIRECT_LEAF_GRADS=0 for those.
+            if _DIRECT_LEAF_GRADS and t.is_leaf and t._backward_hooks is None and \
+                    getattr(t, "_post_accumulate_grad_hooks", None) is None and g.shape == t.shape and \
+                    g.dtype == t.dtype and g.device == t.device and g.is_contiguous():
+                if t.grad is None:
+                    t.grad = g
+                else:
+                    with torch.no_grad():
+                        t.grad.add_(g)
+            else:
+                tensors.append(t)
+                grads.append(g)
+        if tensors:
             torch.autograd.backward(tensors, grads)                    # views / einsum backward -> leaf .grad
 
     def __exit__(self, exc_type, exc, tb):
@@ -176,7 +196,7 @@ class overlap_weight_grads:
         if exc_type is None:
             self.flush()
         else:
-            DEFER["items"] = []
+            DEFER["items"], DEFER["lazy_casts"] = [], []
             torch.cuda.current_stream().wait_stream(DEFER["stream"])
         return False
 
@@ -239,6 +259,17 @@ def _defer(fn, targets, keep, inline=False):
     `keep` are the operands the side-stream kernels read (kept alive until the join so the caching allocator cannot
     hand their memory to main-stream tensors in the meantime).  inline=True: run on the current stream (kernels that
     own whole SMs gain nothing from a second stream) but still hand the gradients over at the join."""
+    DEFER["in_deferred_fn"] = True
+    try:
+        grads = _run_deferred(fn, inline)
+    finally:
+        DEFER["in_deferred_fn"] = False
+    for t, g in zip(targets, grads):
+        if t is not None and g is not None:
+            DEFER["items"].append((t, g.to(t.dtype) if g.dtype != t.dtype else g, keep))
+
+
+def _run_deferred(fn, inline):
     if inline:
         grads = fn()
     else:
@@ -249,9 +280,7 @@ def _defer(fn, targets, keep, inline=False):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             grads = fn()
-    for t, g in zip(targets, grads):
-        if t is not None and g is not None:
-            DEFER["items"].append((t, g.to(t.dtype) if g.dtype != t.dtype else g, keep))
+    return grads
 
 
 class _Timed:
@@ -296,22 +325,34 @@ def sgemm(a, b, trans_a=False, trans_b=True, bias=None, relu=False, out_dtype=No
     return c
 
 
-def _col_sum(dy, y=None, relu=False):
-    """sum over rows of dz = relu ? dy*(y>0) : dy -> float32 [C] (bias gradients)."""
+def _to_float_at_join(s64):
+    """float32 copy of a float64 sum that nobody reads before the step context joins its side stream: inside a deferred
+    weight-gradient function the ~16 conversions of a step become ONE multi-tensor copy at the join (flush)."""
+    if DEFER["on"] and DEFER.get("in_deferred_fn"):
+        out = torch.empty(s64.shape, dtype=torch.float32, device=s64.device)
+        DEFER["lazy_casts"].append((out, s64))
+        return out
+    return s64.float()
+
+
+def _col_sum(dy, y=None, relu=False, at_join=False):
+    """sum over rows of dz = relu ? dy*(y>0) : dy -> float32 [C] (bias gradients).  at_join=True: the caller only hands the
+    result to the deferred-gradient list (see _to_float_at_join); it must not read it."""
+    cast = _to_float_at_join if at_join else (lambda t: t.float())
     m, c = dy.shape
     vec = 8 if dy.dtype == torch.bfloat16 else 4
     if not relu and c > 256 and c % vec == 0:     # wide matrices (the 1600-column graph-conv output)
         s1 = zeros_ws(c, torch.float64, dy.device)
         with torch.cuda.device(dy.device):
             _lib.call("p2r_col_sum_wide", dy.data_ptr(), _DT[dy.dtype], m, c, s1.data_ptr(), _stream())
-        return s1.float()
+        return cast(s1)
     if (c > 256 and c % 256 or c <= 256 and 256 % c) and (c > 8192 or dy.dtype not in _DT or not dy.is_contiguous()):
         return (dy.float() if not relu else dy.float() * (y > 0)).sum(0)
     s1 = zeros_ws(c, torch.float64, dy.device)
     with torch.cuda.device(dy.device):
         _lib.call("p2r_col_bwd_stats", dy.data_ptr(), None, _ptr(y), _DT[dy.dtype], m, c, None, None, int(relu),
                   s1.data_ptr(), None, None, None, _stream())
-    return s1.float()
+    return cast(s1)
 
 
 def _smallk_ok(x, n, k, relu):
@@ -352,11 +393,14 @@ class _Linear(Function):
             if sums is None:     # kernels without the fused epilogue statistics: the caller runs its own pass
                 sums = torch.empty(0, dtype=torch.float64, device=x.device)
             ctx.mark_non_differentiable(sums)
+            ctx.set_materialize_grads(False)      # no zero-filled "gradient" tensor for the statistics output
             return y, sums
         return y
 
     @staticmethod
     def backward(ctx, dy, _dsums=None):
+        if dy is None:
+            return (None,) * 7
         x, weight, y = ctx.saved_tensors
         sp = ctx.sparsity
         dy = dy if dy.is_contiguous() else dy.contiguous()
@@ -393,7 +437,7 @@ class _Linear(Function):
                     else:
                         gw = sgemm(dz, x, True, False, out_dtype=torch.float32, splits=_splits_for(n, k, m))
                 if need_b:
-                    gb = _col_sum(dz)
+                    gb = _col_sum(dz, at_join=True)
                 return [gw, gb]
             _defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dz, x))
             return dx, None, None, None, None, None, None
@@ -432,11 +476,14 @@ class _SmallKMixed(Function):
         if want_stats:
             sums = torch.empty(0, dtype=torch.float64, device=x.device)      # no fused statistics: the caller runs its pass
             ctx.mark_non_differentiable(sums)
+            ctx.set_materialize_grads(False)
             return y, sums
         return y
 
     @staticmethod
     def backward(ctx, dy, _dsums=None):
+        if dy is None:
+            return (None,) * 5
         if ctx.needs_input_grad[0]:
             raise RuntimeError("pose2room_b200: the float32-coordinate first layer has no input gradient")
         (x,) = ctx.saved_tensors
@@ -451,7 +498,7 @@ class _SmallKMixed(Function):
                 with torch.cuda.device(x.device):
                     _lib.call("p2r_smallk_dw_mixed", dz.data_ptr(), x.data_ptr(), m, n, k, gw.data_ptr(), _stream())
             if need_b:
-                gb = _col_sum(dz)
+                gb = _col_sum(dz, at_join=True)
             return [gw, gb]
         if ctx.targets is not None:
             tw, tb = ctx.targets
@@ -602,6 +649,7 @@ class _GraphConv(Function):
         if sums is None:
             sums = torch.empty(0, dtype=torch.float64, device=dev)
         ctx.mark_non_differentiable(sums)
+        ctx.set_materialize_grads(False)
         if with_alias:
             # third output: x itself (autograd hands it out as an alias) for the block's residual branch.  Its gradient
             # then arrives HERE, next to dy, and the input-gradient GEMM adds its product onto it in place (reduce-add
@@ -611,6 +659,8 @@ class _GraphConv(Function):
 
     @staticmethod
     def backward(ctx, dy, _dsums=None, d_alias=None):
+        if dy is None:
+            return (d_alias,) + (None,) * 7
         x, cw, cb, ae, w_eff_t = ctx.saved_tensors
         k, v, co, ci = ctx.dims
         sp = ctx.sparsity
@@ -972,8 +1022,8 @@ class _SAFused(Function):
             with torch.cuda.device(dev):
                 _lib.call("p2r_group_rows", feats.data_ptr(), _DT[feats.dtype], idx.data_ptr(), b, n, c, p, s, xg.data_ptr(),
                           _stream())
-            return [tc.linear_dw(dz1, xg), _col_sum(dz1) if has_b1 else None,
-                    tc.linear_dw(dz2, h1), _col_sum(dz2) if has_b2 else None]
+            return [tc.linear_dw(dz1, xg), _col_sum(dz1, at_join=True) if has_b1 else None,
+                    tc.linear_dw(dz2, h1), _col_sum(dz2, at_join=True) if has_b2 else None]
 
         if ctx.targets is not None:
             # (idx too: the re-gather runs on the side stream after this node's saved tensors have been released -- without
