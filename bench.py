@@ -535,6 +535,11 @@ def kernel_census(replay):
         prof.export_chrome_trace(path)
         events = json.load(open(path))["traceEvents"]
     ker = [e for e in events if e.get("cat") == "kernel" and "dur" in e]
+    if os.environ.get("P2R_BENCH_CENSUS_DUMP") and ker:      # diagnostic: the step's kernels in time order, one per line
+        k0 = min(e["ts"] for e in ker)
+        with open(os.environ["P2R_BENCH_CENSUS_DUMP"], "w") as f:
+            for e in sorted(ker, key=lambda e: e["ts"]):
+                f.write("%9.1f %8.1f %4s %s\n" % (e["ts"] - k0, e["dur"], (e.get("args") or {}).get("stream"), e["name"][:110]))
     if not ker:
         return {"error": "no kernel events (CUPTI unavailable?)"}
     by = {}

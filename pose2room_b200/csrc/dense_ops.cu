@@ -850,6 +850,28 @@ select_rows_grad_kernel(int N, int C, int P, long long dst_rows, const T* __rest
     const uint4* g4 = reinterpret_cast<const uint4*>(grad + ((size_t)b * P + match[0]) * C);
     uint4* d4 = reinterpret_cast<uint4*>(d);
     for (int i = lane; i < C / VEC; i += 32) d4[i] = __ldg(g4 + i);
+  } else if (count <= 32 && C % VEC == 0 && sizeof(T) == 2) {
+    // a frame picked several times (a standing person: arc-length sampling repeats the frame): 16-byte loads, the picks
+    // of one chunk are independent loads, summed in slot order (deterministic)
+    for (int i = lane; i < C / VEC; i += 32) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < count; ++q) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(grad + ((size_t)b * P + match[q]) * C) + i);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(u[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(u[j] & 0xffff0000u);
+        }
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+        o[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      reinterpret_cast<uint4*>(d)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   } else if (count <= 32) {
     for (int i = lane; i < C; i += 32) {
       float t = 0.f;

@@ -972,6 +972,13 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, void* C, 
     return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 1 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
   if (BLOCK_N == 64 && splits <= 1 && total_kb <= 3)
     return launch_with_maps<BLOCK_N == 64 ? 64 : BLOCK_N, A_MN, B_MN, 0, (BLOCK_N == 64 ? 2 : 0)>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
+  // tall split-K weight gradients of the 64-channel layers (dW[64,64] over ~800 k rows, one CTA per SM): the reduction is
+  // pure streaming, and with 4 stages of 16 KB real data per SM it ran at ~27 GB/s per SM -- 8 stages keep twice as much
+  // in flight
+  if constexpr (BLOCK_N == 64 && A_MN && B_MN) {
+    if (splits > 1 && total_kb >= 8 * splits)
+      return launch_with_maps<64, true, true, 0, 8>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
+  }
   return launch_with_maps<BLOCK_N, A_MN, B_MN, 0, 0>(ma, mb, C, ldc, c_dtype, M, N, K, bias, relu, splits, none, st, ex);
 }
 

@@ -17,11 +17,13 @@ USE_SPARSITY = os.environ.get("P2R_GCN_SPARSE", "1") != "0"
 # graph-conv forward / input-gradient GEMMs on CTA pairs (persistent cta_group::2 kernel, 256 x PAIR_BLOCK_N tiles)
 USE_PAIR = os.environ.get("P2R_GCN_PAIR", "1") != "0"
 PAIR_BLOCK_N = int(os.environ.get("P2R_GCN_PAIR_BLOCK_N", "256"))
-# Weight gradient on CTA pairs (gemm2_dw_kernel: 128 us alone vs 212 us for the 128x128-tile kernel).  OFF by default: in
-# the step the weight gradients run on a second stream under the BatchNorm chain, and a persistent kernel that owns all
-# shared memory / TMEM of its SMs cannot co-reside with that chain -- measured 9.44-9.55 ms/step vs 9.32 with the small
-# co-resident tiles.
-USE_PAIR_DW = os.environ.get("P2R_GCN_PAIR_DW", "0") != "0"
+# Weight gradient of the graph convolution on CTA pairs (gemm2_dw_kernel: 256 x 256 tiles, 124 us in the step against ~250
+# for the 128 x 128-tile kernel, which is bound by L2 -> SM operand traffic).  Round 1 and the first half of round 2 kept it
+# off: with the backward's two streams balanced as they were then, a persistent kernel that owns the shared memory / TMEM
+# of its SMs cost more on the BatchNorm chain than it saved (9.44-9.55 ms/step vs 9.32).  After the rest of the backward got
+# shorter the weight-gradient stream became the longer one, and the faster kernel wins: 7.44 vs 7.55 ms/step.
+DW_TILE = (256, 256) if os.environ.get("P2R_GCN_PAIR_DW", "1") != "0" else (128, 128)
+USE_PAIR_DW = os.environ.get("P2R_GCN_PAIR_DW", "1") != "0"
 USE_FUSED_STATS = os.environ.get("P2R_FUSED_STATS", "1") != "0"
 
 
@@ -296,8 +298,9 @@ def _pad_cols(t, cols):
 
 class _Backend:
     """Interface expected by ops._Linear (see ops._TC_GEMM)."""
-    # the CTA-pair weight-gradient kernel owns whole SMs: run it in line with the backward chain, not beside it
-    DW_INLINE = USE_PAIR_DW and os.environ.get("P2R_GCN_DW_INLINE", "1") != "0"
+    # the CTA-pair weight-gradient kernel on the weight-gradient stream like every other dW (measured at the end of round 2:
+    # 7.44 ms/step there, 7.78 in line with the backward chain, 7.55 with the 128 x 128-tile kernel)
+    DW_INLINE = USE_PAIR_DW and os.environ.get("P2R_GCN_DW_INLINE", "0") != "0"
 
     @staticmethod
     def supports(m, n, k):

@@ -193,6 +193,7 @@ class overlap_weight_grads:
         DEFER["keep"] = []
         DEFER["bn_counted"] = set()
         _COLSUM.clear()
+        _GCN_PREBUILT.clear()
         if exc_type is None:
             self.flush()
         else:
@@ -619,6 +620,49 @@ _COLSUM = {}
 _FUSED_COLSUM = os.environ.get("P2R_FUSED_COLSUM", "0") != "0"
 
 
+_GCN_PREBUILT = {}
+
+
+def _gcn_build(conv_w, conv_b, a_eff):
+    """(cw, cb, ae, W_eff, W_eff^T, b_eff) of one graph convolution: W_eff[(w,co),(v,ci)] = sum_k W_k[co,ci] A_k[v,w]
+    (ref: ConvTemporalGraphical.forward, stgcn_layers.py:58-67, as one matrix), both orientations in bf16, one launch."""
+    k, v = a_eff.shape[0], a_eff.shape[1]
+    co, ci = conv_w.shape[0] // k, conv_w.shape[1]
+    dev = conv_w.device
+    cw = conv_w.reshape(k * co, ci).float().contiguous()
+    cb = conv_b.float().contiguous() if conv_b is not None else None
+    ae = a_eff.float().contiguous()
+    w_eff = torch.empty(v * co, v * ci, dtype=torch.bfloat16, device=dev)
+    w_eff_t = torch.empty(v * ci, v * co, dtype=torch.bfloat16, device=dev)
+    b_eff = torch.empty(v * co, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("p2r_gcn_build_weight", cw.data_ptr(), _ptr(cb), ae.data_ptr(), k, v, co, ci, w_eff.data_ptr(),
+                  w_eff_t.data_ptr(), b_eff.data_ptr(), _stream())
+    return cw, cb, ae, w_eff, w_eff_t, b_eff
+
+
+def graph_conv_prebuild(specs):
+    """Build the effective weights of several graph convolutions NOW, on the current stream (a forked branch: they only
+    depend on parameters, so the six builds of the backbone -- 20 us each, serial in front of their GEMMs otherwise -- run
+    beside the embedding layers).  specs: [(conv_weight, conv_bias, a_eff)]; the next graph_conv() call with the same
+    conv_weight / a_eff tensors takes the prebuilt matrices.  Entries not consumed are dropped when the step ends."""
+    out = []
+    _GCN_PREBUILT.clear()          # (whatever an earlier forward pass did not consume)
+    with torch.no_grad():
+        for conv_w, conv_b, a_eff in specs:
+            built = _gcn_build(conv_w.detach(), conv_b.detach() if conv_b is not None else None, a_eff.detach())
+            _GCN_PREBUILT[(conv_w.data_ptr(), a_eff.data_ptr())] = built
+            out.append(built)
+    if DEFER["on"]:
+        DEFER["keep"].append(out)  # allocated on the forked stream, read on the main one: alive until the step ends
+    return out
+
+
+def graph_conv_prebuild_ok(rows):
+    """Will graph_conv() take the tensor-core path for `rows` bf16 frames of 64-channel joints (graph_conv_available)?"""
+    return _TC_GEMM["fn"] is not None and rows >= 128
+
+
 class _GraphConv(Function):
     """The graph convolution of st_gcn_block as ONE tensor-core GEMM (bf16 mode): builds W_eff / W_eff^T / b_eff from
     the conv parameters and A = adjacency * importance with one kernel, runs the block-sparse GEMM (statistics of the
@@ -632,15 +676,8 @@ class _GraphConv(Function):
         co, ci = conv_w.shape[0] // k, conv_w.shape[1]
         x = x if x.is_contiguous() else x.contiguous()
         dev = x.device
-        cw = conv_w.reshape(k * co, ci).float().contiguous()
-        cb = conv_b.float().contiguous() if conv_b is not None else None
-        ae = a_eff.float().contiguous()
-        w_eff = torch.empty(v * co, v * ci, dtype=torch.bfloat16, device=dev)
-        w_eff_t = torch.empty(v * ci, v * co, dtype=torch.bfloat16, device=dev)
-        b_eff = torch.empty(v * co, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.call("p2r_gcn_build_weight", cw.data_ptr(), _ptr(cb), ae.data_ptr(), k, v, co, ci, w_eff.data_ptr(),
-                      w_eff_t.data_ptr(), b_eff.data_ptr(), _stream())
+        built = _GCN_PREBUILT.pop((conv_w.data_ptr(), a_eff.data_ptr()), None)     # graph_conv_prebuild ran ahead
+        cw, cb, ae, w_eff, w_eff_t, b_eff = built if built is not None else _gcn_build(conv_w, conv_b, a_eff)
         with _Timed("fwd", x.shape[0], v * co, v * ci):
             y, sums = tc.linear_fwd_ex(x, w_eff, b_eff, False, sparsity, want_stats)
         ctx.save_for_backward(x, cw, cb, ae, w_eff_t)

@@ -175,6 +175,21 @@ class STGCN(nn.Module):
         act = torch.bfloat16 if self.precision == "bf16" else torch.float32
         seed_job = ops.fork_branch(lambda: self._seed_inds(input_joints))   # needed only after the six blocks
 
+        def effective_adjacency():
+            """A * importance per block (stgcn.py:124-126) and, in bf16 mode, the effective graph-conv weights built from
+            it: parameters only, so all of it runs on a forked stream beside the embedding layers."""
+            a_effs = []
+            for importance in self.edge_importance:
+                a_eff = self.A * importance
+                if self._permuted:
+                    a_eff = a_eff.index_select(1, self._perm_idx).index_select(2, self._perm_idx)
+                a_effs.append(a_eff)
+            if act == torch.bfloat16 and ops.graph_conv_prebuild_ok(b * t):
+                ops.graph_conv_prebuild([(blk.gcn.conv.weight, blk.gcn.conv.bias, a)
+                                         for blk, a in zip(self.st_gcn_networks, a_effs)])
+            return a_effs
+        weights_job = ops.fork_branch(effective_adjacency)
+
         hip = input_joints[:, :, self.origin_joint_id]                       # (B,T,3)
         x0 = input_joints - hip[:, :, None]                                  # joints relative to the hip
         if self._permuted:
@@ -186,10 +201,7 @@ class STGCN(nn.Module):
         # x = sk + mean_k(pos) broadcast over the joints of the frame (stgcn.py:121,129), one fused kernel
         x = ops.embed_sum(sk.reshape(b * t, j, 64), pos.reshape(b * t, self.knn, 64)).reshape(b, t, j, 64)
 
-        for blk, importance in zip(self.st_gcn_networks, self.edge_importance):
-            a_eff = self.A * importance
-            if self._permuted:
-                a_eff = a_eff.index_select(1, self._perm_idx).index_select(2, self._perm_idx)
+        for blk, a_eff in zip(self.st_gcn_networks, weights_job.join()):
             x = blk.forward_rows(x, a_eff, self._w_sparsity)
 
         # conv_joint on the seed frames only; reference channel order is c*J + v (stgcn.py:136-139)
