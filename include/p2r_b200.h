@@ -260,6 +260,9 @@ int p2r_gemm_bf16_pair_dw(int R, int N1, int N2, const void* dz, int ldz, const 
  * of y, i.e. the statistics of the BatchNorm2d that follows the conv (stgcn_layers.py:412).                        */
 int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows, int Ci,
                    int Co, int KT, int V, const float* bias, int splits, double* stats, int stat_copies, void* stream);
+/* Diagnostic (not part of the reference's interface): per-tile globaltimer stamps of one CTA of the halo temporal-conv
+ * kernels into device_buffer[3 roles][64 tiles][8 events] (long long, device memory); NULL switches it off again. */
+int p2r_debug_tconv_trace(long long* device_buffer);
 
 /* Weight plumbing of the fused graph convolution (ref: ConvTemporalGraphical.forward, stgcn_layers.py:58-67; A = adjacency
  * stack * edge importance, stgcn.py:133-134).  Build  W_eff[(w,co),(v,ci)] = sum_k A[k,v,w] W[k*Co+co, ci]  (bf16), its

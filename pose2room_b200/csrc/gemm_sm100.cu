@@ -35,6 +35,21 @@ struct TapArgs {
   int kb_per_tap, rows_per_sample, channels, shift0, shift_step;
 };
 
+// TAP == 3 (temporal conv forward / input gradient with ONE halo tile per 128 output rows instead of three shifted 128-row
+// views: 23 KB instead of 48 KB through L2 -> SM per tile, and the 24 KB of weights loaded once per CTA instead of once
+// per tile -- the three-view kernels moved 472 MB per launch through the crossbar for 165 MB of DRAM traffic and were
+// bound by it).  Shared memory: [weights 3 x 8 KB][HALO_STAGES x halo tile][staging][bias][barriers].
+#define HALO_STAGES 3
+#define HALO_W_BYTES (3 * 8192)
+__host__ __device__ inline int halo_tile_bytes(int v) { return ((GEMM_BLOCK_M + 2 * v) * 128 + 1023) & ~1023; }
+// TAP == 4 (temporal conv weight gradient): the three-view loads of TAP == 2 (one N = 192 MMA per 16 reduction rows; three
+// N = 64 MMAs on row-offset views of one halo tile were tried and are SLOWER, 93 vs 74 us: issuing a tcgen05.mma costs
+// ~60 ns whatever its size), but only the live half of the dy tile is staged -- Co = 64 of the M = 128 operand rows; the
+// other 64-row block of every stage's descriptor points at one shared zero block -- so a stage is 32 KB instead of 40 KB
+// and six of them fit instead of four: the kernel is bound by how many reduction rows are in flight.
+#define DW4_A_BYTES (GEMM_BLOCK_K * 128)
+#define DW4_STAGE_BYTES (DW4_A_BYTES + 3 * GEMM_BLOCK_K * 128)
+
 // Optional extras of one launch (all NULL / 0 = plain dense GEMM):
 //   kb_list   : block-sparse reduction.  Row n_tile of an int table [tiles_n][kb_stride]: entry 0 = number of 64-wide
 //               k-blocks this n-tile visits, entries 1.. = their indices (ascending).  The graph-convolution weight
@@ -44,6 +59,18 @@ struct TapArgs {
 //   stats     : fused BatchNorm statistics of the OUTPUT: per channel c = column % 64, sum and sum of squares of the
 //               values as stored (after bias / rounding to the output type), accumulated with double atomics into
 //               stats[copy][0][c] / stats[copy][1][c], copy = CTA index % stat_copies (spreads the atomic traffic).
+// Diagnostic: per-tile timestamps (globaltimer, ns) of the three roles of ONE CTA of the halo temporal-conv kernels
+// (TAP == 3): trace[((role * 64 + tile) * 8 + event)], role 0 producer / 1 MMA issuer / 2 first epilogue warp.  NULL (the
+// default) = off; set with p2r_debug_tconv_trace().
+__device__ long long* g_tconv_trace = nullptr;
+__device__ __forceinline__ void trace_mark(long long* tr, int role, int tile, int ev) {
+  if (tr != nullptr && tile < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tr[(role * 64 + tile) * 8 + ev] = (long long)t;
+  }
+}
+
 struct GemmExtra {
   const int* kb_list;
   int kb_stride;
@@ -88,7 +115,7 @@ struct GemmSmem {
 // tma_c (box {64 columns, 32 rows}); see the CTA-pair kernel below for why.  Needs bf16 C, BLOCK_N % 64 == 0.
 template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT, bool ATOMIC, int TAP = 0, int NSTAGE = 0, bool STATS = false,
           bool TS = false>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(TAP == 3 ? GEMM_THREADS + 128 : GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c,
                  OutT* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ bias, int relu,
@@ -98,7 +125,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   constexpr int ACC = S::ACC_STAGES;   // accumulator buffers in TMEM (2: the epilogue of tile t overlaps the MMAs of t+1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + S::STAGES * S::STAGE_BYTES;                      // (TS) 1024-byte aligned
+  const int halo_v = tap.shift_step < 0 ? -tap.shift_step : tap.shift_step;  // (TAP 3) rows between two taps
+  const int halo_bytes = halo_tile_bytes(halo_v);
+  constexpr int stage4_bytes = DW4_STAGE_BYTES;                              // (TAP 4) live dy half + three x taps
+  uint8_t* staging = smem + (TAP == 3 ? HALO_W_BYTES + HALO_STAGES * halo_bytes
+                                      : (TAP == 4 ? S::STAGES * stage4_bytes + DW4_A_BYTES : S::STAGES * S::STAGE_BYTES));   // (TS) 1024-byte aligned
   float* sbias = reinterpret_cast<float*>(staging + S::STAGING_BYTES);       // (TS) [2][BLOCK_N]
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
   uint64_t* empty = full + S::STAGES;
@@ -112,7 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int kb0 = blockIdx.z * kblocks_per_split;
   const int kb1 = min(total_kb, kb0 + kblocks_per_split);
   const int* kbl = ex.kb_list != nullptr ? ex.kb_list + (size_t)blockIdx.x * ex.kb_stride + 1 : nullptr;
-  const int nkb = kbl != nullptr ? __ldg(kbl - 1) : kb1 - kb0;
+  const int nkb = TAP == 3 ? 3 : (kbl != nullptr ? __ldg(kbl - 1) : kb1 - kb0);
   const int tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int tile0 = blockIdx.y * tiles_per_cta;
   const int ntiles = min(tiles_per_cta, tiles_m - tile0);   // m-tiles this CTA walks through
@@ -124,7 +155,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       p2r_mbar_init(tmem_full + a, 1);
-      p2r_mbar_init(tmem_empty + a, 4);   // one arrival per epilogue warp
+      p2r_mbar_init(tmem_empty + a, TAP == 3 ? 8 : 4);   // one arrival per epilogue warp
     }
     p2r_fence_mbar_init();
   }
@@ -132,6 +163,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (TS) tma_prefetch_desc(&tma_c);
+  }
+  if (TAP == 4) {   // rows 64..127 of the M = 128 dy operand do not exist (Co = 64): one zero block after the ring
+    uint4* z = reinterpret_cast<uint4*>(smem + S::STAGES * stage4_bytes);
+    for (int i = threadIdx.x; i < DW4_A_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    p2r_fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
   tc_fence_before();
@@ -141,7 +177,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (TAP == 3) {
+      if (lane == 0) {
+        p2r_mbar_expect_tx(full + HALO_STAGES, HALO_W_BYTES);           // the weights of the three taps, once
+#pragma unroll
+        for (int tp = 0; tp < 3; ++tp) {
+          if (!B_MN) tma_load_2d(smem + tp * 8192, &tma_b, full + HALO_STAGES, tp * 64, n0);    // box {64 k, 64 n}
+          else tma_load_2d(smem + tp * 8192, &tma_b, full + HALO_STAGES, n0, tp * 64);           // box {64 n, 64 k}
+        }
+        long long* tr = (blockIdx.y == 1 && blockIdx.x == 0) ? g_tconv_trace : nullptr;
+        for (int t = 0; t < ntiles; ++t) {
+          const int m0 = (tile0 + t) * GEMM_BLOCK_M;
+          const int s = t % HALO_STAGES;
+          p2r_mbar_wait(empty + s, ((uint32_t)(t / HALO_STAGES) & 1u) ^ 1u);
+          trace_mark(tr, 0, t, 0);
+          p2r_mbar_expect_tx(full + s, (uint32_t)(GEMM_BLOCK_M + 2 * halo_v) * 128u);
+          tma_load_3d(smem + HALO_W_BYTES + s * halo_bytes, &tma_a, full + s, 0, (m0 % tap.rows_per_sample) - halo_v,
+                      m0 / tap.rows_per_sample);                          // box {64 c, 128 + 2 V rows, 1 sample}
+          trace_mark(tr, 0, t, 1);
+        }
+      }
+    } else if (TAP == 4) {
+      if (lane == 0) {
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % S::STAGES;
+          p2r_mbar_wait(empty + s, ((uint32_t)(i / S::STAGES) & 1u) ^ 1u);
+          uint8_t* a_dst = smem + s * stage4_bytes;
+          const int k0 = (kb0 + i) * GEMM_BLOCK_K;
+          p2r_mbar_expect_tx(full + s, (uint32_t)stage4_bytes);
+          tma_load_2d(a_dst, &tma_a, full + s, 0, k0);                                            // box {64 co, 64 k}
+#pragma unroll
+          for (int tp = 0; tp < 3; ++tp)                                                          // boxes {64 ci, 64 rows, 1}
+            tma_load_3d(a_dst + DW4_A_BYTES + tp * (GEMM_BLOCK_K * 128), &tma_b, full + s, 0,
+                        (k0 % tap.rows_per_sample) + tap.shift0 + tp * tap.shift_step, k0 / tap.rows_per_sample);
+        }
+      }
+    } else if (lane == 0) {
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int m0 = (tile0 + t) * GEMM_BLOCK_M;
@@ -186,7 +257,68 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (TAP == 3) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(GEMM_BLOCK_M, BLOCK_N, 0, B_MN ? 1 : 0);
+        p2r_mbar_wait(full + HALO_STAGES, 0u);
+        long long* tr = (blockIdx.y == 1 && blockIdx.x == 0) ? g_tconv_trace : nullptr;
+        for (int t = 0; t < ntiles; ++t) {
+          const int as = t % ACC;
+          if (t >= ACC) {
+            p2r_mbar_wait(tmem_empty + as, (uint32_t)((t / ACC) - 1) & 1u);
+            tc_fence_after();
+          }
+          trace_mark(tr, 1, t, 0);
+          const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
+          const int s = t % HALO_STAGES;
+          p2r_mbar_wait(full + s, (uint32_t)(t / HALO_STAGES) & 1u);
+          tc_fence_after();
+          trace_mark(tr, 1, t, 1);
+          const uint32_t a_addr = p2r_smem_u32(smem + HALO_W_BYTES + s * halo_bytes);
+#pragma unroll
+          for (int tp = 0; tp < 3; ++tp) {
+            const int off_rows = halo_v + tap.shift0 + tp * tap.shift_step;   // first row of this tap's 128-row view
+            // A view that starts 25 rows into the TMA-written tile is NOT on the 1024-byte repeat of the 128-byte swizzle.
+            // Measured on B200: the plain descriptor (matrix base offset 0) is exact, the one with base offset
+            // (start >> 7) & 7 is wrong -- the swizzle XOR is a function of the absolute shared-memory address bits, for
+            // the TMA write and for the MMA read alike, so any 128-byte-row offset just works.
+            const uint32_t a_tap = a_addr + (uint32_t)off_rows * 128u;
+            const uint32_t b_tap = p2r_smem_u32(smem + tp * 8192);
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              const uint64_t adesc = make_desc(a_tap + k * 32, 16, 1024);
+              const uint64_t bdesc = B_MN ? make_desc(b_tap + k * 16 * 128, GEMM_BLOCK_K * 128, 1024)
+                                          : make_desc(b_tap + k * 32, 16, 1024);
+              umma_bf16(tmem_acc, adesc, bdesc, idesc, (tp | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty + s);
+          umma_commit(tmem_full + as);
+          trace_mark(tr, 1, t, 2);
+        }
+      }
+    } else if (TAP == 4) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(GEMM_BLOCK_M, 192, 1, 1);
+        const uint32_t zero_addr = p2r_smem_u32(smem + S::STAGES * stage4_bytes);
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % S::STAGES;
+          p2r_mbar_wait(full + s, (uint32_t)(i / S::STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = p2r_smem_u32(smem + s * stage4_bytes);
+          const uint32_t b_addr = a_addr + DW4_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // M block 1 (rows 64..127) = the shared zero block: leading byte offset = its distance from this stage's tile
+            const uint64_t adesc = make_desc(a_addr + k * 16 * 128, zero_addr - a_addr, 1024);
+            const uint64_t bdesc = make_desc(b_addr + k * 16 * 128, GEMM_BLOCK_K * 128, 1024);
+            umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty + s);
+        }
+        umma_commit(tmem_full);
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(GEMM_BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -223,28 +355,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     constexpr bool do_stats = STATS && !ATOMIC;   // (a template flag: the extra registers stay out of the plain kernels)
     if (TS) {
       // ---- TMA-store epilogue: TMEM -> registers -> bias / ReLU / bf16 -> swizzled 32 x 64 staging tile -> bulk store
+      // PAIRED (TAP == 3, 8 epilogue warps): two warps share a TMEM lane quarter and its staging tile; warp `half` converts
+      // the 32 columns [32 half, 32 half + 32) and sums rows [16 half, 16 half + 16) for the statistics -- the 4-warp
+      // epilogue was the longest stage of the halo kernels (2 CTAs x 4 warps per SM, issue slots 45 % busy).
+      constexpr bool PAIRED = TAP == 3;
+      constexpr int EPI_THREADS = PAIRED ? 256 : 128;
       const int et = threadIdx.x - 64;
+      const int half = PAIRED ? ((warp - 2) >> 2) : 0;
+      const int ew = PAIRED ? (warp - 2) : q;                 // slot of this warp in the final reduction
       uint8_t* stg = staging + q * (32 * 128);
       float ts00 = 0.f, ts01 = 0.f, ts10 = 0.f, ts11 = 0.f;   // sum / sum of squares of channels 2 lane, 2 lane + 1
+      long long* tr = (PAIRED && blockIdx.y == 1 && blockIdx.x == 0 && warp == 2 && lane == 0) ? g_tconv_trace : nullptr;
+      // the bias of this CTA's column tile, once (every m-tile of the CTA has the same n0)
+      const float* sb = sbias;
+      for (int c = et; c < BLOCK_N; c += EPI_THREADS) sbias[c] = (bias != nullptr && n0 + c < N) ? __ldg(bias + n0 + c) : 0.f;
+      if (PAIRED) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int t = 0; t < ntiles; ++t) {
         const int as = t % ACC;
         const int row0 = (tile0 + t) * GEMM_BLOCK_M + q * 32;
         const int ncols = min(BLOCK_N, N - n0);
-        float* sb = sbias + as * BLOCK_N;
-        for (int c = et; c < BLOCK_N; c += 128) sb[c] = (bias != nullptr && n0 + c < N) ? __ldg(bias + n0 + c) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        trace_mark(tr, 2, t, 0);
+        trace_mark(tr, 2, t, 1);
         p2r_mbar_wait(tmem_full + as, (uint32_t)(t / ACC) & 1u);
         tc_fence_after();
+        trace_mark(tr, 2, t, 2);
 #pragma unroll 1
         for (int g0 = 0; g0 < ncols; g0 += 64) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            if (PAIRED && h != half) continue;
             const int c0 = g0 + 32 * h;
             float f[32];
             if (c0 < ncols) {   // (warp-uniform)
               uint32_t v[32];
               tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
-              if (c0 + 32 >= ncols) {   // last read of this accumulator buffer
+              if (PAIRED || c0 + 32 >= ncols) {   // last read of this accumulator buffer (by this warp)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) p2r_mbar_arrive(tmem_empty + as);
@@ -259,7 +405,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = 0.f;
             }
-            if (h == 0) {   // the previous bulk store must have finished reading the staging tile
+            if (PAIRED) {   // the previous bulk store has read the staging tile and the partner is done summing it
+              if (half == 0 && lane == 0) tma_store_wait_read();
+              asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+              trace_mark(tr, 2, t, 3);
+            } else if (h == 0) {   // the previous bulk store must have finished reading the staging tile
               if (lane == 0) tma_store_wait_read();
               __syncwarp();
             }
@@ -280,8 +430,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           p2r_fence_proxy_async();
           __syncwarp();
-          if (lane == 0) tma_store_2d(&tma_c, stg, n0 + g0, row0);   // rows >= M / columns >= N are clipped
-          if (do_stats) {
+          trace_mark(tr, 2, t, 4);
+          if (PAIRED) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");      // both halves of the tile are staged
+          if (lane == 0 && half == 0) tma_store_2d(&tma_c, stg, n0 + g0, row0);   // rows >= M / columns >= N are clipped
+          trace_mark(tr, 2, t, 5);
+          if (do_stats && PAIRED) {
+            // (all loads first: with a data-dependent trip count the compiler kept one shared-memory round trip per row,
+            // 28 ns each in the in-kernel timeline)
+            const int r_lo = 16 * half;
+            const int rows_valid = min(32, M - row0);
+            uint32_t wd[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = r_lo + i;
+              wd[i] = r < rows_valid ? *reinterpret_cast<const uint32_t*>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float lo = __uint_as_float(wd[i] << 16), hi = __uint_as_float(wd[i] & 0xffff0000u);
+              ts00 += lo;
+              ts01 = fmaf(lo, lo, ts01);
+              ts10 += hi;
+              ts11 = fmaf(hi, hi, ts11);
+            }
+          } else if (do_stats) {
             const int rows_valid = min(32, M - row0);
 #pragma unroll 8
             for (int r = 0; r < rows_valid; ++r) {
@@ -293,6 +465,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               ts11 = fmaf(hi, hi, ts11);
             }
           }
+          trace_mark(tr, 2, t, 6);
         }
       }
       if (lane == 0) tma_store_wait_all();
@@ -300,16 +473,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_before();
       if (do_stats) {
         float* red = reinterpret_cast<float*>(smem);   // the ring is idle: every MMA of this CTA has completed
-        red[(q * 4 + 0) * 32 + lane] = ts00;
-        red[(q * 4 + 1) * 32 + lane] = ts01;
-        red[(q * 4 + 2) * 32 + lane] = ts10;
-        red[(q * 4 + 3) * 32 + lane] = ts11;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int k = q;
-        const float tot = red[(0 * 4 + k) * 32 + lane] + red[(1 * 4 + k) * 32 + lane] + red[(2 * 4 + k) * 32 + lane] +
-                          red[(3 * 4 + k) * 32 + lane];
-        const int copy = (int)((blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)ex.stat_copies);
-        atomicAdd(ex.stats + ((size_t)copy * 2 + (k & 1)) * 64 + 2 * lane + (k >> 1), (double)tot);
+        red[(ew * 4 + 0) * 32 + lane] = ts00;
+        red[(ew * 4 + 1) * 32 + lane] = ts01;
+        red[(ew * 4 + 2) * 32 + lane] = ts10;
+        red[(ew * 4 + 3) * 32 + lane] = ts11;
+        if (PAIRED) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (half == 0) {
+          const int k = q;
+          float tot = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < (PAIRED ? 8 : 4); ++w8) tot += red[(w8 * 4 + k) * 32 + lane];
+          const int copy = (int)((blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)ex.stat_copies);
+          atomicAdd(ex.stats + ((size_t)copy * 2 + (k & 1)) * 64 + 2 * lane + (k >> 1), (double)tot);
+        }
       }
     } else {
     // statistics accumulators: st[h][r] belongs to channel 32 h + 16 r + (lane & 15); lanes < 16 hold the sum, lanes
@@ -895,6 +1072,21 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 }
 
 
+extern "C" int p2r_debug_tconv_trace(long long* device_buffer) {
+  return cudaMemcpyToSymbol(g_tconv_trace, &device_buffer, sizeof(device_buffer)) == cudaSuccess ? 0 : -1;
+}
+
+// P2R_TCONV_HALO: 1 (default) the halo-tile forward / input-gradient kernels and the six-stage weight gradient, 0 the
+// three-view kernels of round 1
+static int tconv_halo_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("P2R_TCONV_HALO");
+    v = e == nullptr ? 1 : atoi(e);
+  }
+  return v;
+}
+
 static bool ts_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -916,9 +1108,13 @@ static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* 
   } else splits = 1;
   // TMA-store epilogue for bf16 outputs of the 64- and 256-wide tilings (the memory-bound point-MLP / temporal-conv
   // GEMMs; with 128 / 160 columns the extra staging memory would cost the second co-resident CTA)
-  constexpr bool TS_OK = (BLOCK_N == 64 || BLOCK_N == 256) && TAP != 2;
+  constexpr bool TS_OK = (BLOCK_N == 64 || BLOCK_N == 256) && TAP != 2 && TAP != 4;
   const bool ts = TS_OK && c_dtype == 1 && splits == 1 && ex.tile_mask == nullptr && ldc % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(C) % 16) == 0 && ts_enabled();
+  if (TAP == 3 && !ts) {
+    p2r_set_last_error("p2r_tconv_bf16: the halo kernels need the TMA-store epilogue (bf16 output, 16-byte aligned)", -1);
+    return -1;
+  }
   CUtensorMap mc = ma;
   if (ts && make_map(&mc, C, N, M, ldc, 32)) return -1;
   // several m-tiles per CTA when there are many more tiles than CTA slots: barrier / TMEM set-up is amortised and the
@@ -931,20 +1127,34 @@ static int launch_with_maps(const CUtensorMap& ma, const CUtensorMap& mb, void* 
     if (tpc < 1) tpc = 1;
     if (tpc > 8) tpc = 8;
   }
+  if (TAP == 3) {   // persistent: one wave of 2 CTAs per SM walks all tiles (set-up / weights / tail once per CTA)
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("P2R_TCONV_TPC");
+      forced = e == nullptr ? 0 : atoi(e);
+    }
+    tpc = forced > 0 ? forced : (int)p2r_ceil_div(tiles_m * tiles_n, (long long)P2R_SM_COUNT * 2);
+    if (tpc < 1) tpc = 1;
+  }
   dim3 grid((unsigned)tiles_n, (unsigned)p2r_ceil_div(tiles_m, tpc), splits);
 #define GEMM_GO(OutT, ATOMIC, STATS, TS)                                                                        \
   do {                                                                                                          \
     using SS = GemmSmem<BLOCK_N, NSTAGE, TS>;                                                                   \
     auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT, ATOMIC, TAP, NSTAGE, STATS, TS>;                    \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::TOTAL);                         \
-    kern<<<grid, GEMM_THREADS, SS::TOTAL, st>>>(ma, mb, mc, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc, ex); \
+    const int v_rows = tap.shift_step < 0 ? -tap.shift_step : tap.shift_step;                                   \
+    const int smem_bytes = TAP == 3 ? HALO_W_BYTES + HALO_STAGES * halo_tile_bytes(v_rows) + SS::STAGING_BYTES + \
+                                          SS::BIAS_BYTES + 1024 + 256                                           \
+                         : (TAP == 4 ? SS::STAGES * DW4_STAGE_BYTES + DW4_A_BYTES + 1024 + 256                  \
+                                     : SS::TOTAL);                                                              \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);                        \
+    kern<<<grid, TAP == 3 ? GEMM_THREADS + 128 : GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, (OutT*)C, ldc, M, N, K, bias, relu, kps, tap, tpc, ex); \
   } while (0)
   if (ex.stats != nullptr) {
-    if (A_MN || B_MN || TAP == 2 || splits > 1 || c_dtype != 1) {
+    if (A_MN || B_MN || TAP == 2 || TAP == 4 || splits > 1 || c_dtype != 1) {
       p2r_set_last_error("p2r_gemm_bf16_ex: fused statistics need K-major operands, bf16 output, no split-K", -1);
       return -1;
     }
-    if (!A_MN && !B_MN && TAP != 2) {
+    if (!A_MN && !B_MN && TAP != 2 && TAP != 4) {
       if (TS_OK && ts) GEMM_GO(__nv_bfloat16, false, true, TS_OK);
       else GEMM_GO(__nv_bfloat16, false, true, false);
     }
@@ -1000,23 +1210,30 @@ extern "C" int p2r_tconv_bf16(int mode, const void* act, const void* w, const vo
   const int pad = (KT - 1) / 2;
   const int M = B * rows;
   CUtensorMap ma, mb;
+  // one halo tile per 128 output rows instead of three shifted views (see TAP == 3 above): KT = 3, box <= 256 rows
+  const bool halo = KT == 3 && V >= 1 && GEMM_BLOCK_M + 2 * V <= 256 && tconv_halo_mode() != 0 && ts_enabled() &&
+                    (reinterpret_cast<uintptr_t>(out) % 16) == 0;
   if (mode == 0) {
-    if (make_map3(&ma, act, Ci, rows, B, GEMM_BLOCK_M)) return -1;
+    if (make_map3(&ma, act, Ci, rows, B, halo ? GEMM_BLOCK_M + 2 * V : GEMM_BLOCK_M)) return -1;
     if (make_map(&mb, w, (long long)KT * Ci, Co, (long long)KT * Ci, 64)) return -1;
     const TapArgs tap = {Ci / 64, rows, Ci, -pad * V, V};
     const GemmExtra ex = {nullptr, 0, nullptr, stats, stat_copies};
+    if (halo) return launch_with_maps<64, false, false, 3, 4>(ma, mb, out, Co, 1, M, Co, KT * Ci, bias, 0, 1, tap, st, ex);
     return launch_with_maps<64, false, false, 1, 2>(ma, mb, out, Co, 1, M, Co, KT * Ci, bias, 0, 1, tap, st, ex);
   }
   if (mode == 1) {
-    if (make_map3(&ma, act, Co, rows, B, GEMM_BLOCK_M)) return -1;
+    if (make_map3(&ma, act, Co, rows, B, halo ? GEMM_BLOCK_M + 2 * V : GEMM_BLOCK_M)) return -1;
     if (make_map(&mb, w, Ci, (long long)KT * Co, Ci, GEMM_BLOCK_K)) return -1;
     const TapArgs tap = {Co / 64, rows, Co, pad * V, -V};
+    if (halo) return launch_with_maps<64, false, true, 3, 4>(ma, mb, out, Ci, 1, M, Ci, KT * Co, nullptr, 0, 1, tap, st);
     return launch_with_maps<64, false, true, 1, 2>(ma, mb, out, Ci, 1, M, Ci, KT * Co, nullptr, 0, 1, tap, st);
   }
   // mode 2: dW2[Co, KT*Ci] = dy^T . shifted(x)
+  const bool deep_dw = KT == 3 && tconv_halo_mode() != 0;
   if (make_map(&ma, other, Co, M, Co, GEMM_BLOCK_K)) return -1;          // dy as MN-major A: inner = Co, rows = m
   if (make_map3(&mb, act, Ci, rows, B, GEMM_BLOCK_K)) return -1;         // x as MN-major B, 3-D
   const TapArgs tap = {1, rows, Ci, -pad * V, V};
+  if (deep_dw) return launch_with_maps<192, true, true, 4, 6>(ma, mb, out, KT * Ci, 0, Co, KT * Ci, M, nullptr, 0, splits, tap, st);
   // KT = 3: ONE 192-column tile holds all three taps, so dy is streamed once (not once per tap) and a split is a single
   // CTA: 32 KB instead of 48 KB through L2 -> SM per 64 reduction rows
   if (KT == 3) return launch_with_maps<192, true, true, 2, 4>(ma, mb, out, KT * Ci, 0, Co, KT * Ci, M, nullptr, 0, splits, tap, st);

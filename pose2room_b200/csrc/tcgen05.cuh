@@ -80,6 +80,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// (The matrix base offset, bits [49,52), stays 0 even for a view that starts a few 128-byte rows into a larger
+// TMA-written tile: measured on B200, the swizzle is applied on absolute shared-memory address bits -- see the halo
+// temporal-conv path in gemm_sm100.cu.)
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b format BF16 = 1 @7/@10,
 // a_major @15, b_major @16 (1 = MN-major), N>>3 @17, M>>4 @24.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
