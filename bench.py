@@ -30,6 +30,7 @@ B_PER_GPU, T_FRAMES, JOINTS = 32, 1024, 25
 # in the 126 MB L2 when the kernel ends); the weight-gradient GEMM: 214.4 MB (its operands once: 209.7 MB + dW 10 MB)
 GCN_FWD_DRAM_BYTES_NCU = 109.065e6 + 66.726e6
 GCN_DW_DRAM_BYTES_NCU = 214.43e6
+GCN_DW_PAIR_DRAM_BYTES_NCU = 231.39e6 + 14.04e6
 # algorithmic (conv 64->704 + einsum, the reference's formulation) forward FLOPs of ONE graph convolution for ONE
 # sequence at T=1024, J=25: (13.84 + 5.41) GFLOP / 6 blocks  (SURVEY.md section 8d / BASELINE.md section 3)
 GCN_ALGO_GFLOP_PER_SEQ = (13.84 + 5.41) / 6.0
@@ -866,9 +867,15 @@ def main():
               "avg_launch_ms": t_dw, "launches_timed": len(gdw), "executed_over_dense": live_fraction("dw"),
               "executed_tflops": 2.0 * gdw[0][1] * vj * vj * live_fraction("dw") / (t_dw * 1e-3) / 1e12,
               "share_of_step": t_dw * 6 / (ms / args.steps),
-              "traffic": GCN_DW_DRAM_BYTES_NCU if (precision == "bf16" and B == B_PER_GPU) else None,
-              "l2_to_sm_bytes": 1.83e9 if (precision == "bf16" and B == B_PER_GPU) else None,
-              "note": "L2 -> SM bound: l1tex__m_xbar2l1tex_read_bytes 1.83 GB per launch for 0.21 GB of DRAM traffic (128 x 128 tiles)"}
+              "traffic": None, "l2_to_sm_bytes": None}
+        if precision == "bf16" and B == B_PER_GPU:     # ncu --set full of the same launch, profiles/r02_ncu_hot_kernels_summary.txt
+            if getattr(_g, "USE_PAIR_DW", False):
+                dw.update({"traffic": GCN_DW_PAIR_DRAM_BYTES_NCU, "l2_to_sm_bytes": 1.376e9,
+                           "note": "CTA-pair kernel, 256 x 256 tiles (41 of 49 live), reduce-add split-K: tensor pipe 85.7 % active under ncu; "
+                                   "1.38 GB through L2 -> SM per launch for 0.245 GB of DRAM traffic"})
+            else:
+                dw.update({"traffic": GCN_DW_DRAM_BYTES_NCU, "l2_to_sm_bytes": 1.83e9,
+                           "note": "L2 -> SM bound: l1tex__m_xbar2l1tex_read_bytes 1.83 GB per launch for 0.21 GB of DRAM traffic (128 x 128 tiles)"})
         dw["frac"] = dw["achieved"] / dw["peak"]
         roofline["other_kernels"] = [dw]
     ops.PROFILE["log"] = []

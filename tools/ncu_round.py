@@ -26,6 +26,7 @@ for _ in range(2):
     dx = gemm_sm100.gemm_pair(dy, w, block_n=256, kb_list=sp.kb_list(256, True, dev))                        # input gradient
     dx = gemm_sm100.gemm_pair(dy, w, block_n=256, kb_list=sp.kb_list(256, True, dev), accumulate_into=dx)    # ... added onto the residual gradient
     dw = gemm_sm100.gemm(dy, x, True, True, out_dtype=torch.float32, block_n=128, tile_mask=sp.tile_mask(128, 128, dev))
+    dw = gemm_sm100.gemm_pair_dw(dy, x, sp.tile_list(256, 256, dev))                                          # the default since round 2
 rows = torch.randn(M * V, C, device=dev).bfloat16().requires_grad_(True)
 res = torch.randn(M * V, C, device=dev).bfloat16()
 bn = nn.BatchNorm2d(C).to(dev)
