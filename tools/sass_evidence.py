@@ -1,5 +1,5 @@
 """Static evidence for profiles/: which Blackwell instructions each kernel of libp2r_b200.so contains and what it costs
-in registers / shared memory (run here, on the CPU box: `python tools/sass_evidence.py profiles/r01_sass_evidence.txt`).
+in registers / shared memory (run here, on the CPU box: `python tools/sass_evidence.py profiles/r02_sass_evidence.txt`).
 
 Per kernel (cuobjdump -sass / -res-usage of the shipped sm_100a library): counts of UTC*MMA (tcgen05.mma), LDTM / STTM
 (tcgen05.ld / st), UTMALDG / UTMASTG / UTMAREDG (tensor TMA load / store / reduce), UBLKCP (1-D bulk TMA), LDGSTS
