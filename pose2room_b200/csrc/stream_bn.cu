@@ -85,7 +85,10 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
   // (row stride 72 floats + a per-lane rotation of the channel order make the 32 lanes of a warp hit 32 banks)
   constexpr int CS_LD = 72, CS_MAXP = 32;
   __shared__ float cs_tab[MODE == BWD_APPLY ? CS_MAXP * CS_LD : 1];
-  const bool do_cs = MODE == BWD_APPLY && a.colsum != nullptr;
+  // period == 1 (plain column sums of dx: the bias gradient of the conv in front of this BatchNorm) needs no table: every
+  // thread sums its own 8 channels in registers (acc1, unused in this mode) and the CTA folds them like the STATS modes
+  const bool do_cs1 = MODE == BWD_APPLY && a.colsum != nullptr && a.period == 1;
+  const bool do_cs = MODE == BWD_APPLY && a.colsum != nullptr && !do_cs1;
   if (do_cs)
     for (int i = tid; i < CS_MAXP * CS_LD; i += SB_THREADS) cs_tab[i] = 0.f;
   if (tid == 0) {
@@ -207,6 +210,12 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
           if (a.out[1]) *reinterpret_cast<uint4*>(a.out[1] + go) = pack8(p);
           const uint4 gp = pack8(g);
           *reinterpret_cast<uint4*>(a.out[0] + go) = gp;
+          if (do_cs1) {     // sums of the STORED (bf16) dx, like a separate pass over dx would see them
+            float gr[8];
+            unpack8(gp, gr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc1[i] += gr[i];
+          }
           if (do_cs) {      // sums of the STORED (bf16) dx, like a separate pass over dx would see them
             float gr[8];
             unpack8(gp, gr);
@@ -231,6 +240,26 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stream_bn_kernel(const StreamAr
         const float v = cs_tab[(i / SB_C) * CS_LD + (i % SB_C)];
         if (v != 0.f) atomicAdd(a.colsum + i, (double)v);
       }
+    }
+  }
+  if (MODE == BWD_APPLY && do_cs1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc1[i] += __shfl_xor_sync(0xffffffffu, acc1[i], 8);
+      acc1[i] += __shfl_xor_sync(0xffffffffu, acc1[i], 16);
+    }
+    P2R_NAMED_BARRIER_SYNC_1_256();   // every consumer is past its last tile: the ring is free
+    float* red = reinterpret_cast<float*>(sb_smem);  // [8 warps][64 channels]
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp * 64 + c0 + i] = acc1[i];
+    }
+    P2R_NAMED_BARRIER_SYNC_1_256();
+    if (tid < 64) {
+      double t = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += (double)red[w8 * 64 + tid];
+      atomicAdd(a.colsum + tid, t);
     }
   }
   if (MODE == STATS_FWD || MODE == STATS_BWD) {

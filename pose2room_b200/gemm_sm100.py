@@ -226,6 +226,11 @@ class _TemporalConvTC(torch.autograd.Function):
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
         dy = dy if dy.is_contiguous() else dy.contiguous()
+        # [1, Co] sums of dy left by the backward of the BatchNorm that follows this conv (ops.batchnorm_act(...,
+        # colsum_period=1)): the bias gradient without another pass over dy
+        fused_cs = ops._COLSUM.pop(dy.data_ptr(), None)
+        if fused_cs is not None and fused_cs.numel() != co:
+            fused_cs = None
         dx = dw = db = None
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:
@@ -247,7 +252,7 @@ class _TemporalConvTC(torch.autograd.Function):
                                   kt, v, None, max(1, min(148, m // 4096)), None, 1, _stream())
                         gw = dw2.reshape(co, kt, ci).permute(0, 2, 1).unsqueeze(-1)
                     if need_b:
-                        gb = ops._col_sum(dy, at_join=True)
+                        gb = ops._to_float_at_join(fused_cs.reshape(-1)) if fused_cs is not None else ops._col_sum(dy, at_join=True)
                     return [gw, gb]
                 ops._defer(weight_grads, [tw if need_w else None, tb if need_b else None], (dy, x))
                 return dx, None, None, None, None

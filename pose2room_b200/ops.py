@@ -618,6 +618,7 @@ _COLSUM = {}
 # OFF by default: the kernel is correct in isolation and in an eager step (tests), but bench.py's
 # back-to-back warm-up steps did not finish with it enabled (two runs, cause not established) -- see DESIGN.md section 3.
 _FUSED_COLSUM = os.environ.get("P2R_FUSED_COLSUM", "0") != "0"
+_FUSED_COLSUM1 = os.environ.get("P2R_FUSED_COLSUM1", "1") != "0"
 
 
 _GCN_PREBUILT = {}
@@ -828,7 +829,10 @@ class _BatchNormAct(Function):
         sums = zeros_ws((2, c), torch.float64, dev)
         period = ctx.colsum_period
         cs = None
-        if 0 < period <= 32 and DEFER["on"] and _FUSED_COLSUM and _lib.query("p2r_stream_bn_supported", dt, m, c) == 1:
+        # period 1 (plain column sums: the bias gradient of the conv right in front of this BatchNorm) costs the pass
+        # nothing -- per-thread register sums -- and is on by default; longer periods go through shared-memory atomics
+        if 0 < period <= 32 and DEFER["on"] and (_FUSED_COLSUM or (period == 1 and _FUSED_COLSUM1)) and \
+                _lib.query("p2r_stream_bn_supported", dt, m, c) == 1:
             cs = zeros_ws((period, c), torch.float64, dev)      # per-(row % period, channel) sums of dx, by-product
         with torch.cuda.device(dev):
             _lib.call("p2r_col_bwd_stats", dy.data_ptr(), x.data_ptr(), _ptr(y), dt, m, c, stats[0].data_ptr(),

@@ -89,7 +89,8 @@ class st_gcn_block(nn.Module):
         # BN + ReLU; its backward also leaves the per-(joint, channel) sums of dg = the graph conv's bias gradient
         h = ops.batchnorm_act(g.reshape(b * t * v, co), self.tcn[0], relu=True, sums=s1, colsum_period=v)
         y, s2 = ops.temporal_conv(h.reshape(b, t, v, co), self.tcn[2].weight, self.tcn[2].bias, want_stats=True)
-        out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res, sums=s2)                       # BN + res + ReLU
+        # BN + res + ReLU; its backward also leaves the column sums of dy = the temporal conv's bias gradient
+        out = ops.batchnorm_act(y, self.tcn[3], relu=True, residual=res, sums=s2, colsum_period=1)
         return out.reshape(b, t, v, co)
 
 

@@ -254,13 +254,15 @@ def test_embed_sum_fwd_bwd(cuda, dtype):
     assert torch.allclose(gpos.float(), want, rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-6)
 
 
-def test_bn_backward_fused_periodic_column_sums(cuda):
+@pytest.mark.parametrize("P", [25, 1])
+def test_bn_backward_fused_periodic_column_sums(cuda, P):
     """p2r_bn_bwd_apply with colsum / period: the per-(row % period, channel) sums of the dx it writes equal a separate
-    column sum over the stored bf16 dx (the graph convolution's bias gradient, 25 joints)."""
+    column sum over the stored bf16 dx (period 25: the graph convolution's bias gradient over the 25 joints, shared-memory
+    table; period 1: the temporal conv's bias gradient, per-thread register sums)."""
     from pose2room_b200 import _lib
     if _lib.query("p2r_stream_bn_supported", 1, 25 * 2048, 64) != 1:
         pytest.skip("streaming kernels disabled")
-    M, C, P = 25 * 2048 + 25 * 3, 64, 25
+    M, C = 25 * 2048 + 25 * 3, 64
     g = torch.Generator().manual_seed(77)
     x = torch.randn(M, C, generator=g).to(cuda).bfloat16()
     dy = torch.randn(M, C, generator=g).to(cuda).bfloat16()

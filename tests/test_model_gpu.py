@@ -198,6 +198,42 @@ def test_overlapped_weight_gradients_match_plain_backward(cuda, golden):
         gemm_sm100.uninstall()
 
 
+def test_deferred_gradients_direct_and_through_autograd_agree(cuda, golden):
+    """At the join of ops.overlap_weight_grads() a parameter takes its deferred gradient directly (no AccumulateGrad copy);
+    with that switched off, or with a tensor hook on the parameter, it goes through autograd.  Same gradients either way,
+    the hook fires, and a second backward without zero_grad accumulates."""
+    from pose2room_b200 import gemm_sm100, ops, synthetic
+    gemm_sm100.install()
+    saved = ops._DIRECT_LEAF_GRADS
+    try:
+        out = []
+        for direct in (True, False):
+            ops._DIRECT_LEAF_GRADS = direct
+            net = H.make_product("bl", "train", golden, precision="bf16").to(cuda)
+            net.train()
+            data = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v)
+                    for k, v in synthetic.make_batch(4, 1024, 25, seed=5).items()}
+            fired = []
+            hooked = net.backbone.st_gcn_networks[2].gcn.conv.weight
+            hooked.register_hook(lambda g: fired.append(g.shape))
+            for _ in range(2):                       # two backward passes, no zero_grad in between: gradients add up
+                torch.manual_seed(11)
+                with ops.overlap_weight_grads():
+                    loss = net.loss(net(data), data)["total"]
+                    loss.backward()
+            torch.cuda.synchronize()
+            assert len(fired) == 2, "the tensor hook of a deferred-gradient parameter did not fire"
+            out.append({k: p.grad.detach().double().clone() for k, p in net.named_parameters() if p.grad is not None})
+        assert set(out[0]) == set(out[1])
+        for k in out[0]:
+            a, b = out[0][k], out[1][k]
+            scale = a.abs().max().item() + 1e-12
+            assert (a - b).abs().max().item() <= 2e-3 * scale, (k, (a - b).abs().max().item(), scale)
+    finally:
+        ops._DIRECT_LEAF_GRADS = saved
+        gemm_sm100.uninstall()
+
+
 def test_weight_shadows_change_nothing(cuda, golden):
     """ops.register_weight_shadows (one multi-tensor fp32 -> bf16 copy per step instead of a cast per layer): the first
     step's loss bit for bit and its gradients to atomics noise; after an optimiser step the shadows must hold the NEW

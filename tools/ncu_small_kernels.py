@@ -129,34 +129,9 @@ for _ in range(2):
     ops.embed_sum(sk, torch.randn(B * T, 20, 64, device=dev).bfloat16())
 torch.cuda.synchronize()
 
-# ---- round-2 additions: first embed layer on fp32 coordinates, seed-frame pick, odd-width / periodic column sums,
-# ---- the graph-conv weight build and its gradient fold ----------------------------------------------------------------
-import torch.nn as nn
-xyz = torch.randn(B * T * J, 3, device=dev)
-w3 = (torch.randn(64, 3, device=dev) / 3 ** 0.5).requires_grad_(True)
-bn_e = nn.BatchNorm1d(64).to(dev).train()
-frames = torch.randn(B, T, J * 64, device=dev).bfloat16().requires_grad_(True)
-picks = torch.sort(torch.randint(0, T, (B, 512), device=dev), dim=1)[0]
-odd = torch.randn(16384, 259, device=dev).bfloat16()
-wide = torch.randn(B * T, J * 64, device=dev).bfloat16()
-from pose2room_b200.p2rnet.graph import layout_for_joints, spatial_adjacency
-A_e = torch.tensor(spatial_adjacency(layout_for_joints(J), max_hop=5), dtype=torch.float32, device=dev)
-cw = torch.randn(A_e.shape[0] * 64, 64, device=dev) / 8
-cb = torch.randn(A_e.shape[0] * 64, device=dev)
-for _ in range(2):
-    y_e = ops.embed_l1(xyz, w3, bn_e)
-    y_e.backward(torch.randn_like(y_e))
-    sel = ops.select_rows(frames, picks)
-    sel.backward(torch.randn_like(sel))
-    ops._col_sum(odd)
-    ops._col_sum(wide)
-    built = ops._gcn_build(cw, cb, A_e)
-    dwe = torch.randn(J * 64, J * 64, device=dev)
-    dbe = torch.randn(J * 64, device=dev)
-    d_w, d_b, d_a = torch.empty_like(cw), torch.empty_like(cb), torch.empty_like(A_e)
-    _lib.call("p2r_gcn_reduce_weight_grad", dwe.data_ptr(), dbe.data_ptr(), cw.data_ptr(), cb.data_ptr(), A_e.data_ptr(),
-              A_e.shape[0], J, 64, 64, d_w.data_ptr(), d_b.data_ptr(), d_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
-torch.cuda.synchronize()
+# ---- round-2 additions (first embed layer, seed-frame pick, odd-width / periodic column sums, graph-conv weight build and
+# ---- gradient fold): tools/ncu_new_kernels.py, also runnable on its own
+import ncu_new_kernels  # noqa: E402,F401
 
 # ---- eval kernels on 125 scenes of the 1000-scene set (BASELINE config #5) --------------------------------------------
 cfg = P2RConfig(mode="test", joint_num=J).eval_config
