@@ -866,15 +866,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if (STATS) {
           // column sums straight from the staged bf16 tile: lane l owns columns 2l, 2l+1 of this 64-column group
           // (= channels 2l, 2l+1: n0 + g0 is a multiple of 64); one conflict-free 4-byte read per row
+          // (eight loads, then their sums: with the row count as the trip count the compiler kept one shared-memory round
+          // trip per row -- 28 ns each in the temporal-conv timeline)
           const int rows_valid = min(32, M - row0);
-#pragma unroll 8
-          for (int r = 0; r < rows_valid; ++r) {
-            const uint32_t wd = *reinterpret_cast<const uint32_t*>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-            const float lo = __uint_as_float(wd << 16), hi = __uint_as_float(wd & 0xffff0000u);
-            st00 += lo;
-            st01 = fmaf(lo, lo, st01);
-            st10 += hi;
-            st11 = fmaf(hi, hi, st11);
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint32_t wd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = c8 * 8 + i;
+              wd[i] = r < rows_valid ? *reinterpret_cast<const uint32_t*>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float lo = __uint_as_float(wd[i] << 16), hi = __uint_as_float(wd[i] & 0xffff0000u);
+              st00 += lo;
+              st01 = fmaf(lo, lo, st01);
+              st10 += hi;
+              st11 = fmaf(hi, hi, st11);
+            }
           }
         }
       }
