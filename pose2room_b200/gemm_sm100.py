@@ -188,6 +188,35 @@ def gemm_pair_dw(dz, x, tile_list=None, splits=0):
     return dw
 
 
+_TCONV_PREBUILT = {}
+ops._STEP_END_HOOKS.append(_TCONV_PREBUILT.clear)
+
+
+def _tconv_layouts(weight, bias):
+    """The two bf16 layouts of a (Co, Ci, KT, 1) temporal-conv weight the implicit GEMMs read -- forward [Co, KT*Ci]
+    (column dt*Ci + ci), input gradient [KT*Co, Ci] (row dt*Co + co) -- and the float32 bias."""
+    co, ci, kt, _ = weight.shape
+    wb = ops.bf16_weight(weight)[:, :, :, 0]
+    w2 = wb.permute(0, 2, 1).reshape(co, kt * ci).contiguous()
+    wt = wb.permute(2, 0, 1).reshape(kt * co, ci).contiguous()
+    return w2, wt, (bias.float().contiguous() if bias is not None else None)
+
+
+def tconv_prebuild(convs):
+    """Lay the temporal-conv weights out NOW, on the current stream (a forked branch at the top of the forward: parameters
+    only), for the next temporal_conv() call with the same weight tensor; unused entries are dropped when the step ends."""
+    _TCONV_PREBUILT.clear()
+    out = []
+    with torch.no_grad():
+        for weight, bias in convs:
+            built = _tconv_layouts(weight.detach(), bias.detach() if bias is not None else None)
+            _TCONV_PREBUILT[weight.data_ptr()] = built
+            out.append(built)
+    if ops.DEFER["on"]:
+        ops.DEFER["keep"].append(out)
+    return out
+
+
 class _TemporalConvTC(torch.autograd.Function):
     """(KT x 1) temporal conv of st_gcn_block.tcn as implicit tensor-core GEMMs (forward, d input, d weight):
     three row-shifted TMA views of the SAME activation tensor instead of an unfold buffer."""
@@ -198,9 +227,9 @@ class _TemporalConvTC(torch.autograd.Function):
         b, t, v, ci = x.shape
         co, _, kt, _ = weight.shape
         x = x if x.is_contiguous() else x.contiguous()
-        w2 = ops.bf16_weight(weight)[:, :, :, 0].permute(0, 2, 1).reshape(co, kt * ci).contiguous()   # column = dt*Ci + ci
+        w2, wt, bias_f = _TCONV_PREBUILT.pop(weight.data_ptr(), None) or _tconv_layouts(weight, bias)
+        ctx.wt = wt
         y = torch.empty(b * t * v, co, dtype=torch.bfloat16, device=x.device)
-        bias_f = bias.float().contiguous() if bias is not None else None
         sums = None
         if want_stats and USE_FUSED_STATS and co == 64:
             sums = ops.zeros_ws((STAT_COPIES, 2, 64), torch.float64, x.device)
@@ -234,7 +263,7 @@ class _TemporalConvTC(torch.autograd.Function):
         dx = dw = db = None
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:
-                wt = ops.bf16_weight(weight)[:, :, :, 0].permute(2, 0, 1).reshape(kt * co, ci).contiguous()
+                wt = ctx.wt
                 dx = torch.empty(b, t, v, ci, dtype=torch.bfloat16, device=x.device)
                 _lib.call("p2r_tconv_bf16", 1, dy.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), b, t * v, ci, co, kt, v,
                           None, 1, None, 1, _stream())

@@ -194,6 +194,8 @@ class overlap_weight_grads:
         DEFER["bn_counted"] = set()
         _COLSUM.clear()
         _GCN_PREBUILT.clear()
+        for hook in _STEP_END_HOOKS:
+            hook()
         if exc_type is None:
             self.flush()
         else:
@@ -622,6 +624,7 @@ _FUSED_COLSUM1 = os.environ.get("P2R_FUSED_COLSUM1", "1") != "0"
 
 
 _GCN_PREBUILT = {}
+_STEP_END_HOOKS = []      # callables run when the multi-stream step context exits (caches of per-step prebuilt operands)
 
 
 def _gcn_build(conv_w, conv_b, a_eff):
