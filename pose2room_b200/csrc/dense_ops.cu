@@ -480,6 +480,15 @@ affine_act_kernel(long long total, int C, const T* __restrict__ x, const float* 
 
 // Vectorised variants require (256 * VEC) % C == 0, so a thread's channel offset is the same in every iteration of
 // the grid-stride loop and the per-channel coefficients live in registers (no per-element parameter loads).
+// Grid of the vectorised elementwise BatchNorm kernels: every thread first loads the per-channel constants of its 4 / 8
+// columns (up to 48 scalar loads + double arithmetic), so a thread should own several vectors -- with one vector per thread
+// the 16 384 x 256 passes of the vote MLP took 33 us for 24 MB.
+static inline int vec_grid(long long nvec) {
+  const long long blocks = (nvec + 255) / 256;
+  const long long cap = (long long)P2R_SM_COUNT * 4;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 affine_act_vec_kernel(long long nvec, int C, const T* __restrict__ x, const float* __restrict__ scale,
@@ -515,9 +524,9 @@ extern "C" int p2r_affine_act(const void* x, int dtype, long long M, int C, cons
   P2R_CHECK_ARG(relu_mask == nullptr, "p2r_affine_act (the ReLU bit mask needs p2r_stream_bn_supported(dtype, M, C))");
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, x, residual, y))
-    affine_act_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
+    affine_act_vec_kernel<float><<<vec_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(total / 4, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
   else if (dtype == 1 && vec_ok<__nv_bfloat16>(C, x, residual, y))
-    affine_act_vec_kernel<__nv_bfloat16><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 8, C, (const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y);
+    affine_act_vec_kernel<__nv_bfloat16><<<vec_grid(total / 8), 256, 0, (cudaStream_t)stream>>>(total / 8, C, (const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y);
   else if (dtype == 0)
     affine_act_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, (const float*)x, scale, shift, (const float*)residual, relu, (float*)y);
   else
@@ -633,9 +642,9 @@ extern "C" int p2r_bn_bwd_apply_ex(const void* dy, const void* x, const void* y,
   P2R_CHECK_ARG(colsum == nullptr, "p2r_bn_bwd_apply (fused column sums need p2r_stream_bn_supported(dtype, M, C))");
   const int grid = (int)min((long long)P2R_SM_COUNT * 16, (total + 255) / 256);
   if (dtype == 0 && vec_ok<float>(C, dy, x, y, dx, dres))
-    bn_bwd_apply_vec_kernel<float><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);
+    bn_bwd_apply_vec_kernel<float><<<vec_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(total / 4, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);
   else if (dtype == 1 && vec_ok<__nv_bfloat16>(C, dy, x, y, dx, dres))
-    bn_bwd_apply_vec_kernel<__nv_bfloat16><<<(int)min((long long)P2R_SM_COUNT * 16, (total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total / 8, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, shift);
+    bn_bwd_apply_vec_kernel<__nv_bfloat16><<<vec_grid(total / 8), 256, 0, (cudaStream_t)stream>>>(total / 8, C, 1.0 / (double)M, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, rstd, scale, s1, s2, relu, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, shift);
   else if (dtype == 0)
     bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(total, C, 1.0 / (double)M, (const float*)dy, (const float*)x, (const float*)y, mean, rstd, scale, s1, s2, relu, (float*)dx, (float*)dres, shift);
   else
@@ -828,15 +837,25 @@ select_rows_grad_kernel(int N, int C, int P, long long dst_rows, const T* __rest
   __shared__ int s_match[8][32];                 // the first 32 slots that picked this row, per warp
   int* match = s_match[threadIdx.x >> 5];
   int count = 0;
-  for (int p0 = 0; p0 < P; p0 += 32) {
-    const int p = p0 + lane;
-    const bool hit = p < P && __ldg(picks + p) == row;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      const int slot = count + __popc(m & ((1u << lane) - 1u));
-      if (slot < 32) match[slot] = p;
+  for (int pc = 0; pc < P; pc += 512) {          // 16 independent loads per lane, then their ballots: one round trip per
+    int pk[16];                                  // 512 picks instead of sixteen dependent ones
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int p = pc + 32 * k + lane;
+      pk[k] = p < P ? __ldg(picks + p) : -1;
     }
-    count += __popc(m);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const bool hit = pk[k] == row;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m != 0u) {
+        if (hit) {
+          const int slot = count + __popc(m & ((1u << lane) - 1u));
+          if (slot < 32) match[slot] = pc + 32 * k + lane;
+        }
+        count += __popc(m);
+      }
+    }
   }
   __syncwarp();
   if (count == 0) {
@@ -849,7 +868,20 @@ select_rows_grad_kernel(int N, int C, int P, long long dst_rows, const T* __rest
   } else if (count == 1 && C % VEC == 0) {
     const uint4* g4 = reinterpret_cast<const uint4*>(grad + ((size_t)b * P + match[0]) * C);
     uint4* d4 = reinterpret_cast<uint4*>(d);
-    for (int i = lane; i < C / VEC; i += 32) d4[i] = __ldg(g4 + i);
+    const int nv = C / VEC;
+    for (int i0 = 0; i0 < nv; i0 += 8 * 32) {    // up to eight 16-byte loads in flight per lane, then the stores
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + 32 * k + lane;
+        if (i < nv) v[k] = __ldg(g4 + i);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + 32 * k + lane;
+        if (i < nv) d4[i] = v[k];
+      }
+    }
   } else if (count <= 32 && C % VEC == 0 && sizeof(T) == 2) {
     // a frame picked several times (a standing person: arc-length sampling repeats the frame): 16-byte loads, the picks
     // of one chunk are independent loads, summed in slot order (deterministic)

@@ -384,6 +384,8 @@ class _Backend:
             dz, w = _pad_cols(dz, n8), _pad_rows(w, n8)
         n_out = w.shape[1]
         sp = sparsity if USE_SPARSITY else None
+        # (the CTA-pair kernel on the one wide dense layer, conv_joint's 256 -> 1600 input gradient, measured 7.04 ms per
+        # step against 7.00 with the 160-wide tiles: four k-blocks do not amortise its pipeline)
         if (n_out % 160 == 0 and n_out >= 640) or sp is not None:
             # graph-conv sized layers: a 5 MB transpose of W_eff buys the zero-waste 128x160 K-major tiling
             bn = GCN_BLOCK_N if sp is not None else 160

@@ -217,16 +217,18 @@ def parallel_branches(fns):
     if not DEFER["on"] or PROFILE["on"] or len(fns) < 2:
         return [fn() for fn in fns]
     main = torch.cuda.current_stream()
-    while len(DEFER["branch_streams"]) < len(fns) - 1:
+    while len(DEFER["branch_streams"]) < len(fns):
         DEFER["branch_streams"].append(torch.cuda.Stream())
     outs = [None] * len(fns)
-    for i in range(len(fns) - 1):
+    for i in range(len(fns)):
         DEFER["branch_streams"][i].wait_stream(main)          # fork point: before anything of this group is enqueued
-    outs[0] = fns[0]()                                        # host issue order = list order (RNG consumption order)
-    for i, fn in enumerate(fns[1:]):
+    # EVERY chain gets a branch stream, the first one too: in the backward autograd runs the chains in reverse issue order
+    # and accumulates their gradients of the shared input on the main stream as they arrive -- a chain that lives on the
+    # main stream is queued behind those accumulations, i.e. behind all the other chains (117 us in the step's timeline)
+    for i, fn in enumerate(fns):                              # host issue order = list order (RNG consumption order)
         with torch.cuda.stream(DEFER["branch_streams"][i]):
-            outs[i + 1] = fn()
-    for i in range(len(fns) - 1):
+            outs[i] = fn()
+    for i in range(len(fns)):
         main.wait_stream(DEFER["branch_streams"][i])
     DEFER["keep"].append(outs)
     return outs
