@@ -260,6 +260,13 @@ int p2r_gemm_bf16_pair_dw(int R, int N1, int N2, const void* dz, int ldz, const 
  * of y, i.e. the statistics of the BatchNorm2d that follows the conv (stgcn_layers.py:412).                        */
 int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, void* out, int B, int rows, int Ci,
                    int Co, int KT, int V, const float* bias, int splits, double* stats, int stat_copies, void* stream);
+/* AdamW over n float32 tensors in a few launches, capturable in a CUDA graph: the update rule of torch.optim.AdamW
+ * (amsgrad = False, maximize = False) that the reference's optimiser factory builds (models/optimizers.py:90).
+ * params / grads / exp_avg / exp_avg_sq: HOST arrays of n device pointers, numel: host array of n element counts;
+ * step: DEVICE float = number of updates already applied (read by every launch, incremented once at the end).    */
+int p2r_adamw_step(int n, const void* const* params, const void* const* grads, void* const* exp_avg,
+                   void* const* exp_avg_sq, const long long* numel, float* step, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, void* stream);
 /* Diagnostic (not part of the reference's interface): per-tile globaltimer stamps of one CTA of the halo temporal-conv
  * kernels into device_buffer[3 roles][64 tiles][8 events] (long long, device memory); NULL switches it off again. */
 int p2r_debug_tconv_trace(long long* device_buffer);

@@ -71,6 +71,8 @@ SIGNATURES = {
     "p2r_bn_bwd_apply_ex": [_vp, _vp, _vp, _c_int, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp,
                             _c_int, _vp, _vp, _vp],
     "p2r_debug_tconv_trace": [_vp],
+    "p2r_adamw_step": [_c_int, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                       ctypes.c_double, ctypes.c_double, _vp],
     "p2r_relu_bwd": [_vp, _vp, _c_int, _c_ll, _vp, _vp],
     "p2r_temporal_unfold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "p2r_temporal_fold": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
