@@ -262,7 +262,8 @@ int p2r_tconv_bf16(int mode, const void* act, const void* w, const void* other, 
                    int Co, int KT, int V, const float* bias, int splits, double* stats, int stat_copies, void* stream);
 /* AdamW over n float32 tensors in a few launches, capturable in a CUDA graph: the update rule of torch.optim.AdamW
  * (amsgrad = False, maximize = False) that the reference's optimiser factory builds (models/optimizers.py:90).
- * params / grads / exp_avg / exp_avg_sq: HOST arrays of n device pointers, numel: host array of n element counts;
+ * params / grads / exp_avg / exp_avg_sq: HOST arrays of n device pointers, numel: host array of n element counts
+ * (positive: float32 tensors; negative: -count elements of float64 -- parameter, gradient and moments alike);
  * step: DEVICE float = number of updates already applied (read by every launch, incremented once at the end).    */
 int p2r_adamw_step(int n, const void* const* params, const void* const* grads, void* const* exp_avg,
                    void* const* exp_avg_sq, const long long* numel, float* step, double lr, double beta1, double beta2,

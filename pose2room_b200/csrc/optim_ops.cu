@@ -21,16 +21,34 @@ struct AdamWChunk {
   const float* g[P2R_ADAMW_CHUNK];
   float* m[P2R_ADAMW_CHUNK];
   float* v[P2R_ADAMW_CHUNK];
-  long long numel[P2R_ADAMW_CHUNK];
+  long long numel[P2R_ADAMW_CHUNK];   // negative: a float64 tensor of -numel elements (P2RNet has one: gmm_heading.mdn.mu)
 };
 
 __global__ void __launch_bounds__(P2R_ADAMW_THREADS)
 adamw_chunk_kernel(const AdamWChunk c, const float* __restrict__ step, double lr, double beta1_d, double beta2_d, float eps,
                    double weight_decay) {
   const int t = blockIdx.y;
-  const long long n = c.numel[t];
+  const bool f64 = c.numel[t] < 0;
+  const long long n = f64 ? -c.numel[t] : c.numel[t];
   const long long e0 = ((long long)blockIdx.x * P2R_ADAMW_THREADS + threadIdx.x) * P2R_ADAMW_PER_THREAD;
   if (e0 >= n) return;
+  if (f64) {      // the same update in double, element by element
+    const double s = (double)__ldg(step) + 1.0;
+    const double bc2_sqrt = sqrt(1.0 - pow(beta2_d, s)), step_size = lr / (1.0 - pow(beta1_d, s));
+    double* p = reinterpret_cast<double*>(c.p[t]);
+    const double* g = reinterpret_cast<const double*>(c.g[t]);
+    double* m = reinterpret_cast<double*>(c.m[t]);
+    double* v = reinterpret_cast<double*>(c.v[t]);
+    for (long long e = e0; e < n && e < e0 + P2R_ADAMW_PER_THREAD; ++e) {
+      const double gg = g[e];
+      const double mm = m[e] + (gg - m[e]) * (1.0 - beta1_d);
+      const double vv = beta2_d * v[e] + (1.0 - beta2_d) * gg * gg;
+      m[e] = mm;
+      v[e] = vv;
+      p[e] = p[e] * (1.0 - lr * weight_decay) - step_size * (mm / (sqrt(vv) / bc2_sqrt + (double)eps));
+    }
+    return;
+  }
   // scalars in double like torch's Python side (1 - 0.999f is 1.3e-5 off 0.001), cast to float where torch casts
   const double s = (double)__ldg(step) + 1.0;
   const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, s));
@@ -82,7 +100,8 @@ adamw_chunk_kernel(const AdamWChunk c, const float* __restrict__ step, double lr
 
 __global__ void adamw_step_inc_kernel(float* step) { *step += 1.f; }
 
-// params / grads / exp_avg / exp_avg_sq: HOST arrays of n device pointers (float32, dense), numel: host array of n counts.
+// params / grads / exp_avg / exp_avg_sq: HOST arrays of n device pointers (dense), numel: host array of n counts -- positive for
+// float32 tensors, NEGATIVE for float64 ones (parameter, gradient and both moments in double).
 // step: DEVICE float, the number of updates already applied; incremented by 1 after all tensors are updated.
 extern "C" int p2r_adamw_step(int n, const void* const* params, const void* const* grads, void* const* exp_avg,
                               void* const* exp_avg_sq, const long long* numel, float* step, double lr, double beta1,
@@ -100,7 +119,8 @@ extern "C" int p2r_adamw_step(int n, const void* const* params, const void* cons
       c.m[i] = live ? (float*)exp_avg[i0 + i] : nullptr;
       c.v[i] = live ? (float*)exp_avg_sq[i0 + i] : nullptr;
       c.numel[i] = live ? numel[i0 + i] : 0;
-      if (c.numel[i] > mx) mx = c.numel[i];
+      const long long an = c.numel[i] < 0 ? -c.numel[i] : c.numel[i];
+      if (an > mx) mx = an;
     }
     if (mx == 0) continue;
     const long long per_block = (long long)P2R_ADAMW_THREADS * P2R_ADAMW_PER_THREAD;

@@ -6,7 +6,7 @@ torch's own capturable fused AdamW evaluates the bias corrections per element (0
 1.44 M parameters of P2RNet); this one evaluates them once per thread.  State layout and `state_dict()` keys are torch's
 (`step`, `exp_avg`, `exp_avg_sq` per parameter), so checkpoints written by either optimiser load into the other
 (`CheckpointIO`, net_utils/utils.py:57-78).  CUDA dense parameters only -- there is no CPU path; parameters that are not
-float32 take the same update through torch kernels."""
+float32 or float64 are refused."""
 import ctypes
 
 import numpy as np
@@ -42,10 +42,12 @@ class AdamW(torch.optim.Optimizer):
             for p in ps:
                 if not p.is_cuda or p.grad.is_sparse:
                     raise RuntimeError("pose2room_b200.optim.AdamW: CUDA dense parameters only (there is no CPU path)")
-            # float32 contiguous parameters go through the kernel; anything else (P2RNet has ONE float64 parameter,
-            # detection.gmm_heading.mdn.mu) takes the same update with a handful of torch kernels, on the same device counter
-            fast = [p for p in ps if p.dtype == torch.float32 and p.grad.dtype == torch.float32 and p.is_contiguous()]
-            slow = [p for p in ps if not (p.dtype == torch.float32 and p.grad.dtype == torch.float32 and p.is_contiguous())]
+            # float32 and float64 contiguous parameters go through the kernel (P2RNet has ONE float64 parameter,
+            # detection.gmm_heading.mdn.mu); anything else is refused
+            for p in ps:
+                if p.dtype not in (torch.float32, torch.float64) or p.grad.dtype != p.dtype or not p.is_contiguous():
+                    raise RuntimeError("pose2room_b200.optim.AdamW: float32 / float64 contiguous parameters with gradients "
+                                       "of their own dtype only")
             # one device step counter per group, shared by its parameters' state entries (torch keeps one per parameter;
             # after load_state_dict they are separate tensors again: re-share the first one)
             gstep = None
@@ -60,19 +62,6 @@ class AdamW(torch.optim.Optimizer):
             if gstep.dtype != torch.float32:
                 gstep = gstep.float()
             b1, b2 = group["betas"]
-            if slow:        # before the kernel call (which increments the counter at its end)
-                t = gstep.double() + 1.0
-                bc1, bc2_sqrt = 1.0 - b1 ** t, (1.0 - b2 ** t).sqrt()
-                for p in slow:
-                    st = self._init_state(p, gstep)
-                    st["step"] = gstep
-                    g = p.grad.to(p.dtype)
-                    p.mul_(1.0 - group["lr"] * group["weight_decay"])
-                    st["exp_avg"].lerp_(g, 1.0 - b1)
-                    st["exp_avg_sq"].mul_(b2).addcmul_(g, g, value=1.0 - b2)
-                    denom = (st["exp_avg_sq"].sqrt() / bc2_sqrt.to(p.dtype)).add_(group["eps"])
-                    p.sub_((group["lr"] / bc1).to(p.dtype) * (st["exp_avg"] / denom))
-            ps = fast
             grads, ms, vs = [], [], []
             for p in ps:
                 st = self._init_state(p, gstep)
@@ -84,7 +73,7 @@ class AdamW(torch.optim.Optimizer):
             n = len(ps)
             ptrs = lambda ts: np.array([t.data_ptr() for t in ts], dtype=np.uint64)
             a_p, a_g, a_m, a_v = ptrs(ps), ptrs(grads), ptrs(ms), ptrs(vs)
-            numel = np.array([p.numel() for p in ps], dtype=np.int64)
+            numel = np.array([p.numel() if p.dtype == torch.float32 else -p.numel() for p in ps], dtype=np.int64)
             with torch.cuda.device(ps[0].device):
                 _lib.call("p2r_adamw_step", n, a_p.ctypes.data_as(ctypes.c_void_p), a_g.ctypes.data_as(ctypes.c_void_p),
                           a_m.ctypes.data_as(ctypes.c_void_p), a_v.ctypes.data_as(ctypes.c_void_p),
