@@ -370,20 +370,21 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_any_kernel(long long M, int C, int rows_per_block, const T* __restrict__ dy, const T* __restrict__ y,
                   double* __restrict__ s1) {
-  P2R_DYN_SMEM(float, ca_tab);  // [C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x) ca_tab[c] = 0.f;
-  __syncthreads();
+  // thread t owns columns t, t + 256, ...: consecutive threads read consecutive elements of a row (coalesced), the sum
+  // over the block's rows stays in a register, one double atomic per column and block.  (The first version added every
+  // element into a shared table with an atomic and an integer modulo: 41 us for 8.5 MB.)
   const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long n = min((long long)rows_per_block, M - r0) * C;
-  const T* g = dy + r0 * C;
-  const T* yy = y != nullptr ? y + r0 * C : nullptr;
-  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-    float v = ldf<T>(g + e);
-    if (yy != nullptr && !(ldf<T>(yy + e) > 0.f)) v = 0.f;
-    atomicAdd(ca_tab + (int)(e % C), v);
+  const long long r1 = min(M, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (long long r = r0; r < r1; ++r) {
+      float v = ldf<T>(dy + r * C + c);
+      if (y != nullptr && !(ldf<T>(y + r * C + c) > 0.f)) v = 0.f;
+      acc += v;
+    }
+    atomicAdd(s1 + c, (double)acc);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(s1 + c, (double)ca_tab[c]);
 }
 
 // backward column sums: s1 = sum dz, s2 = sum dz*xhat (s2/x/mean/rstd may be NULL -> only s1, e.g. a bias grad)
@@ -394,13 +395,12 @@ extern "C" int p2r_col_bwd_stats(const void* dy, const void* x, const void* y, i
   P2R_CHECK_ARG(M >= 0 && C > 0 && (any_width || (C <= 256 ? 256 % C == 0 : C % 256 == 0)), "p2r_col_bwd_stats");
   P2R_CHECK_ARG(!(relu == 1 && y == nullptr), "p2r_col_bwd_stats (relu = 1 needs y)");
   if (M > 0 && any_width && !(C <= 256 ? 256 % C == 0 : C % 256 == 0)) {
-    const int rpb = (int)max(16LL, min(1024LL, (M + P2R_SM_COUNT * 2 - 1) / (P2R_SM_COUNT * 2)));
+    const int rpb = (int)max(16LL, min(256LL, (M + P2R_SM_COUNT * 4 - 1) / (P2R_SM_COUNT * 4)));
     const int grid = (int)((M + rpb - 1) / rpb);
-    const size_t smem = (size_t)C * sizeof(float);
     if (dtype == 0)
-      colsum_any_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(M, C, rpb, (const float*)dy, relu ? (const float*)y : nullptr, s1);
+      colsum_any_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, rpb, (const float*)dy, relu ? (const float*)y : nullptr, s1);
     else
-      colsum_any_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(M, C, rpb, (const __nv_bfloat16*)dy, relu ? (const __nv_bfloat16*)y : nullptr, s1);
+      colsum_any_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, rpb, (const __nv_bfloat16*)dy, relu ? (const __nv_bfloat16*)y : nullptr, s1);
     P2R_RETURN_LAUNCH("p2r_col_bwd_stats");
   }
   P2R_CHECK_ARG(!(relu == 2 && (x == nullptr || scale == nullptr || shift == nullptr)), "p2r_col_bwd_stats (relu = 2 needs x, scale, shift)");

@@ -48,4 +48,17 @@ for _ in range(2):
               A_e.shape[0], J, 64, 64, d_w.data_ptr(), d_b.data_ptr(), d_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 
+# ---- AdamW over the 131 parameter tensors of P2RNet (shapes from the model itself) ----------------------------------
+from pose2room_b200.config import P2RConfig
+from pose2room_b200.optim import AdamW
+from pose2room_b200.p2rnet import P2RNet
+
+net = P2RNet(P2RConfig(mode="train", joint_num=J, num_frames=T, precision="bf16")).to(dev)
+params = [p for p in net.parameters() if p.requires_grad]
+for p in params:
+    p.grad = torch.randn_like(p)
+opt = AdamW(params, lr=1e-3)
+for _ in range(2):
+    opt.step()
+torch.cuda.synchronize()
 print("new kernels done")
